@@ -1,0 +1,503 @@
+// Dense bf16 GEMM on Blackwell 5th-gen tensor cores (tcgen05 + TMEM + TMA), the compute half of
+// the sharded-op kernel dispatch: the aten.mm.default nodes of the sharded FX graph
+// (Linear fwd / dgrad / wgrad) land here.
+//
+//   C[M,N] (bf16) = A · B, fp32 accumulation in tensor memory.
+//     A: K-major  ([M,K] row-major)  or MN-major (stored [K,M])
+//     B: K-major  ([N,K] row-major, i.e. nn.Linear weight) or MN-major (stored [K,N])
+//
+// Structure (one persistent CTA per SM, 192 threads):
+//   warp 0      : TMA producer   — cp.async.bulk.tensor tiles of A and B into a 4/6-stage smem ring
+//   warp 1      : MMA issuer     — one elected lane issues tcgen05.mma (128 x BN x 16), accumulators
+//                                  live in TMEM, double-buffered so the epilogue of tile i overlaps
+//                                  the main loop of tile i+1; also owns TMEM alloc/dealloc
+//   warps 2..5  : epilogue       — tcgen05.ld TMEM -> registers -> bf16 -> 16-byte global stores
+// Synchronisation is mbarrier-only (full/empty per smem stage, full/empty per TMEM stage).
+//
+// Shared-memory tiles use the canonical 128-byte-swizzle UMMA layouts, written by TMA with
+// CU_TENSOR_MAP_SWIZZLE_128B and described to the tensor core with matching smem descriptors
+// (K-major: SBO = 1024 B; MN-major: one 64-element atom per TMA box, LBO = atom stride).
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include "edb_internal.cuh"
+
+namespace edb {
+
+constexpr int BM = 128;
+constexpr int BK = 64;  // 64 bf16 = 128 bytes = one swizzle atom
+constexpr int UMMA_K = 16;
+constexpr int kGemmThreads = 192;
+constexpr int kSmemABytes = BM * BK * 2;  // 16 KiB
+
+template <int BN> struct TileCfg {
+  static constexpr int kSmemBBytes = BN * BK * 2;
+  static constexpr int kStageBytes = kSmemABytes + kSmemBBytes;
+  static constexpr int kStages = (BN == 256) ? 4 : 6;
+  static constexpr int kTmemCols = 2 * BN;  // two accumulator stages
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+// ---- PTX wrappers ------------------------------------------------------------------------------------
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t addr, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(addr), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Spin on an mbarrier phase.  A watchdog turns a protocol bug into a trap (kernel error) instead
+// of a hung GPU: 4 s is ~1000x the longest legitimate wait of any role in these kernels.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  if (mbar_try_wait(addr, parity)) return;
+  const uint64_t t0 = globaltimer_ns();
+  uint32_t spins = 0;
+  while (!mbar_try_wait(addr, parity)) {
+    if ((++spins & 0xfff) == 0 && globaltimer_ns() - t0 > 4000000000ull) {
+      printf("edb gemm watchdog: block %d thread %d stuck on barrier %u parity %u\n", blockIdx.x,
+             threadIdx.x, addr, parity);
+      asm volatile("trap;");
+    }
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* smem,
+                                            int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, "
+      "%4}], [%2];" ::"r"(smem_u32(smem)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                   smem_u32(dst_smem)),
+               "r"(cols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols)
+               : "memory");
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
+                                         uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+          smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+        "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
+        "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() {
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// ---- descriptors -------------------------------------------------------------------------------------
+
+// Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
+//   [0,14) start address >> 4   [16,30) leading byte offset >> 4   [32,46) stride byte offset >> 4
+//   [46,48) version = 1 (sm_100)   [61,64) layout type: 2 = SWIZZLE_128B
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes,
+                                                   uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3fff);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3fff) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3fff) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+// Instruction descriptor for kind::f16 (cute::UMMA::InstrDescriptor bit layout):
+//   [4,6) D format: 1 = F32   [7,10) A format: 1 = BF16   [10,13) B format: 1 = BF16
+//   [15] A major: 0 = K, 1 = MN   [16] B major   [17,23) N >> 3   [24,29) M >> 4
+__host__ __device__ constexpr uint32_t make_idesc(int m, int n, bool a_mn, bool b_mn) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
+         ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+struct GemmParams {
+  __nv_bfloat16* C;
+  int64_t ldc;
+  int M, N, K;
+  int m_tiles, n_tiles;
+};
+
+// ---- kernel ------------------------------------------------------------------------------------------
+
+template <int BN, bool A_KMAJOR, bool B_KMAJOR>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+    k_gemm_bf16(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                const GemmParams p) {
+  using Cfg = TileCfg<BN>;
+  constexpr int kStages = Cfg::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + kStages * kSmemABytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::kStageBytes);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + kStages;
+  uint64_t* tmem_full = bars + 2 * kStages;
+  uint64_t* tmem_empty = bars + 2 * kStages + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_tiles = p.m_tiles * p.n_tiles;
+  const int k_blocks = (p.K + BK - 1) / BK;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmap_a);
+    prefetch_tmap(&tmap_b);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < kStages; ++s) {
+        mbar_init(&full_bar[s], 1);
+        mbar_init(&empty_bar[s], 1);
+      }
+      for (int s = 0; s < 2; ++s) {
+        mbar_init(&tmem_full[s], 1);
+        mbar_init(&tmem_empty[s], 4);  // one arrive per epilogue warp
+      }
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, Cfg::kTmemCols);
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        const int m_blk = t % p.m_tiles, n_blk = t / p.m_tiles;
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+          uint8_t* sa = smem_a + stage * kSmemABytes;
+          uint8_t* sb = smem_b + stage * Cfg::kSmemBBytes;
+          if (A_KMAJOR) {
+            tma_load_2d(&tmap_a, &full_bar[stage], sa, kb * BK, m_blk * BM);
+          } else {
+            // MN-major: one 64(m) x 64(k) swizzle atom column per box
+#pragma unroll
+            for (int h = 0; h < BM / 64; ++h)
+              tma_load_2d(&tmap_a, &full_bar[stage], sa + h * (64 * BK * 2), m_blk * BM + h * 64,
+                          kb * BK);
+          }
+          if (B_KMAJOR) {
+            tma_load_2d(&tmap_b, &full_bar[stage], sb, kb * BK, n_blk * BN);
+          } else {
+#pragma unroll
+            for (int h = 0; h < BN / 64; ++h)
+              tma_load_2d(&tmap_b, &full_bar[stage], sb + h * (64 * BK * 2), n_blk * BN + h * 64,
+                          kb * BK);
+          }
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    constexpr uint32_t idesc = make_idesc(BM, BN, !A_KMAJOR, !B_KMAJOR);
+    int stage = 0;
+    uint32_t phase = 0;
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      mbar_wait(&tmem_empty[as], aphase ^ 1);
+      tcgen05_fence_after();
+      const uint32_t tmem_d = tmem_base + as * BN;
+      for (int kb = 0; kb < k_blocks; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tcgen05_fence_after();
+        if (lane == 0) {
+          const uint32_t a_addr = smem_u32(smem_a + stage * kSmemABytes);
+          const uint32_t b_addr = smem_u32(smem_b + stage * Cfg::kSmemBBytes);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            uint64_t da, db;
+            if (A_KMAJOR) da = make_smem_desc(a_addr + k * UMMA_K * 2, 0, 1024);
+            else da = make_smem_desc(a_addr + k * UMMA_K * 128, 64 * BK * 2, 1024);
+            if (B_KMAJOR) db = make_smem_desc(b_addr + k * UMMA_K * 2, 0, 1024);
+            else db = make_smem_desc(b_addr + k * UMMA_K * 128, 64 * BK * 2, 1024);
+            umma_f16(tmem_d, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);  // frees the smem stage when these MMAs retire
+          if (kb == k_blocks - 1) umma_commit(&tmem_full[as]);
+        }
+        __syncwarp();
+        if (++stage == kStages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+      if (++as == 2) {
+        as = 0;
+        aphase ^= 1;
+      }
+    }
+  } else {
+    // ===== epilogue warps 2..5 =====
+    const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      const int m_blk = t % p.m_tiles, n_blk = t / p.m_tiles;
+      mbar_wait(&tmem_full[as], aphase);
+      tcgen05_fence_after();
+      const int row = m_blk * BM + quad * 32 + lane;
+      const bool row_ok = row < p.M;
+      __nv_bfloat16* crow = p.C + (int64_t)row * p.ldc + (int64_t)n_blk * BN;
+      const int n_left = p.N - n_blk * BN;  // valid columns in this tile (multiple of 8)
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t v[32];
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BN + c0);
+        tmem_ld_32x32b_x32(taddr, v);
+        tmem_ld_wait();
+        if (row_ok) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            if (c0 + j < n_left) {
+              uint4 o;
+              __nv_bfloat162 h0 = __floats2bfloat162_rn(__uint_as_float(v[j + 0]), __uint_as_float(v[j + 1]));
+              __nv_bfloat162 h1 = __floats2bfloat162_rn(__uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+              __nv_bfloat162 h2 = __floats2bfloat162_rn(__uint_as_float(v[j + 4]), __uint_as_float(v[j + 5]));
+              __nv_bfloat162 h3 = __floats2bfloat162_rn(__uint_as_float(v[j + 6]), __uint_as_float(v[j + 7]));
+              o.x = *reinterpret_cast<uint32_t*>(&h0);
+              o.y = *reinterpret_cast<uint32_t*>(&h1);
+              o.z = *reinterpret_cast<uint32_t*>(&h2);
+              o.w = *reinterpret_cast<uint32_t*>(&h3);
+              *reinterpret_cast<uint4*>(crow + c0 + j) = o;
+            }
+          }
+        }
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[as]);
+      if (++as == 2) {
+        as = 0;
+        aphase ^= 1;
+      }
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+// ---- host side ---------------------------------------------------------------------------------------
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+      q != cudaDriverEntryPointSuccess)
+    return nullptr;
+  fn = reinterpret_cast<EncodeTiledFn>(p);
+  return fn;
+}
+
+// 2-D bf16 tensor map: `inner` contiguous elements, `outer` rows `ld` elements apart.
+static int make_tmap(CUtensorMap* map, const void* base, int64_t inner, int64_t outer, int64_t ld,
+                     int box_inner, int box_outer) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return set_error(EDB_E_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult rc = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides,
+                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (rc != CUDA_SUCCESS)
+    return set_error(EDB_E_CUDA, "cuTensorMapEncodeTiled failed (%d) inner=%lld outer=%lld ld=%lld",
+                     (int)rc, (long long)inner, (long long)outer, (long long)ld);
+  return EDB_OK;
+}
+
+template <int BN, bool AK, bool BK_>
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p,
+                       cudaStream_t st) {
+  using Cfg = TileCfg<BN>;
+  static bool configured = false;
+  auto kern = k_gemm_bf16<BN, AK, BK_>;
+  if (!configured) {
+    EDB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    configured = true;
+  }
+  const int tiles = p.m_tiles * p.n_tiles;
+  const int grid = tiles < rt().sm_count ? tiles : rt().sm_count;
+  kern<<<grid, kGemmThreads, Cfg::kSmemBytes, st>>>(ta, tb, p);
+  count_launch();
+  return cuda_check(cudaGetLastError(), "k_gemm_bf16 launch");
+}
+
+static int pick_bn(int64_t M, int64_t N, int sms) {
+  // fewer, larger tiles unless that leaves SMs idle: compare wave efficiency of BN=256 vs 128
+  auto eff = [&](int bn) {
+    const int64_t tiles = ((M + BM - 1) / BM) * ((N + bn - 1) / bn);
+    const int64_t waves = (tiles + sms - 1) / sms;
+    return (double)tiles / (double)(waves * sms);
+  };
+  if (N <= 128) return 128;
+  const double e256 = eff(256), e128 = eff(128);
+  return (e256 + 0.05 >= e128) ? 256 : 128;
+}
+
+}  // namespace edb
+
+using namespace edb;
+
+extern "C" {
+
+int edb_gemm_bf16(void* C, const void* A, const void* B, int64_t M, int64_t N, int64_t K,
+                  int64_t lda, int64_t ldb, int64_t ldc, int a_kmajor, int b_kmajor,
+                  int accumulate_into_c, void* stream) {
+  if (accumulate_into_c) return set_error(EDB_E_UNSUPPORTED, "edb_gemm_bf16: accumulate_into_c");
+  if (M <= 0 || N <= 0 || K <= 0) return set_error(EDB_E_UNSUPPORTED, "edb_gemm_bf16: empty problem");
+  if (M > 0x7fffffff || N > 0x7fffffff || K > 0x7fffffff)
+    return set_error(EDB_E_UNSUPPORTED, "edb_gemm_bf16: dimension too large");
+  if (((uintptr_t)A | (uintptr_t)B | (uintptr_t)C) & 15)
+    return set_error(EDB_E_UNSUPPORTED, "edb_gemm_bf16: base pointers must be 16-byte aligned");
+  if ((lda | ldb | ldc | N) & 7)
+    return set_error(EDB_E_UNSUPPORTED, "edb_gemm_bf16: lda/ldb/ldc/N must be multiples of 8");
+  if ((a_kmajor && (K & 7)) || (!a_kmajor && (M & 7)))
+    return set_error(EDB_E_UNSUPPORTED, "edb_gemm_bf16: A inner extent must be a multiple of 8");
+  Runtime& r = rt();
+  int sms = r.sm_count;
+  if (!r.inited) {
+    int dev = 0;
+    EDB_CUDA(cudaGetDevice(&dev));
+    EDB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    r.sm_count = sms;
+  }
+  const int bn = pick_bn(M, N, sms);
+  CUtensorMap ta, tb;
+  int rc;
+  if (a_kmajor) rc = make_tmap(&ta, A, K, M, lda, BK, BM);
+  else rc = make_tmap(&ta, A, M, K, lda, 64, BK);
+  if (rc) return rc;
+  if (b_kmajor) rc = make_tmap(&tb, B, K, N, ldb, BK, bn);
+  else rc = make_tmap(&tb, B, N, K, ldb, 64, BK);
+  if (rc) return rc;
+  GemmParams p;
+  p.C = static_cast<__nv_bfloat16*>(C);
+  p.ldc = ldc;
+  p.M = (int)M;
+  p.N = (int)N;
+  p.K = (int)K;
+  p.m_tiles = (int)((M + BM - 1) / BM);
+  p.n_tiles = (int)((N + bn - 1) / bn);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int key = (bn == 256 ? 4 : 0) | (a_kmajor ? 2 : 0) | (b_kmajor ? 1 : 0);
+  switch (key) {
+    case 7: return launch_gemm<256, true, true>(ta, tb, p, st);
+    case 6: return launch_gemm<256, true, false>(ta, tb, p, st);
+    case 5: return launch_gemm<256, false, true>(ta, tb, p, st);
+    case 4: return launch_gemm<256, false, false>(ta, tb, p, st);
+    case 3: return launch_gemm<128, true, true>(ta, tb, p, st);
+    case 2: return launch_gemm<128, true, false>(ta, tb, p, st);
+    case 1: return launch_gemm<128, false, true>(ta, tb, p, st);
+    default: return launch_gemm<128, false, false>(ta, tb, p, st);
+  }
+}
+
+int edb_ag_gemm_bf16(int gid, void* C, const void* A, uint64_t b_shard_off, uint64_t b_full_off,
+                     int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldc, void* stream) {
+  (void)gid; (void)C; (void)A; (void)b_shard_off; (void)b_full_off; (void)M; (void)N; (void)K;
+  (void)lda; (void)ldc; (void)stream;
+  return set_error(EDB_E_UNSUPPORTED, "edb_ag_gemm_bf16: not built yet");
+}
+
+int edb_gemm_rs_bf16(int gid, void* dst, uint64_t c_stage_off, const void* A, const void* B,
+                     int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb, int a_kmajor,
+                     int b_kmajor, float post_scale, int out_dtype, void* stream) {
+  (void)gid; (void)dst; (void)c_stage_off; (void)A; (void)B; (void)M; (void)N; (void)K; (void)lda;
+  (void)ldb; (void)a_kmajor; (void)b_kmajor; (void)post_scale; (void)out_dtype; (void)stream;
+  return set_error(EDB_E_UNSUPPORTED, "edb_gemm_rs_bf16: not built yet");
+}
+
+}  // extern "C"

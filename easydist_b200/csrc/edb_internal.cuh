@@ -1,0 +1,198 @@
+// Internal declarations shared by the translation units of libedb.so.
+// Not part of the C-ABI (that is include/edb.h).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "edb.h"
+
+namespace edb {
+
+constexpr int kMaxWorld = 64;
+constexpr int kMaxGroup = EDB_MAX_GROUP;
+constexpr int kMaxGroups = EDB_MAX_GROUPS;
+
+// ---- flag area at the start of every rank's slab --------------------------------------------
+// One 1 KiB block (128 x u64) per group slot.  All counters are monotonically increasing
+// sequence numbers ("epochs"), never reset, so the same kernel parameters stay valid across
+// CUDA-graph replays.
+constexpr size_t kFlagBlockBytes = 1024;
+constexpr size_t kFlagAreaBytes = 64 * 1024;           // kMaxGroups blocks + spare
+constexpr size_t kScratchBytes = 1 << 20;              // per-rank scratch (tile counters etc.)
+constexpr size_t kUserOffset = kFlagAreaBytes + kScratchBytes;
+
+enum FlagWord : int {
+  F_READY = 0,    // [0..7]   READY[p]  : peer p staged its data for op q          (written by p)
+  F_DONE = 8,     // [8..15]  DONE[p]   : peer p finished reading my data of op q  (written by p)
+  F_READY2 = 16,  // [16..23] READY2[p] : second phase of two-shot ops             (written by p)
+  F_SEQ = 24,     // last op number completed locally                              (written by me)
+  F_CNT_A = 25,   // last-block counters
+  F_CNT_B = 26,
+  F_CNT_C = 27,
+  F_ERR = 28,     // != 0: a spin wait timed out (value = op number)
+  F_CHUNK = 32,   // [32..95] per-chunk flags for fused kernels (written by peers / local CTAs)
+};
+
+struct Group {
+  int n = 0, me = -1, slot = -1;
+  int ranks[kMaxGroup];
+};
+
+struct Runtime {
+  bool inited = false;
+  int rank = 0, world = 1, device = 0, sm_count = 148;
+  char* heap = nullptr;
+  size_t heap_bytes = 0;
+  size_t bump = kUserOffset;
+  char* peer_heap[kMaxWorld] = {};
+  bool peer_is_ipc[kMaxWorld] = {};
+  Group groups[kMaxGroups];
+  int ngroups = 0;
+  // options
+  int64_t allreduce_oneshot_bytes = 512 * 1024;
+  int64_t copy_ctas_per_sm = 4;
+  int64_t comm_ctas = 16;
+  int64_t spin_timeout_ms = 10000;
+};
+
+Runtime& rt();
+int set_error(int code, const char* fmt, ...);
+int cuda_check(cudaError_t e, const char* what);
+void count_launch();
+
+#define EDB_CUDA(call)                                  \
+  do {                                                  \
+    int _rc = ::edb::cuda_check((call), #call);         \
+    if (_rc) return _rc;                                \
+  } while (0)
+
+#define EDB_REQUIRE(cond, ...)                                        \
+  do {                                                                \
+    if (!(cond)) return ::edb::set_error(EDB_E_INVALID, __VA_ARGS__); \
+  } while (0)
+
+inline uint64_t* flag_block(char* heap, int slot) {
+  return reinterpret_cast<uint64_t*>(heap + (size_t)slot * kFlagBlockBytes);
+}
+
+// ---- kernel-side descriptors ------------------------------------------------------------------
+
+struct Box {
+  const char* src;
+  char* dst;
+  int64_t inner;    // contiguous bytes per row
+  int64_t ext[4];   // outer extents, ext[0] slowest; unused dims = 1
+  int64_t sstr[4];  // byte strides
+  int64_t dstr[4];
+  int32_t vec;      // bytes per access: 16, 8, 4, 2 or 1
+  int32_t peer;     // group index whose READY flag gates this box; -1 = none (local)
+};
+
+struct FlagCtx {
+  uint64_t* local;            // my flag block of this group
+  uint64_t* peer[kMaxGroup];  // every member's flag block (peer[me] == local)
+  int n, me;
+  int n_war;                  // number of local flag blocks to check for write-after-read
+  uint64_t* war_block[4];
+  int war_n[4];
+  int war_me[4];
+  uint64_t timeout_ns;
+};
+
+constexpr int kMaxBoxes = 18;
+
+struct GatherDesc {
+  FlagCtx f;
+  int n_in;     // boxes [0, n_in) are the local copy-in phase
+  int n_boxes;  // boxes [n_in, n_boxes) are pulled after the READY flags
+  Box box[kMaxBoxes];
+};
+
+struct ReduceDesc {
+  FlagCtx f;
+  int has_in;  // copy `in` first
+  Box in;
+  // reduction geometry: n_src sources with identical layout
+  const char* src[kMaxGroup];
+  char* dst;
+  int64_t inner;  // bytes per row (source dtype)
+  int64_t ext[4];
+  int64_t sstr[4];
+  int64_t dstr[4];  // destination byte strides (destination dtype)
+  int n_src;
+  int dtype, out_dtype, redop;
+  float scale;
+  // two-shot all-reduce: after reducing my part into dst (which lives in my stage2), pull the
+  // other parts from the peers' stage2 into final_dst
+  int two_shot;
+  int n_pull;
+  Box pull[kMaxGroup];
+};
+
+// host helpers (edb_reshard.cu)
+int make_box(Box* out, const void* src, const int64_t* src_strides, void* dst,
+             const int64_t* dst_strides, const int64_t* extents, int ndim, int elem_size, int peer);
+int fill_flagctx(FlagCtx* f, int gid);
+int grid_for_bytes(size_t bytes, int threads);
+
+inline size_t dtype_size(int dt) {
+  switch (dt) {
+    case EDB_F32: return 4;
+    case EDB_BF16: return 2;
+    case EDB_F16: return 2;
+    case EDB_F64: return 8;
+    case EDB_I32: return 4;
+    case EDB_I64: return 8;
+  }
+  return 0;
+}
+
+// ---- device helpers ---------------------------------------------------------------------------
+
+__device__ __forceinline__ uint64_t ld_acquire_sys(const uint64_t* p) {
+  uint64_t v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(uint64_t* p, uint64_t v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ uint64_t ld_relaxed_gpu(const uint64_t* p) {
+  uint64_t v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint64_t ld_acquire_gpu(const uint64_t* p) {
+  uint64_t v;
+  asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_gpu(uint64_t* p, uint64_t v) {
+  asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ uint64_t globaltimer_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+// Spin until *flag >= target (system scope acquire).  On timeout records the op in F_ERR and
+// returns false; callers carry on so that a lost peer never wedges the GPU.
+__device__ __forceinline__ bool spin_wait_sys(const uint64_t* flag, uint64_t target,
+                                              uint64_t timeout_ns, uint64_t* err_word) {
+  if (ld_acquire_sys(flag) >= target) return true;
+  uint64_t t0 = globaltimer_ns();
+  while (ld_acquire_sys(flag) < target) {
+    __nanosleep(64);
+    if (globaltimer_ns() - t0 > timeout_ns) {
+      if (err_word) atomicMax((unsigned long long*)err_word, (unsigned long long)target);
+      return false;
+    }
+  }
+  return true;
+}
+
+}  // namespace edb

@@ -1,0 +1,336 @@
+"""Host-side mirror of the reference's reshard operator interface, backed by libedb.so.
+
+Same names, argument meaning and error behaviour as the ten FX `call_function` targets of
+easydist/torch/passes/sharding.py:94-168 (`all_reduce_start/end`, `all_gather_start/end`,
+`reduce_scatter_start/end`, `all_to_all_start/end`, `scatter_wrapper`, `copy_wrapper`) plus the
+registries other passes key on (`COMM_FUNCS`, `COMM_SYNC_FUNCS`, `CUSTOM_FUNCS`,
+sharding.py:166-168), so they can be bound in place of the reference's callables.
+
+Differences that are the point of this backend:
+  * every `*_start` is ONE CUDA kernel over peer memory (no NCCL, no funcol, no wait_tensor);
+    the matching `*_end` is the identity because the work is stream-ordered;
+  * non-dim-0 gathers/scatters need no chunk+cat copy: the dim is folded into the box indexing;
+  * `all_to_all` moves 1/n of the bytes (the reference all-gathers and slices, sharding.py:155-163);
+  * an optional keyword `_buf=(offset, nbytes[, offset2])` names static symmetric buffers chosen at
+    lowering time; without it a staging ring is used and results are copied to torch-owned memory.
+There is no CPU path: tensors must live on the runtime's CUDA device (FakeTensors are accepted so
+that FX meta propagation works, mirroring how the reference's passes call these ops on fakes).
+"""
+from ctypes import byref, c_int64
+from typing import List
+
+import torch
+from torch._subclasses.fake_tensor import FakeTensor
+
+from . import _lib
+from ._lib import DTYPE_CODES, REDOP_CODES, check, i64_array
+from .runtime import SymmBuffer, get_runtime
+
+_TORCH_DTYPE_CODE = {
+    torch.float32: DTYPE_CODES["float32"],
+    torch.bfloat16: DTYPE_CODES["bfloat16"],
+    torch.float16: DTYPE_CODES["float16"],
+    torch.float64: DTYPE_CODES["float64"],
+    torch.int32: DTYPE_CODES["int32"],
+    torch.int64: DTYPE_CODES["int64"],
+}
+
+
+def _is_fake(t):
+    return isinstance(t, FakeTensor) or (isinstance(t, torch.Tensor) and t.is_meta)
+
+
+def _require_cuda(t, what):
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{what}: expected a tensor, got {type(t)}")
+    if not t.is_cuda:
+        raise _lib.EdbError(_lib.EDB_E_INVALID,
+                            f"{what}: tensor is on {t.device}; easydist_b200 has no CPU path")
+
+
+def _dtype_code(t, what):
+    code = _TORCH_DTYPE_CODE.get(t.dtype)
+    if code is None:
+        raise _lib.EdbError(_lib.EDB_E_UNSUPPORTED, f"{what}: dtype {t.dtype} cannot be reduced")
+    return code
+
+
+def _redop(name, what):
+    try:
+        return REDOP_CODES[name]
+    except KeyError:
+        raise _lib.EdbError(_lib.EDB_E_INVALID, f"{what}: unknown reduceOp {name!r}") from None
+
+
+def _norm_dim(dim, ndim):
+    return dim + ndim if dim < 0 else dim
+
+
+def _group(group):
+    rt = get_runtime()
+    gid = rt.group(group)
+    return rt, gid, rt.group_size(gid), rt.group_index(gid)
+
+
+def _buffers(rt, _buf, sizes):
+    """Resolve static (`_buf`) or ring staging buffers for the byte sizes in `sizes`."""
+    if _buf is not None:
+        offs = [_buf[0]] + list(_buf[2:])
+        return [SymmBuffer(rt, o, s) for o, s in zip(offs, sizes)], True
+    return [rt.ring_alloc(s) for s in sizes], False
+
+
+# ---- all_reduce -------------------------------------------------------------------------------------
+
+
+def all_reduce_start(self: torch.Tensor, reduceOp: str, group: List[int], tag: str = "", *,
+                     _buf=None):
+    """P(op) -> R. Reference: sharding.py:94-98 (c10d_functional.all_reduce)."""
+    if _is_fake(self):
+        return torch.empty_like(self, memory_format=torch.contiguous_format)
+    _require_cuda(self, "all_reduce_start")
+    rt, gid, n, _ = _group(group)
+    x = self.contiguous()
+    out = torch.empty_like(x)
+    nbytes = x.numel() * x.element_size()
+    if nbytes == 0:
+        return out
+    two_shot = n > 1 and nbytes > rt.get_option("allreduce_oneshot_bytes")
+    sizes = [nbytes, nbytes] if two_shot else [nbytes]
+    if n > 1:
+        bufs, _ = _buffers(rt, _buf, sizes)
+        s1 = bufs[0].offset
+        s2 = bufs[1].offset if two_shot else 0
+    else:
+        s1 = s2 = 0
+    check(rt.lib.edb_all_reduce(gid, out.data_ptr(), s1, s2, x.data_ptr(), x.numel(),
+                                _dtype_code(x, "all_reduce_start"),
+                                _redop(reduceOp, "all_reduce_start"), rt.stream()))
+    return out
+
+
+def all_reduce_end(self: torch.Tensor, reduceOp: str, group: List[int], tag: str = ""):
+    """Reference: sharding.py:101-102 (wait_tensor). Stream-ordered here: identity."""
+    return self
+
+
+# ---- all_gather --------------------------------------------------------------------------------------
+
+
+def all_gather_start(self: torch.Tensor, gather_dim: int, group: List[int], tag: str = "", *,
+                     _buf=None):
+    """S(gather_dim) -> R. Reference: sharding.py:105-111 gathers along dim 0 and leaves the
+    chunk+cat to all_gather_end (:114-119); here the result is already laid out along
+    `gather_dim`."""
+    n_hint = len(group)
+    ndim = self.dim()
+    dim = _norm_dim(gather_dim, ndim)
+    out_shape = list(self.shape)
+    out_shape[dim] = out_shape[dim] * n_hint
+    if _is_fake(self):
+        return self.new_empty(out_shape)
+    _require_cuda(self, "all_gather_start")
+    rt, gid, n, _ = _group(group)
+    x = self.contiguous()
+    nbytes = x.numel() * x.element_size() * n
+    if nbytes == 0:
+        return x.new_empty(out_shape)
+    (buf,), static = _buffers(rt, _buf, [nbytes])
+    check(rt.lib.edb_all_gather(gid, buf.offset, x.data_ptr(), i64_array(x.shape), ndim, dim,
+                                x.element_size(), rt.stream()))
+    out = buf.tensor(x.dtype, out_shape)
+    return out if static else out.clone()
+
+
+def all_gather_end(self: torch.Tensor, gather_dim: int, group: List[int], tag: str = ""):
+    """Reference: sharding.py:114-119. Identity: all_gather_start already produced the layout."""
+    return self
+
+
+# ---- local ops ---------------------------------------------------------------------------------------
+
+
+def scatter_wrapper(tensor, num_chunks, dim, indice):
+    """R -> S(dim), local. Reference: sharding.py:122-123 `aten.chunk(t, n, dim)[i].contiguous()`
+    (torch.chunk = ceil-div blocks; an index past the last chunk raises IndexError there too)."""
+    ndim = tensor.dim()
+    d = _norm_dim(dim, ndim)
+    size = tensor.shape[d]
+    block = -(-size // num_chunks) if size > 0 else 0
+    n_actual = -(-size // block) if block > 0 else 1
+    if indice >= n_actual or indice < 0:
+        raise IndexError("tuple index out of range")
+    lo = min(size, block * indice)
+    hi = min(size, block * (indice + 1))
+    out_shape = list(tensor.shape)
+    out_shape[d] = hi - lo
+    if _is_fake(tensor):
+        return tensor.new_empty(out_shape)
+    _require_cuda(tensor, "scatter_wrapper")
+    rt = get_runtime()
+    x = tensor.contiguous()
+    out = x.new_empty(out_shape)
+    if out.numel():
+        ext = c_int64()
+        check(rt.lib.edb_scatter(out.data_ptr(), x.data_ptr(), i64_array(x.shape), ndim, d,
+                                 int(num_chunks), int(indice), x.element_size(), byref(ext),
+                                 rt.stream()))
+    return out
+
+
+def copy_wrapper(self, other):
+    """State write-back. Reference: sharding.py:126-127 `aten.copy_(self, other)`; returns self."""
+    if _is_fake(self) or _is_fake(other):
+        return self
+    _require_cuda(self, "copy_wrapper")
+    if (other.is_cuda and self.shape == other.shape and self.dtype == other.dtype
+            and self.is_contiguous() and other.is_contiguous()):
+        if self.numel() and self.data_ptr() != other.data_ptr():
+            rt = get_runtime()
+            check(rt.lib.edb_copy(self.data_ptr(), other.data_ptr(),
+                                  self.numel() * self.element_size(), rt.stream()))
+        return self
+    return torch.ops.aten.copy_.default(self, other)  # broadcasting / dtype-converting copies
+
+
+# ---- reduce_scatter ----------------------------------------------------------------------------------
+
+
+def reduce_scatter_start(self: torch.Tensor, reduceOp: str, scatter_dim: int, group: List[int],
+                         tag: str = "", *, _buf=None, _scale: float = 1.0, _out_dtype=None):
+    """P(op) -> S(scatter_dim). Reference: sharding.py:130-144 (pre-permute copy for dim != 0 and
+    reduce_scatter_tensor). `_scale`/`_out_dtype` fuse the gradient scale / cast into the kernel."""
+    n = len(group)
+    ndim = self.dim()
+    dim = _norm_dim(scatter_dim, ndim)
+    assert self.size(dim) % n == 0, (
+        f"input dimension 0 ({self.size(0)} must be a multiple of group_size {n}")
+    out_shape = list(self.shape)
+    out_shape[dim] //= n
+    out_dtype = _out_dtype or self.dtype
+    if _is_fake(self):
+        return self.new_empty(out_shape, dtype=out_dtype)
+    _require_cuda(self, "reduce_scatter_start")
+    rt, gid, n, _ = _group(group)
+    x = self.contiguous()
+    out = x.new_empty(out_shape, dtype=out_dtype)
+    nbytes = x.numel() * x.element_size()
+    if nbytes == 0:
+        return out
+    stage = 0
+    if n > 1:
+        (buf,), _ = _buffers(rt, _buf, [nbytes])
+        stage = buf.offset
+    check(rt.lib.edb_reduce_scatter(gid, out.data_ptr(), stage, x.data_ptr(), i64_array(x.shape),
+                                    ndim, dim, _dtype_code(x, "reduce_scatter_start"),
+                                    _redop(reduceOp, "reduce_scatter_start"), float(_scale),
+                                    _TORCH_DTYPE_CODE[out_dtype], rt.stream()))
+    return out
+
+
+def reduce_scatter_end(self: torch.Tensor, reduceOp: str, scatter_dim: int, group: List[int],
+                       tag: str = ""):
+    """Reference: sharding.py:147-152 (wait_tensor). Identity."""
+    return self
+
+
+# ---- all_to_all --------------------------------------------------------------------------------------
+
+
+def all_to_all_start(tensor, gather_dim, scatter_dim, num_chunks, indice, ranks, tag: str = "", *,
+                     _buf=None):
+    """S(gather_dim) -> S(scatter_dim). Reference: sharding.py:155-163 (all-gather + local chunk,
+    n x over-communication); here a true all-to-all: each rank pulls only its slice."""
+    n = len(ranks)
+    ndim = tensor.dim()
+    g, s = _norm_dim(gather_dim, ndim), _norm_dim(scatter_dim, ndim)
+    out_shape = list(tensor.shape)
+    out_shape[g] *= n
+    if out_shape[s] % n != 0:
+        raise _lib.EdbError(_lib.EDB_E_INVALID,
+                            f"all_to_all: dim {s} of size {out_shape[s]} not divisible by {n}")
+    out_shape[s] //= n
+    if _is_fake(tensor):
+        return tensor.new_empty(out_shape)
+    _require_cuda(tensor, "all_to_all_start")
+    rt, gid, n, me = _group(ranks)
+    assert me == indice, f"all_to_all: indice {indice} is not this rank's coordinate {me}"
+    x = tensor.contiguous()
+    out = x.new_empty(out_shape)
+    nbytes = x.numel() * x.element_size()
+    if nbytes == 0:
+        return out
+    stage = 0
+    if n > 1:
+        (buf,), _ = _buffers(rt, _buf, [nbytes])
+        stage = buf.offset
+    check(rt.lib.edb_all_to_all(gid, out.data_ptr(), stage, x.data_ptr(), i64_array(x.shape), ndim,
+                                g, s, x.element_size(), rt.stream()))
+    return out
+
+
+def all_to_all_end(tensor, gather_dim, scatter_dim, num_chunks, indice, ranks, tag: str = ""):
+    """Reference: sharding.py:160-163. Identity: all_to_all_start already sliced."""
+    return tensor
+
+
+# ---- extras beyond the ten callables -----------------------------------------------------------------
+
+
+def halo_exchange(tensor, dim, halo, group, *, _buf=None):
+    """S(dim) with halo: concat(prev[-halo:], x, next[:halo]) along dim — the lowering of
+    metashard/halo.py:33-55 halo_padding that the reference never emits."""
+    ndim = tensor.dim()
+    d = _norm_dim(dim, ndim)
+    if _is_fake(tensor):
+        raise NotImplementedError("halo_exchange on fake tensors needs the rank coordinate")
+    _require_cuda(tensor, "halo_exchange")
+    rt, gid, n, me = _group(group)
+    if halo > tensor.shape[d]:
+        raise RuntimeError("Cannot halo padding for this sharded_tensor")  # halo.py:47-48
+    x = tensor.contiguous()
+    out_shape = list(x.shape)
+    out_shape[d] += (halo if me > 0 else 0) + (halo if me < n - 1 else 0)
+    out = x.new_empty(out_shape)
+    nbytes = x.numel() * x.element_size()
+    if nbytes == 0:
+        return out
+    stage = 0
+    if n > 1:
+        (buf,), _ = _buffers(rt, _buf, [nbytes])
+        stage = buf.offset
+    check(rt.lib.edb_halo_exchange(gid, out.data_ptr(), stage, x.data_ptr(), i64_array(x.shape),
+                                   ndim, d, int(halo), x.element_size(), rt.stream()))
+    return out
+
+
+def box_exchange(tensor, dst_shape, boxes, peer_src_shapes, group, *, _buf=None):
+    """Partition P2P redistribution (reference: do_p2p_comm_wrapper, sharding.py:595-612).
+
+    `boxes`: list of (member_index, src_start, dst_start, extents) for THIS rank's destination;
+    `peer_src_shapes`: source-partition shape of every group member."""
+    _require_cuda(tensor, "box_exchange")
+    rt, gid, n, me = _group(group)
+    x = tensor.contiguous()
+    ndim = x.dim()
+    out = x.new_empty([int(s) for s in dst_shape])
+    if not boxes and n == 1:
+        return out
+    nbytes = x.numel() * x.element_size()
+    stage = 0
+    if n > 1:
+        (buf,), _ = _buffers(rt, _buf, [max(16, nbytes)])
+        stage = buf.offset
+    peers = _lib.int_array([b[0] for b in boxes])
+    flat = lambda k: i64_array([v for b in boxes for v in b[k]])
+    shapes = i64_array([v for s in peer_src_shapes for v in s])
+    check(rt.lib.edb_box_exchange(gid, out.data_ptr(), i64_array(out.shape), stage,
+                                  x.data_ptr() if x.numel() else None, i64_array(x.shape), ndim,
+                                  x.element_size(), len(boxes), peers, flat(1), flat(2), flat(3),
+                                  shapes, rt.stream()))
+    return out
+
+
+COMM_FUNCS = [all_reduce_start, all_gather_start, reduce_scatter_start, all_to_all_start]
+COMM_SYNC_FUNCS = [all_reduce_end, all_gather_end, reduce_scatter_end, all_to_all_end]
+CUSTOM_FUNCS = COMM_FUNCS + COMM_SYNC_FUNCS + [scatter_wrapper, copy_wrapper]

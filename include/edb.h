@@ -1,0 +1,202 @@
+/*
+ * edb.h — C-ABI of the easydist-b200 runtime (libedb.so).
+ *
+ * This is the drop-in boundary for the reshard / redistribute hot path of
+ * alibaba/easydist's PyTorch backend.  Every entry point replaces one of the ten
+ * Python callables the reference inserts into the sharded FX graph
+ * (easydist/torch/passes/sharding.py:94-168) or the NCCL/funcol call underneath it.
+ * The reference has no FFI for this path (it is pure Python over
+ * torch.ops.c10d_functional.*); the binding a maintainer would add is the ctypes
+ * shim shown in INTEGRATION.md (and implemented in easydist_b200/_lib.py).
+ *
+ * Conventions
+ *   - one process per GPU; the library holds one runtime per process
+ *   - every function returns 0 on success, non-zero on error; the message of the
+ *     last error of the calling thread is returned by edb_last_error()
+ *   - plain pointers and sizes only; `stream` is a cudaStream_t passed as void*
+ *     (NULL = legacy default stream); all work is stream-ordered and CUDA-graph
+ *     capturable: no host synchronisation, no allocation, static peer pointers
+ *   - "symmetric heap": one cudaMalloc'd slab per rank, the same size on every
+ *     rank, mapped into every peer with CUDA IPC.  A symmetric buffer is named by
+ *     its byte offset in the slab; the same offset names the matching buffer on
+ *     every rank of a group
+ *   - shapes are int64 row-major (contiguous) extents; `elem_size` in bytes
+ *   - `gid` is a group handle from edb_group_create (ranks of one mesh dim, in
+ *     mesh-coordinate order, exactly the `group` list the reference passes)
+ */
+#ifndef EDB_H_
+#define EDB_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EDB_VERSION 100          /* 0.1.0 */
+#define EDB_MAX_GROUP 8          /* ranks per group (one NVSwitch domain) */
+#define EDB_MAX_GROUPS 16        /* groups per process */
+#define EDB_IPC_HANDLE_BYTES 64  /* sizeof(cudaIpcMemHandle_t) */
+
+/* dtype codes (reductions need the arithmetic type; pure data movement only needs elem_size) */
+enum edb_dtype { EDB_F32 = 0, EDB_BF16 = 1, EDB_F16 = 2, EDB_F64 = 3, EDB_I32 = 4, EDB_I64 = 5 };
+/* reduce ops: the reference's reduce_map, sharding.py:68-73 */
+enum edb_redop { EDB_SUM = 0, EDB_MAX = 1, EDB_MIN = 2, EDB_AVG = 3 };
+
+/* ---- runtime ---------------------------------------------------------------------------- */
+
+int edb_version(void);
+/* message of the last failing call on this thread ("" if none) */
+const char* edb_last_error(void);
+
+/* Bind the process to `device`, allocate the symmetric heap (`heap_bytes`, rounded up to 2 MiB)
+ * and zero its flag area.  Replaces: the process-group bootstrap the user does with
+ * init_process_group("nccl") + easydist/torch/device_mesh.py:129-150 set_device_mesh. */
+int edb_init(int rank, int world, int device, size_t heap_bytes);
+int edb_finalize(void);
+int edb_is_initialized(void);
+/* base address / size of the local heap; `user_offset` = first byte usable by edb_symm_alloc */
+int edb_heap_info(void** base, size_t* bytes, size_t* user_offset);
+
+/* CUDA-IPC bootstrap: export my slab handle (64 bytes), attach every peer's.  The exchange of
+ * the 64-byte blobs is done by the host language over whatever it has (torch.distributed
+ * all_gather_object here; same role as ProcessGroupNCCL's ncclUniqueId exchange over the c10d
+ * store).  Mechanism also used by the reference in tensorfield/csrc/allocator_interface.cpp:106-110. */
+int edb_ipc_export(void* handle_out);
+int edb_ipc_attach(int peer_rank, const void* handle);
+/* testing aid for single-process multi-"rank" loopback: peer slab = pointer in this process */
+int edb_attach_local(int peer_rank, void* base);
+
+/* Create the group of `n` global `ranks` (mesh-dim order).  `slot` selects the group's flag block
+ * in the slab and must be the same number on every member (the mesh-dim index, or any agreed id
+ * < EDB_MAX_GROUPS).  Replaces funcol's _expand_group(group, tag) (sharding.py:95). */
+int edb_group_create(const int* ranks, int n, int slot, int* gid_out);
+int edb_group_info(int gid, int* n_out, int* my_index_out);
+
+/* Deterministic bump allocator over the symmetric heap (same call sequence on every rank =>
+ * same offsets).  edb_symm_reset(mark) rewinds to a previous edb_symm_mark(). */
+int edb_symm_alloc(size_t bytes, size_t align, uint64_t* offset_out);
+int edb_symm_mark(uint64_t* mark_out);
+int edb_symm_reset(uint64_t mark);
+
+/* ---- local reshard ops (no peer traffic) ------------------------------------------------- */
+
+/* scatter_wrapper (sharding.py:122-123): dst = contiguous(chunk(src, num_chunks, dim)[index]).
+ * torch.chunk semantics: block = ceil(shape[dim]/num_chunks); trailing chunks may be short/empty;
+ * `dst_extent_out` (may be NULL) receives the dst extent along `dim`. */
+int edb_scatter(void* dst, const void* src, const int64_t* shape, int ndim, int dim,
+                int num_chunks, int index, int elem_size, int64_t* dst_extent_out, void* stream);
+
+/* copy_wrapper (sharding.py:126-127): dst[0:bytes] = src[0:bytes] (both contiguous, same dtype). */
+int edb_copy(void* dst, const void* src, size_t bytes, void* stream);
+
+/* Generic strided N-D box copy (local): dst and src are base pointers, strides in BYTES.
+ * Used for Partition boxes (sharding.py:336-474) that stay on the rank. */
+int edb_box_copy_local(void* dst, const int64_t* dst_strides, const void* src,
+                       const int64_t* src_strides, const int64_t* extents, int ndim, int elem_size,
+                       void* stream);
+
+/* ---- collectives over peer memory --------------------------------------------------------- */
+
+/* all_gather_start/end (sharding.py:105-119): out = concat over group ranks of `src` along `dim`.
+ * `src`: this rank's shard, contiguous, shape `local_shape`.  The result is written to the
+ * symmetric buffer at `dst_off` (shape: local_shape with [dim] multiplied by n); each rank copies
+ * its shard into its own slot and pulls the other slots from the peers' buffers. */
+int edb_all_gather(int gid, uint64_t dst_off, const void* src, const int64_t* local_shape, int ndim,
+                   int dim, int elem_size, void* stream);
+
+/* reduce_scatter_start/end (sharding.py:130-152): dst = reduce_op over ranks of `src`, chunk
+ * `my_index` along `dim` (shape[dim] % n must be 0, as the reference asserts).  `src` (full-shape
+ * partial value) is first staged at symmetric offset `stage_off` (pass src == NULL when the
+ * producer already wrote it there); every rank then pulls its chunk from every peer's stage and
+ * reduces in rank order 0..n-1 with fp32 accumulation (f64 for f64, exact for ints).
+ * out = reduce * post_scale, cast to `out_dtype` (EDB_AVG multiplies by 1/n after the sum). */
+int edb_reduce_scatter(int gid, void* dst, uint64_t stage_off, const void* src,
+                       const int64_t* shape, int ndim, int dim, int dtype, int redop,
+                       float post_scale, int out_dtype, void* stream);
+
+/* all_reduce_start/end (sharding.py:94-102).  One-shot (every rank reduces every peer's stage)
+ * up to `edb_set_option("allreduce_oneshot_bytes")`, two-shot (reduce-scatter into `stage2_off`,
+ * then all-gather) above.  `dst` may be any device pointer (contiguous, numel elements). */
+int edb_all_reduce(int gid, void* dst, uint64_t stage_off, uint64_t stage2_off, const void* src,
+                   int64_t numel, int dtype, int redop, void* stream);
+
+/* all_to_all_start/end (sharding.py:155-163): S(gather_dim) -> S(scatter_dim).
+ * dst = chunk(all_gather(src, gather_dim), n, scatter_dim)[my_index], moving only 1/n of what the
+ * reference's all-gather implementation moves.  `src` is staged at `stage_off` (src==NULL: already
+ * there); dst is a plain device pointer (contiguous result). */
+int edb_all_to_all(int gid, void* dst, uint64_t stage_off, const void* src,
+                   const int64_t* local_shape, int ndim, int gather_dim, int scatter_dim,
+                   int elem_size, void* stream);
+
+/* Partition P2P redistribution (do_p2p_comm_wrapper, sharding.py:595-612): after `src` (this
+ * rank's source partition, contiguous, `src_shape`) is staged at `stage_off`, copy `nbox` boxes
+ * into `dst` (contiguous, `dst_shape`).  Box b comes from group member peer[b] and is given in the
+ * coordinates of that member's source partition (src_start), of my destination partition
+ * (dst_start) and its extents; 3*ndim int64 per box, all members must pass the same ndim. */
+int edb_box_exchange(int gid, void* dst, const int64_t* dst_shape, uint64_t stage_off,
+                     const void* src, const int64_t* src_shape, int ndim, int elem_size, int nbox,
+                     const int* peer, const int64_t* src_start, const int64_t* dst_start,
+                     const int64_t* extents, const int64_t* peer_src_shapes, void* stream);
+
+/* Halo exchange for S(dim) with halo width w (metashard/halo.py:33-55 halo_padding): dst =
+ * concat(prev_rank.src[-w:], src, next_rank.src[:w]) along dim (edges only have one neighbour).
+ * The reference discovers halo shardings but never lowers them; semantics follow halo_padding. */
+int edb_halo_exchange(int gid, void* dst, uint64_t stage_off, const void* src,
+                      const int64_t* local_shape, int ndim, int dim, int halo, int elem_size,
+                      void* stream);
+
+/* Producer-side guard: make the stream wait until every peer has finished reading this rank's
+ * symmetric buffers from earlier collectives (write-after-read), then — when `signal` != 0 —
+ * publish "my symmetric data for the next op is ready" without moving data.  Used by fused
+ * producers (GEMM epilogues, optimizer updates) that write symmetric memory themselves. */
+int edb_symm_guard(int gid, void* stream);
+
+/* ---- dense compute on the path (sharded-op kernel dispatch) ------------------------------- */
+
+/* C[M,N] (bf16, row-major, ldc) = A·B with fp32 accumulation on tcgen05 tensor cores.
+ *   a_kmajor: A is [M,K] row-major (lda = elements between rows)   else A is stored [K,M] (lda between k rows)
+ *   b_kmajor: B is [N,K] row-major (i.e. C = A·Bᵀ, nn.Linear fwd)  else B is stored [K,N] (ldb between k rows)
+ * Replaces the aten.mm.default nodes of the sharded graph (Linear fwd / dgrad / wgrad;
+ * easydist/torch/passes/fix_bias.py turns addmm into mm+add first).
+ * Requirements: 16-byte aligned bases, lda/ldb/ldc multiples of 8 elements.  Returns
+ * EDB_E_UNSUPPORTED (=2) for shapes it does not cover so the host can dispatch elsewhere. */
+int edb_gemm_bf16(void* C, const void* A, const void* B, int64_t M, int64_t N, int64_t K,
+                  int64_t lda, int64_t ldb, int64_t ldc, int a_kmajor, int b_kmajor,
+                  int accumulate_into_c, void* stream);
+
+/* all-gather fused into the consuming GEMM: B (weights [N,K], K-major) is sharded S(0) over the
+ * group, shard (N/n rows) resident at symmetric offset `b_shard_off` on every rank.  The kernel's
+ * copy CTAs pull the peer shards into the local gathered buffer `b_full_off` chunk by chunk while
+ * the MMA CTAs start on the local shard and consume chunks as their flags arrive.
+ * C[M,N] = A[M,K]·B_fullᵀ.  (all_gather_end -> aten.mm pattern) */
+int edb_ag_gemm_bf16(int gid, void* C, const void* A, uint64_t b_shard_off, uint64_t b_full_off,
+                     int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldc, void* stream);
+
+/* GEMM fused with reduce-scatter: partial C[M,N] = A·B is produced tile by tile into the
+ * symmetric stage `c_stage_off` (row-chunks destined for other ranks first); reduce CTAs of the
+ * owner pull each finished chunk from every peer, sum in rank order, scale and cast into `dst`
+ * ([M/n, N], out_dtype).  (aten.mm -> reduce_scatter_start pattern.) */
+int edb_gemm_rs_bf16(int gid, void* dst, uint64_t c_stage_off, const void* A, const void* B,
+                     int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb, int a_kmajor,
+                     int b_kmajor, float post_scale, int out_dtype, void* stream);
+
+/* ---- options / introspection --------------------------------------------------------------- */
+
+/* integer options: "allreduce_oneshot_bytes", "copy_ctas_per_sm", "comm_ctas", "spin_timeout_ms" */
+int edb_set_option(const char* name, int64_t value);
+int edb_get_option(const char* name, int64_t* value_out);
+/* number of kernels this library has launched since load (all entry points) */
+uint64_t edb_launch_count(void);
+
+#define EDB_OK 0
+#define EDB_E_INVALID 1
+#define EDB_E_UNSUPPORTED 2
+#define EDB_E_CUDA 3
+#define EDB_E_STATE 4
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EDB_H_ */
