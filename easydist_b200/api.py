@@ -1,0 +1,259 @@
+"""`easydist_compile` for the B200 backend + registration behind the reference's own decorator.
+
+Two ways in, both keeping the reference's user-facing contract (easydist/torch/api.py:227-256):
+
+  * standalone:  `from easydist_b200 import easydist_compile` — same decorator signature
+    (`parallel_mode`, `tracing_mode`, `cuda_graph`, `compile_only`, ...); modes
+    "ddp" / "zero2" / "zero3" (compile_dp.py) need no solver and run anywhere; mode "auto" needs a
+    plan: from the reference's solver when it is importable, or a recorded plan (`plan=` kwarg).
+  * behind the reference:  `register()` plugs the backend into the reference through its
+    `register_parallel_method` hook (api.py:39-50, dispatch :136-140) as modes "b200_ddp",
+    "b200_zero2", "b200_zero3", and rebinds `compile_auto.sharding_transform` (the name imported
+    at compile_auto.py:46-49, called at :569) so `parallel_mode="auto"` lowers through this
+    backend while annotation + ILP stay the reference's.
+
+CUDA graphs: as in the reference (`cuda_graph=True` default, api.py:180-224) the whole step is
+captured after one eager warm-up and replayed with static input buffers; every kernel on the path
+(libedb collectives included) is capture-safe.
+"""
+import logging
+from functools import update_wrapper
+from typing import Any
+
+import torch
+import torch.utils._pytree as pytree
+
+from . import lowering
+from . import reshard as _default_ops
+from .compile import EDCompiledFunc, GraphIO, trace_train_step
+from .device_mesh import get_device_mesh
+
+logger = logging.getLogger(__name__)
+
+DP_MODES = ("ddp", "zero2", "zero3")
+PARALLEL_EXTENTION = {}
+
+
+def register_parallel_method(parallel_mode: str, compiler_func=None):
+    """Same plugin hook as the reference (api.py:39-50)."""
+
+    def wrapper(fn):
+        PARALLEL_EXTENTION[parallel_mode] = fn
+        return fn
+
+    return wrapper if compiler_func is None else wrapper(compiler_func)
+
+
+def _dp_group(mesh):
+    """Ranks of the data-parallel group: the mesh dim named 'dp' (compile_dp.py:57, 312-315) or,
+    for a 1-D mesh, its only dim."""
+    if "dp" in mesh.dim_names:
+        d = mesh.dim_names.index("dp")
+    else:
+        assert mesh.ndim == 1, "data-parallel modes need a mesh dim named 'dp'"
+        d = 0
+    return mesh.ranks_along(d), mesh.get_coordinate()[d]
+
+
+def _flat_inputs(params, buffers, named_states, args, kwargs):
+    return pytree.tree_flatten((params, buffers, named_states, args, kwargs))[0]
+
+
+def _finish(gm, params, buffers, named_states, args, kwargs, ops, native):
+    """Local metas -> static symmetric buffers -> GEMM dispatch."""
+    lowering.propagate_local_meta(gm, _flat_inputs(params, buffers, named_states, args, kwargs))
+    info = {"comm_nodes": lowering.count_nodes(gm, ops)}
+    if native:
+        from .runtime import get_runtime
+        info["symm_bytes"] = lowering.assign_static_buffers(gm, get_runtime(), ops)
+        info["gemm_nodes"] = lowering.dispatch_compute(gm)
+    gm.graph.lint()
+    gm.recompile()
+    return info
+
+
+def _compile_dp(func, parallel_mode, tracing_mode, args, kwargs, *, ops=_default_ops,
+                native=True):
+    """ddp / zero2 / zero3 (reference: _compile_dp, compile_dp.py:201-381)."""
+    mode = parallel_mode.replace("b200_", "")
+    assert mode in DP_MODES, parallel_mode
+    params, buffers, named_states, gm, module, opt = trace_train_step(func, args, kwargs,
+                                                                      tracing_mode)
+    io = GraphIO(gm, params, buffers, named_states)
+    ranks, my_index = _dp_group(get_device_mesh())
+    n = len(ranks)
+    shard_info = {}
+    if n > 1:
+        if mode == "ddp":
+            lowering.transform_ddp(gm, io, ranks, ops)
+        else:
+            _, shard_info = lowering.transform_fsdp(gm, io, ranks, my_index,
+                                                    shard_param=(mode == "zero3"), ops=ops)
+    # pre-shard parameters (zero3) and optimizer states (zero2/zero3): flat 1/n shards
+    # (compile_dp.py:330-343)
+    with torch.no_grad():
+        params = {k: v.detach() for k, v in params.items()}
+        if shard_info:
+            ph_names = {ph.name: i for i, ph in enumerate(io.param_ph)}
+            for ph_name, idx in ph_names.items():
+                if ph_name in shard_info:
+                    name = io.param_names[idx]
+                    params[name] = ops.scatter_wrapper(params[name].flatten(), n, 0, my_index)
+            flat_states, spec = pytree.tree_flatten(named_states)
+            for i, ph in enumerate(io.state_ph):
+                if ph.name in shard_info and isinstance(flat_states[i], torch.Tensor):
+                    flat_states[i] = ops.scatter_wrapper(flat_states[i].detach().flatten(), n, 0,
+                                                         my_index)
+            named_states = pytree.tree_unflatten(flat_states, spec)
+    info = _finish(gm, params, buffers, named_states, args, kwargs, ops, native)
+    info.update(mode=mode, dp_size=n)
+    return EDCompiledFunc(gm, params, buffers, named_states, info=info)
+
+
+def _compile_auto(func, tracing_mode, args, kwargs, *, plan=None, ops=_default_ops, native=True,
+                  planner="GREEDY"):
+    """Auto-SPMD with a given plan: {node_name: {'strategy': NodeSPMDStrategy}} in the vocabulary
+    of easydist_b200.metair (or the reference's own objects).  The plan is what the reference's
+    AutoFlow solver emits (compile_auto.py:93-186); producing it stays the reference's job."""
+    if plan is None:
+        raise NotImplementedError(
+            "parallel_mode='auto' needs a sharding plan: use easydist_b200.api.register() to run "
+            "behind the reference's solver, or pass plan=<recorded plan>")
+    from . import metair as M
+    params, buffers, named_states, gm, module, opt = trace_train_step(func, args, kwargs,
+                                                                      tracing_mode)
+    io = GraphIO(gm, params, buffers, named_states)
+    mesh = get_device_mesh("spmd")
+    plan = lowering._normalise_plan(plan)
+    lowering.sharding_transform(gm, plan, io.state_io_map(), ops=ops, mesh=mesh, planner=planner)
+    env = gm._edb_shard_env
+
+    def shard_local(t, ph):
+        strat = env.get(ph.name)
+        if not isinstance(t, torch.Tensor) or strat is None:
+            return t
+        coord = mesh.get_coordinate()
+        for mdim, s in enumerate(strat):
+            if s.is_shard():
+                t = ops.scatter_wrapper(t, mesh.size(mdim), s.dim, coord[mdim])
+        return t
+
+    with torch.no_grad():
+        params = {k: shard_local(v.detach(), ph) for (k, v), ph in zip(params.items(), io.param_ph)}
+        buffers = {k: shard_local(v.detach(), ph) for (k, v), ph in zip(buffers.items(),
+                                                                       io.buffer_ph)}
+        flat_states, spec = pytree.tree_flatten(named_states)
+        flat_states = [shard_local(s.detach() if isinstance(s, torch.Tensor) else s, ph)
+                       for s, ph in zip(flat_states, io.state_ph)]
+        named_states = pytree.tree_unflatten(flat_states, spec)
+    input_phs = io.input_ph
+
+    def input_transform(a, kw):
+        flat, spec_in = pytree.tree_flatten((a, kw))
+        flat = [shard_local(x.detach() if isinstance(x, torch.Tensor) else x, ph)
+                for x, ph in zip(flat, input_phs)]
+        return pytree.tree_unflatten(flat, spec_in)
+
+    largs, lkwargs = input_transform(args, kwargs)
+    info = _finish(gm, params, buffers, named_states, largs, lkwargs, ops, native)
+    info.update(mode="auto", mesh=mesh.shape)
+    return EDCompiledFunc(gm, params, buffers, named_states, input_transform=input_transform,
+                          info=info)
+
+
+class CompiledFuncWrapper:
+    """Dispatch + CUDA-graph capture/replay (reference: api.py:53-224)."""
+
+    def __init__(self, func, parallel_mode="auto", tracing_mode="fake", cuda_graph=True,
+                 enable_mono_graph=False, compile_only=False, compile_kwargs=None):
+        update_wrapper(self, func)
+        self.original_func = func
+        self.compiled_func = None
+        self.parallel_mode = parallel_mode
+        self.tracing_mode = tracing_mode
+        self.enable_cuda_graph = cuda_graph
+        self.compile_only = compile_only
+        self.compile_kwargs = compile_kwargs or {}
+        self._graph = None
+        self._static_inputs = None
+        self._static_output = None
+
+    def _compile(self, args, kwargs):
+        mode = self.parallel_mode
+        if mode == "auto":
+            return _compile_auto(self.original_func, self.tracing_mode, args, kwargs,
+                                 **self.compile_kwargs)
+        if mode in DP_MODES:
+            return _compile_dp(self.original_func, mode, self.tracing_mode, args, kwargs,
+                               **self.compile_kwargs)
+        if mode in PARALLEL_EXTENTION:
+            return PARALLEL_EXTENTION[mode](self.original_func, mode, self.tracing_mode, args,
+                                            kwargs)
+        raise NotImplementedError()
+
+    def __call__(self, *args: Any, **kwargs: Any) -> Any:
+        if self.compiled_func is None:
+            self.compiled_func = self._compile(args, kwargs)
+        if self.compile_only:
+            return self.compiled_func
+        if not self.enable_cuda_graph:
+            return self.compiled_func(*args, **kwargs)
+        flat, spec = pytree.tree_flatten([args, kwargs])
+        if self._graph is None:
+            self._static_inputs = [torch.empty_like(x).copy_(x) if isinstance(x, torch.Tensor)
+                                   else x for x in flat]
+            sargs, skwargs = pytree.tree_unflatten(self._static_inputs, spec)
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                self._static_output = self.compiled_func(*sargs, **skwargs)  # eager warm-up
+            torch.cuda.current_stream().wait_stream(s)
+            torch.cuda.synchronize()
+            self._graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self._graph):
+                self._static_output = self.compiled_func(*sargs, **skwargs)
+        else:
+            for dst, src in zip(self._static_inputs, flat):
+                if isinstance(dst, torch.Tensor):
+                    dst.copy_(src, non_blocking=True)
+        self._graph.replay()
+        return self._static_output
+
+
+def easydist_compile(func=None, parallel_mode="auto", tracing_mode="fake", cuda_graph=True,
+                     enable_mono_graph=False, use_hint=False, liveness_only_input=False,
+                     max_solver_time=float("inf"), compile_only=False, **compile_kwargs):
+    """Same decorator surface as the reference's easydist_compile (api.py:227-256)."""
+    if parallel_mode not in ("auto",) + DP_MODES and parallel_mode not in PARALLEL_EXTENTION:
+        raise NotImplementedError(
+            "please use [auto, ddp, zero2, zero3] for `parallel_mode` or register your parallel "
+            "extention")
+
+    def wrap(f):
+        return CompiledFuncWrapper(f, parallel_mode, tracing_mode, cuda_graph, enable_mono_graph,
+                                   compile_only, compile_kwargs)
+
+    return wrap(func) if func else wrap
+
+
+def register(reference_api=None, reference_compile_auto=None):
+    """Plug this backend into an importable reference (`easydist.torch`)."""
+    import easydist.torch.api as ref_api
+    import easydist.torch.compile_auto as ref_auto
+    reference_api = reference_api or ref_api
+    reference_compile_auto = reference_compile_auto or ref_auto
+
+    def dp_entry(original_func, parallel_mode, tracing_mode, args, kwargs):
+        return _compile_dp(original_func, parallel_mode, tracing_mode, args, kwargs)
+
+    for mode in DP_MODES:
+        reference_api.register_parallel_method(f"b200_{mode}", dp_entry)
+
+    def sharding_transform(fx_module, opt_strategy, state_io_map):
+        from easydist.torch.device_mesh import get_device_mesh as ref_mesh
+        from .device_mesh import set_device_mesh
+        mesh = set_device_mesh(ref_mesh("spmd"), rank=torch.distributed.get_rank())
+        return lowering.sharding_transform(fx_module, opt_strategy, state_io_map, mesh=mesh)
+
+    reference_compile_auto.sharding_transform = sharding_transform
+    return reference_api

@@ -1,0 +1,351 @@
+"""Tracing front-end + compiled-graph executor.
+
+Front-end: turns `train_step(*args)` (which closes over an nn.Module and an Optimizer found in
+its arguments) into ONE FX graph holding forward, backward and the optimizer update, with the
+calling convention the reference uses (easydist/torch/compile.py:25-94):
+
+    graph(params: dict, buffers: dict, named_states: dict, args, kwargs)
+        -> (params, buffers, named_states, grads: dict, user_return)
+
+Executor: `EDCompiledFunc` has the surface `CompiledFuncWrapper` and the reference's tests rely on
+(compile_auto.py:720-815): `.graph`, `.run_with_graph`, `.named_parameters()`, `.named_buffers()`,
+`._optimizer_state_dict()`, `.parameters()`, `.buffers()`, `.get_state()`.
+
+Unlike the reference's executor there is no per-step `distribute_tensor` of every input
+(compile_auto.py:737-745: a DTensor scatter/broadcast from rank 0 per argument per step): inputs
+are rank-local by construction and are sliced locally when the plan shards them.
+"""
+import contextlib
+import copy
+import logging
+import operator
+from functools import partial
+from typing import Any, Dict
+
+import torch
+import torch.utils._pytree as pytree
+from torch.fx.experimental.proxy_tensor import make_fx
+from torch.nn.utils import stateless
+
+logger = logging.getLogger(__name__)
+aten = torch.ops.aten
+
+# ---- in-place optimizer ops -> functional op + copy_ back --------------------------------------------
+# make_fx traces ATen calls; the in-place `_foreach_*_` / `_fused_*_` ops of torch.optim would
+# mutate graph inputs invisibly, so each is rewritten as its functional twin followed by explicit
+# `copy_` nodes onto the inputs (same approach as the reference's EASYDIST_DECOMP_TABLE,
+# easydist/torch/decomp_utils.py:108-131; built programmatically here).
+
+
+def _inplace_via_functional(functional, self, *rest, **kw):
+    updated = functional(self, *rest, **kw)
+    for dst, src in zip(self, updated):
+        dst.copy_(src)
+
+
+def _fused_multi_output(functional, n_lists, skip, self, *rest, **kw):
+    lists = (self,) + tuple(rest[:n_lists - 1])
+    updated = functional(self, *rest, **kw)
+    for idx, (orig, new) in enumerate(zip(lists, updated)):
+        if idx in skip:
+            continue
+        for dst, src in zip(orig, new):
+            dst.copy_(src)
+
+
+def aten_op_names(prefix):
+    """Base names of registered aten ops starting with `prefix` (the op namespace is lazy, so
+    dir(torch.ops.aten) only shows what was already touched)."""
+    names = set()
+    for full in torch._C._dispatch_get_all_op_names():
+        if full.startswith("aten::" + prefix):
+            names.add(full[len("aten::"):].split(".")[0])
+    return sorted(names)
+
+
+def build_decomposition_table():
+    table = {}
+    for name in aten_op_names("_foreach_"):
+        if not name.endswith("_"):
+            continue
+        packet = getattr(aten, name)
+        fpacket = getattr(aten, name[:-1], None)
+        if fpacket is None:
+            continue
+        for overload in packet.overloads():
+            if hasattr(fpacket, overload):
+                table[getattr(packet, overload)] = partial(_inplace_via_functional,
+                                                           getattr(fpacket, overload))
+    if hasattr(aten, "_fused_adam_"):
+        # (params, grads, exp_avgs, exp_avg_sqs, max_exp_avg_sqs); grads are not written back
+        table[aten._fused_adam_.default] = partial(_fused_multi_output, aten._fused_adam.default,
+                                                   5, (1,))
+    if hasattr(aten, "_fused_adamw_"):
+        table[aten._fused_adamw_.default] = partial(_fused_multi_output, aten._fused_adamw.default,
+                                                    5, (1,))
+    if hasattr(aten, "_fused_sgd_"):
+        # (params, grads, momentum_buffer_list)
+        table[aten._fused_sgd_.default] = partial(_fused_multi_output, aten._fused_sgd.default,
+                                                  3, (1,))
+    from torch._decomp.decompositions import mse_loss, mse_loss_backward
+    table[aten.mse_loss.default] = mse_loss
+    table[aten.mse_loss_backward.default] = mse_loss_backward
+    return table
+
+
+DECOMPOSITION_TABLE = build_decomposition_table()
+
+
+@contextlib.contextmanager
+def _optimizer_sees(opt, named_states, params):
+    """Point the optimizer at the traced (proxy) params/states for the duration of the trace."""
+    saved_state = copy.copy(opt.state)
+    for n in named_states:
+        opt.state[params[n]] = named_states[n]
+    group = opt.param_groups[0]  # single param group, like the reference (utils.py:174-177)
+    saved_params = group["params"]
+    group["params"] = list(params.values())
+    try:
+        yield
+    finally:
+        group["params"] = saved_params
+        opt.state.clear()
+        opt.state.update(saved_state)
+
+
+@contextlib.contextmanager
+def _pretend_compiling():
+    """torch.optim consults `is_compiling()` to pick the graph-friendly code path (no .item(),
+    no Python-side step increments); the reference flips the same switch (utils.py:186-207)."""
+    import torch._dynamo
+    targets = [torch._utils.is_compiling, torch._dynamo.is_compiling]
+    if hasattr(torch, "compiler") and hasattr(torch.compiler, "is_compiling"):
+        targets.append(torch.compiler.is_compiling)
+    saved = [t.__code__ for t in targets]
+
+    def _true():
+        return True
+
+    for t in targets:
+        t.__code__ = _true.__code__
+    try:
+        yield
+    finally:
+        for t, code in zip(targets, saved):
+            t.__code__ = code
+
+
+def find_module_and_optimizer(args, kwargs):
+    module, opt = None, None
+    for leaf in pytree.tree_flatten(list(args) + list(kwargs.values()))[0]:
+        if isinstance(leaf, torch.nn.Module):
+            assert module is None, "Only support single nn.Module in args now"
+            module = leaf
+        if isinstance(leaf, torch.optim.Optimizer):
+            assert opt is None, "Only support single Optimizer in args now"
+            opt = leaf
+    return module, opt
+
+
+def _stateless_call(func, module, opt, grad_nodes, params, buffers, named_states, args, kwargs):
+    ctx_m = stateless._reparametrize_module(module, {**params, **buffers}, tie_weights=True) \
+        if module is not None else contextlib.nullcontext()
+    ctx_o = _optimizer_sees(opt, named_states, params) if opt is not None \
+        else contextlib.nullcontext()
+    # Record the FX node of every final gradient while tracing: train steps usually end with
+    # opt.zero_grad(), which leaves `param.grad is None` at return time (the reference then returns
+    # None grads, compile.py:36); the data-parallel rewrites need the node the optimizer consumes.
+    from torch.fx.experimental.proxy_tensor import get_proxy_mode, get_proxy_slot
+    mode = get_proxy_mode()
+    handles = []
+    if mode is not None and grad_nodes is not None:
+        for name, p in params.items():
+            if not p.requires_grad:
+                continue
+
+            def hook(param, name=name):
+                try:
+                    grad_nodes[name] = get_proxy_slot(param.grad, mode.tracer).proxy.node
+                except Exception:  # untracked tensor: leave it to the output-based lookup
+                    pass
+
+            handles.append(p.register_post_accumulate_grad_hook(hook))
+    try:
+        with ctx_m, ctx_o:
+            ret = func(*args, **kwargs)
+    finally:
+        for h in handles:
+            h.remove()
+    grads = {k: v.grad for k, v in params.items()}
+    return params, buffers, named_states, grads, ret
+
+
+def warm_up_optimizer(module, opt):
+    """One zero-gradient step so that the optimizer materialises its state tensors
+    (compile.py:52-66); `step` counters are rewound by one."""
+    named_states = {}
+    params = dict(module.named_parameters())
+    if opt is None:
+        return named_states
+    with torch.no_grad():
+        for p in params.values():
+            p.grad = torch.zeros_like(p)
+    opt.step()
+    opt.zero_grad(True)
+    for n, p in params.items():
+        if p in opt.state:
+            named_states[n] = opt.state[p]
+            if "step" in named_states[n]:
+                named_states[n]["step"] -= 1
+    flat, _ = pytree.tree_flatten(named_states)
+    if all(s is None for s in flat):  # plain SGD has no state
+        named_states = {}
+    return named_states
+
+
+def strip_profiler_nodes(gm):
+    """torch >= 2.5 records profiler enter/exit nodes from Optimizer.step; they carry no data."""
+    for node in reversed(list(gm.graph.nodes)):
+        if node.op == "call_function" and "_record_function" in str(node.target):
+            if len(node.users) == 0:
+                gm.graph.erase_node(node)
+    return gm
+
+
+def eliminate_detach(gm):
+    """aten.detach nodes only alias (same clean-up as the reference's passes/eliminate_detach)."""
+    recorded = getattr(gm, "_edb_grad_nodes", None)
+    for node in list(gm.graph.nodes):
+        if node.op == "call_function" and node.target == aten.detach.default:
+            if recorded:
+                for k, v in list(recorded.items()):
+                    if v is node:
+                        recorded[k] = node.args[0]
+            node.replace_all_uses_with(node.args[0])
+            gm.graph.erase_node(node)
+    return gm
+
+
+def trace_train_step(func, args, kwargs, tracing_mode="fake"):
+    """-> (params, buffers, named_states, traced GraphModule, module, opt).
+    `gm._edb_grad_nodes` maps parameter names to the node of their final gradient."""
+    module, opt = find_module_and_optimizer(args, kwargs)
+    params = dict(module.named_parameters()) if module is not None else {}
+    buffers = dict(module.named_buffers()) if module is not None else {}
+    named_states = warm_up_optimizer(module, opt) if module is not None else {}
+    grad_nodes = {}
+    with _pretend_compiling():
+        gm = make_fx(partial(_stateless_call, func, module, opt, grad_nodes),
+                     tracing_mode=tracing_mode,
+                     decomposition_table=DECOMPOSITION_TABLE, _allow_non_fake_inputs=False)(
+            params, buffers, named_states, args, kwargs)
+    strip_profiler_nodes(gm)
+    # keep the recorded gradient nodes valid across detach elimination
+    alive = set(gm.graph.nodes)
+    gm._edb_grad_nodes = {k: v for k, v in grad_nodes.items() if v in alive}
+    eliminate_detach(gm)
+    gm.graph.eliminate_dead_code()
+    gm.recompile()
+    alive = set(gm.graph.nodes)
+    gm._edb_grad_nodes = {k: v for k, v in gm._edb_grad_nodes.items() if v in alive}
+    return params, buffers, named_states, gm, module, opt
+
+
+# ---- graph I/O bookkeeping -------------------------------------------------------------------------------
+
+
+class GraphIO:
+    """Which placeholders / outputs of the flat graph are params, buffers, optimizer states,
+    user inputs, grads and user returns (all index-based on the pytree-flattened signature)."""
+
+    def __init__(self, gm, params, buffers, named_states):
+        self.placeholders = [n for n in gm.graph.nodes if n.op == "placeholder"]
+        self.output = next(n for n in gm.graph.nodes if n.op == "output")
+        self.param_names = list(params.keys())
+        self.buffer_names = list(buffers.keys())
+        flat_states, self.state_spec = pytree.tree_flatten(named_states)
+        np_, nb, ns = len(self.param_names), len(self.buffer_names), len(flat_states)
+        self.n_params, self.n_buffers, self.n_states = np_, nb, ns
+        self.param_ph = self.placeholders[:np_]
+        self.buffer_ph = self.placeholders[np_:np_ + nb]
+        self.state_ph = self.placeholders[np_ + nb:np_ + nb + ns]
+        self.input_ph = self.placeholders[np_ + nb + ns:]
+        outs = list(self.output.args[0])
+        self.out_params = outs[:np_]
+        self.out_buffers = outs[np_:np_ + nb]
+        self.out_states = outs[np_ + nb:np_ + nb + ns]
+        self.out_grads = outs[np_ + nb + ns:np_ + nb + ns + np_]
+        self.out_user = outs[np_ + nb + ns + np_:]
+        self.state_is_tensor = [isinstance(s, torch.Tensor) for s in flat_states]
+        # final gradient node per parameter: recorded at trace time, else the returned .grad
+        recorded = getattr(gm, "_edb_grad_nodes", {})
+        self.final_grads = []
+        for name, out in zip(self.param_names, self.out_grads):
+            node = recorded.get(name)
+            if node is None and isinstance(out, torch.fx.Node):
+                node = out
+            self.final_grads.append(node)
+
+    def state_io_map(self):
+        """placeholder -> output node for every state tensor (params, buffers, opt states);
+        the reference builds the same map from MetaGraph (compile_auto.py:160-173)."""
+        m = {}
+        for ph, out in zip(self.param_ph + self.buffer_ph + self.state_ph,
+                           self.out_params + self.out_buffers + self.out_states):
+            if isinstance(out, torch.fx.Node):
+                m[ph] = out
+        return m
+
+
+# ---- executor -----------------------------------------------------------------------------------------------
+
+
+class EDCompiledFunc:
+    """Runs the lowered graph; same surface as the reference's EDCompiledFunc
+    (compile_auto.py:720-815 / compile_dp.py:346-381)."""
+
+    def __init__(self, graph, params, buffers, named_states, input_transform=None, info=None):
+        self.graph = graph
+        self._params = params
+        self._buffers = buffers
+        self._named_states = named_states
+        self._input_transform = input_transform
+        self.info = info or {}
+
+    @torch.no_grad()
+    def compiled_func(self, graph, *args, **kwargs):
+        if self._input_transform is not None:
+            args, kwargs = self._input_transform(args, kwargs)
+        params, buffers, named_states, grads, out = graph(self._params, self._buffers,
+                                                          self._named_states, args, kwargs)
+        self._params, self._buffers, self._named_states = params, buffers, named_states
+        for name in params:
+            params[name].grad = grads[name]
+        return out
+
+    def __call__(self, *args: Any, **kwargs: Any) -> Any:
+        return self.compiled_func(self.graph, *args, **kwargs)
+
+    def run_with_graph(self, graph, *args: Any, **kwargs: Any) -> Any:
+        return self.compiled_func(graph, *args, **kwargs)
+
+    def compile_mono_graph(self, *args, **kwargs):
+        raise NotImplementedError("enable_mono_graph is not supported by the b200 backend")
+
+    def get_state(self):
+        return self._params, self._buffers, self._named_states
+
+    def parameters(self):
+        return self._params.values()
+
+    def named_parameters(self):
+        return self._params
+
+    def buffers(self):
+        return self._buffers.values()
+
+    def named_buffers(self):
+        return self._buffers
+
+    def _optimizer_state_dict(self):
+        return self._named_states

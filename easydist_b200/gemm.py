@@ -85,3 +85,8 @@ def mm(a, b):
                             1 if a_k else 0, 1 if b_k else 0, 0, stream))
     _stats["edb_gemm"] += 1
     return out
+
+
+def addmm(bias, a, b):
+    """aten.addmm.default(bias, a, b) = bias + a @ b with the product on the tcgen05 kernel."""
+    return torch.ops.aten.add.Tensor(mm(a, b), bias)

@@ -1,0 +1,438 @@
+"""Plan -> executable graph: the B200 replacement of the reference's lowering passes.
+
+  sharding_transform(fx_module, opt_strategy, state_io_map)
+        drop-in for easydist/torch/passes/sharding.py:852-979 (call site compile_auto.py:569):
+        walks the traced graph with the solver's per-node NodeSPMDStrategy, tracks the placement
+        of every value (`shard_env`), and wherever producer and consumer placements differ emits
+        the reshard steps chosen by the edge planner (insert_comm_node, sharding.py:704-809);
+        view/reshape/expand size arguments are rewritten to local shapes (override_args,
+        :812-849); user outputs are replicated and state outputs are forced back to the placement
+        of their input placeholder + copy_wrapper (:920-949).
+  transform_ddp / transform_fsdp
+        the data-parallel rewrites of easydist/torch/compile_dp.py:55-198 (modes ddp / zero2 /
+        zero3), generalised from "the `_fused_adam` node" to any elementwise optimizer by working
+        on the optimizer region of the graph (everything downstream of the final gradients).
+  assign_static_buffers / dispatch_compute / propagate_local_meta
+        B200-specific finishing passes: symmetric-heap buffers fixed at compile time (so the
+        graph is CUDA-graph capturable with zero allocations in the comm path), bf16 `aten.mm` ->
+        tcgen05 GEMM dispatch.
+
+The emitted `call_function` targets are the callables of an `ops` namespace with the reference's
+names and signatures (default: easydist_b200.reshard -> libedb.so).
+"""
+import operator
+from typing import Dict, List, Optional
+
+import torch
+import torch.utils._pytree as pytree
+from torch.fx.node import Node
+
+from . import metair as M
+from . import planners
+from . import reshard as _default_ops
+from .device_mesh import get_device_mesh
+
+aten = torch.ops.aten
+
+CREATE_ATEN_OP = [
+    aten.empty.memory_format, aten.zeros.default, aten.ones.default, aten.scalar_tensor.default,
+    aten.arange.default, aten.arange.start, aten.full.default,
+]
+
+# ---- local shapes -----------------------------------------------------------------------------------------
+
+
+def local_shape(global_shape, mesh, placements):
+    """Shape of this rank's shard: torch.chunk (ceil-div) blocks per sharded mesh dim, applied
+    outer mesh dim first (DTensor compute_local_shape, used by torch/utils.py:106-136)."""
+    shape = list(global_shape)
+    coord = mesh.get_coordinate()
+    for mdim, p in enumerate(placements):
+        if p is not None and p.is_shard():
+            d, n = p.dim, mesh.size(mdim)
+            full = -(-shape[d] // n)
+            lo = min(shape[d], full * coord[mdim])
+            hi = min(shape[d], full * (coord[mdim] + 1))
+            shape[d] = hi - lo
+    return shape
+
+
+def _torch_placements(strategy):
+    from torch.distributed.tensor import Partial, Replicate, Shard
+    out = []
+    for s in strategy:
+        if s.is_shard():
+            out.append(Shard(s.dim))
+        elif s.is_partial():
+            out.append(Partial(s.op))
+        else:
+            out.append(Replicate())
+    return out
+
+
+def _view_rules(node):
+    from torch.distributed.tensor._ops._view_ops import expand, normalize_sizes, view_groups
+    if node.target in (aten.view.default, aten._unsafe_view.default, aten.reshape.default):
+        return lambda in_shape, shape: view_groups(in_shape, shape)
+    if node.target == aten.expand.default:
+        return lambda in_shape, sizes: expand(in_shape, normalize_sizes(sizes))
+    return None
+
+
+def override_args(node, invars_strategy, mesh):
+    """Rewrite the size argument of view/reshape/expand nodes to the LOCAL output shape under the
+    input's placement (sharding.py:812-849)."""
+    rules_fn = _view_rules(node)
+    if rules_fn is None:
+        return
+    from torch.distributed.tensor._ops._view_ops import propagate_shape_and_sharding
+    global_in_shape = tuple(node.args[0].meta["val"].shape)
+    in_spec = _torch_placements(invars_strategy[0])
+    rules = rules_fn(global_in_shape, node.args[1])
+    _, shard_out = propagate_shape_and_sharding(in_spec, global_in_shape, rules,
+                                                tuple(mesh.shape))
+    if shard_out is None:
+        shard_out = in_spec
+    from torch.distributed.tensor import Shard
+    out_strategy = [M.S(p.dim) if isinstance(p, Shard) else M.R() for p in shard_out]
+    global_out_shape = list(node.meta["val"].shape)
+    node.update_arg(1, local_shape(global_out_shape, mesh, out_strategy))
+
+
+# ---- edge lowering -----------------------------------------------------------------------------------------
+
+
+def insert_comm_node(gm, node, var_, src_specs, tgt_specs, mesh, ops, planner="GREEDY",
+                     copy_innode=None):
+    """Emit the reshard steps turning `var_` (placement src_specs) into tgt_specs in front of
+    `node` (sharding.py:704-809).  One step = one op on the flat rank group of one mesh dim."""
+    steps = planners.PLANNERS[planner](src_specs, tgt_specs)
+    coord = mesh.get_coordinate()
+    graph = gm.graph
+    for mdim, cur, tgt in steps:
+        kind = planners.step_kind(cur, tgt)
+        if kind is None:
+            continue
+        n = mesh.size(mdim)
+        ranks = mesh.ranks_along(mdim)
+        with graph.inserting_before(node):
+            if kind == "scatter":
+                new = graph.call_function(ops.scatter_wrapper, args=(var_, n, tgt.dim, coord[mdim]))
+            elif kind == "all_to_all":
+                a = (cur.dim, tgt.dim, n, coord[mdim], ranks)
+                s = graph.call_function(ops.all_to_all_start, args=(var_, *a))
+                new = graph.call_function(ops.all_to_all_end, args=(s, *a))
+            elif kind == "reduce_scatter":
+                a = (cur.op, tgt.dim, ranks)
+                s = graph.call_function(ops.reduce_scatter_start, args=(var_, *a))
+                new = graph.call_function(ops.reduce_scatter_end, args=(s, *a))
+            elif kind == "all_gather":
+                a = (cur.dim, ranks)
+                s = graph.call_function(ops.all_gather_start, args=(var_, *a))
+                new = graph.call_function(ops.all_gather_end, args=(s, *a))
+            elif kind == "all_reduce":
+                a = (cur.op, ranks)
+                s = graph.call_function(ops.all_reduce_start, args=(var_, *a))
+                new = graph.call_function(ops.all_reduce_end, args=(s, *a))
+            else:  # pragma: no cover
+                raise AssertionError(kind)
+        node.replace_input_with(var_, new)
+        var_ = new
+    if copy_innode is not None:
+        with graph.inserting_before(node):
+            cp = graph.call_function(ops.copy_wrapper, args=(copy_innode, var_))
+        node.replace_input_with(var_, cp)
+    return gm
+
+
+def _normalise_plan(opt_strategy):
+    """Accept the reference's objects (duck typed) or ours."""
+    any_entry = next(iter(opt_strategy.values()), None)
+    if any_entry is None or isinstance(any_entry["strategy"], M.NodeSPMDStrategy):
+        return opt_strategy
+    return M.plan_from_reference(opt_strategy)
+
+
+def _num_user_returns(gm):
+    spec = gm._out_spec
+    children = spec.children() if callable(getattr(spec, "children", None)) else spec.children_specs
+    return children[-1].num_leaves
+
+
+def sharding_transform(fx_module: torch.fx.GraphModule, opt_strategy, state_io_map, *,
+                       ops=_default_ops, mesh=None, planner="GREEDY"):
+    """Drop-in for the reference's sharding_transform (same positional arguments)."""
+    mesh = mesh or get_device_mesh("spmd")
+    plan = _normalise_plan(opt_strategy)
+    shard_env: Dict[str, object] = {}
+    replicate = M.replicate_strategy(mesh.ndim)
+    n_ret = _num_user_returns(fx_module)
+    placeholders = {}
+    for node in list(fx_module.graph.nodes):
+        if node.op == "placeholder":
+            if node.name in plan:
+                shard_env[node.name] = plan[node.name]["strategy"].out_strtg_group[0]
+            else:
+                shard_env[node.name] = replicate
+            placeholders[node.name] = node
+        elif node.op == "call_function":
+            if node.target in CREATE_ATEN_OP:
+                shard_env[node.name] = replicate
+                continue
+            if node.target == operator.getitem:
+                shard_env[node.name] = shard_env[node.args[0].name][node.args[1]]
+                continue
+            invars = [a for a in pytree.tree_flatten(node.args)[0] if isinstance(a, Node)]
+            if node.name not in plan:
+                raise KeyError(f"no strategy for node {node.name} in the plan")
+            strat = plan[node.name]["strategy"]
+            in_strats = strat.in_strtg_group
+            override_args(node, in_strats, mesh)
+            assert len(invars) == len(in_strats), (node.name, len(invars), len(in_strats))
+            seen = set()
+            for var_, tgt in zip(invars, in_strats):
+                if var_ in seen:
+                    continue
+                seen.add(var_)
+                src = shard_env[var_.name]
+                if tgt is not None and tgt != src:
+                    insert_comm_node(fx_module, node, var_, src, tgt, mesh, ops, planner)
+            out = strat.out_strtg_group
+            shard_env[node.name] = out[0] if len(out) == 1 else out
+        elif node.op == "output":
+            outs = list(node.args[0])
+            for o in [o for o in outs[len(outs) - n_ret:] if isinstance(o, Node)]:
+                src = shard_env[o.name]
+                if src is not None and src != replicate:
+                    insert_comm_node(fx_module, node, o, src, replicate, mesh, ops, planner)
+            for in_node, out_node in state_io_map.items():
+                if in_node.name not in shard_env:
+                    continue
+                o = next((x for x in node.args[0] if isinstance(x, Node) and
+                          x.name == out_node.name), None)
+                assert o is not None, out_node.name
+                src, tgt = shard_env[o.name], shard_env[in_node.name]
+                if tgt != src:
+                    insert_comm_node(fx_module, node, o, src, tgt, mesh, ops, planner,
+                                     copy_innode=placeholders[in_node.name])
+    fx_module.graph.lint()
+    fx_module.recompile()
+    fx_module._edb_shard_env = shard_env
+    return fx_module
+
+
+# ---- data-parallel rewrites (compile_dp.py:55-198) ---------------------------------------------------------
+
+_ELEMENTWISE_OPT_OPS = None
+
+
+def _optimizer_elementwise_ops():
+    global _ELEMENTWISE_OPT_OPS
+    if _ELEMENTWISE_OPT_OPS is None:
+        ok = {operator.getitem}
+        from .compile import aten_op_names
+        for name in aten_op_names("_foreach_"):
+            if not name.endswith("_") and "norm" not in name and name != "_foreach_max":
+                ok.update(getattr(getattr(aten, name), o) for o in getattr(aten, name).overloads())
+        for name in ("_fused_adam", "_fused_adamw", "_fused_sgd", "copy_", "add", "sub", "mul",
+                     "div", "addcmul", "addcdiv", "sqrt", "rsqrt", "pow", "neg", "reciprocal",
+                     "lerp", "clone", "maximum", "minimum", "_to_copy", "where", "abs", "sign",
+                     "zeros_like", "ones_like", "detach", "alias", "lt", "gt", "ge", "le", "eq"):
+            if hasattr(aten, name):
+                pk = getattr(aten, name)
+                ok.update(getattr(pk, o) for o in pk.overloads())
+        _ELEMENTWISE_OPT_OPS = ok
+    return _ELEMENTWISE_OPT_OPS
+
+
+def optimizer_region(gm, io):
+    """Nodes downstream of the final gradients (the optimizer update), in graph order."""
+    grads = [g for g in io.final_grads if isinstance(g, Node)]
+    region, stack = set(), list(grads)
+    while stack:
+        n = stack.pop()
+        for u in n.users:
+            if u.op != "output" and u not in region:
+                region.add(u)
+                stack.append(u)
+    return [n for n in gm.graph.nodes if n in region]
+
+
+def transform_ddp(gm, io, ranks, ops=_default_ops):
+    """ddp: all-reduce(avg) every final gradient before the optimizer consumes it
+    (compile_dp.py:55-79 does this for the gradient list of `_fused_adam`)."""
+    ranks = list(ranks)
+    if len(ranks) <= 1:
+        return gm
+    for g in dict.fromkeys(x for x in io.final_grads if isinstance(x, Node)):
+        with gm.graph.inserting_after(g):
+            s = gm.graph.call_function(ops.all_reduce_start, args=(g, "avg", ranks))
+        with gm.graph.inserting_after(s):
+            e = gm.graph.call_function(ops.all_reduce_end, args=(s, "avg", ranks))
+        g.replace_all_uses_with(e, delete_user_cb=lambda u: u is not s)
+    gm.graph.lint()
+    gm.recompile()
+    return gm
+
+
+def transform_fsdp(gm, io, ranks, my_index, shard_param, ops=_default_ops):
+    """zero2 (shard_param=False) / zero3 (True), compile_dp.py:82-198: gradients are flattened and
+    reduce-scattered(avg), optimizer states (and, for zero3, parameters) live as flat 1/n shards;
+    zero3 all-gathers a parameter in front of each forward/backward use, zero2 scatters the
+    parameter into the optimizer and all-gathers the updated shard back."""
+    ranks = list(ranks)
+    n = len(ranks)
+    if n <= 1:
+        return gm, {}
+    graph = gm.graph
+    region = optimizer_region(gm, io)
+    region_set = set(region)
+    allowed = _optimizer_elementwise_ops()
+    for node in region:
+        if node.op == "call_function" and node.target not in allowed and \
+                node.target not in ops.CUSTOM_FUNCS:
+            raise NotImplementedError(
+                f"zero2/zero3: optimizer op {node.target} is not elementwise over (param, grad, "
+                f"state); cannot run it on flat shards")
+    shard_info = {}  # placeholder name -> original shape (for pre-sharding the state)
+
+    def check_divisible(ph):
+        numel = ph.meta["val"].numel()
+        if numel % n != 0:
+            # reduce_scatter_start asserts the same (sharding.py:136-137)
+            raise AssertionError(f"{ph.name}: numel {numel} must be a multiple of group_size {n}")
+
+    # (1) gradients: flatten + reduce_scatter(avg) along dim 0
+    for g in dict.fromkeys(x for x in io.final_grads if isinstance(x, Node)):
+        with graph.inserting_after(g):
+            f = graph.call_function(aten.flatten.using_ints, args=(g,))
+        with graph.inserting_after(f):
+            s = graph.call_function(ops.reduce_scatter_start, args=(f, "avg", 0, ranks))
+        with graph.inserting_after(s):
+            e = graph.call_function(ops.reduce_scatter_end, args=(s, "avg", 0, ranks))
+        g.replace_all_uses_with(e, delete_user_cb=lambda u: u is not f)
+
+    # (2) parameters
+    for ph in io.param_ph:
+        check_divisible(ph)
+        shape = list(ph.meta["val"].shape)
+        if shard_param:
+            shard_info[ph.name] = shape
+            for user in list(ph.users):
+                if user in region_set or user.op == "output":
+                    continue
+                with graph.inserting_before(user):
+                    s = graph.call_function(ops.all_gather_start, args=(ph, 0, ranks))
+                    e = graph.call_function(ops.all_gather_end, args=(s, 0, ranks))
+                    v = graph.call_function(aten.view.default, args=(e, shape))
+                user.replace_input_with(ph, v)
+        else:
+            opt_users = [u for u in ph.users if u in region_set]
+            if not opt_users:
+                continue
+            first = min(opt_users, key=lambda u: region.index(u))
+            with graph.inserting_before(first):
+                f = graph.call_function(aten.flatten.using_ints, args=(ph,))
+                sc = graph.call_function(ops.scatter_wrapper, args=(f, n, 0, my_index))
+            for user in opt_users:
+                if user.target == aten.copy_.default and user.args[0] is ph:
+                    # write-back of the updated shard: gather it into the full parameter
+                    new_shard = user.args[1]
+                    with graph.inserting_before(user):
+                        s = graph.call_function(ops.all_gather_start, args=(new_shard, 0, ranks))
+                        e = graph.call_function(ops.all_gather_end, args=(s, 0, ranks))
+                        v = graph.call_function(aten.view.default, args=(e, shape))
+                    user.update_arg(1, v)
+                else:
+                    user.replace_input_with(ph, sc)
+
+    # (3) optimizer states with the parameter's numel live as flat shards
+    param_numels = {ph.meta["val"].numel() for ph in io.param_ph}
+    for ph, is_t in zip(io.state_ph, io.state_is_tensor):
+        if not is_t:
+            continue
+        val = ph.meta.get("val")
+        if val is None or val.dim() == 0 or val.numel() not in param_numels:
+            continue  # step counters etc. stay replicated
+        check_divisible(ph)
+        shard_info[ph.name] = list(val.shape)
+
+    graph.lint()
+    gm.recompile()
+    return gm, shard_info
+
+
+# ---- finishing passes -----------------------------------------------------------------------------------------
+
+
+def propagate_local_meta(gm, flat_inputs):
+    """Re-run shape propagation on the lowered graph with LOCAL placeholder values so that every
+    node's meta['val'] is the per-rank tensor (the reference recomputes metas node by node with
+    create_meta_from_node, sharding.py:953-977)."""
+    from torch._subclasses.fake_tensor import FakeTensorMode
+    from torch.fx.passes.fake_tensor_prop import FakeTensorProp
+    mode = FakeTensorMode(allow_non_fake_inputs=True)
+    fake_inputs = [mode.from_tensor(x) if isinstance(x, torch.Tensor) else x for x in flat_inputs]
+    FakeTensorProp(gm, mode).propagate_dont_convert_inputs(*fake_inputs)
+    return gm
+
+
+def _nbytes(val):
+    return val.numel() * val.element_size()
+
+
+def assign_static_buffers(gm, rt, ops=_default_ops):
+    """Give every communication node fixed symmetric-heap buffers (`_buf` kwarg) sized from the
+    local metas: no allocation, no address change on the comm path => CUDA-graph capturable and
+    zero-copy outputs.  Returns the number of bytes reserved."""
+    total = 0
+    oneshot = rt.get_option("allreduce_oneshot_bytes")
+    for node in gm.graph.nodes:
+        if node.op != "call_function" or node.target not in ops.COMM_FUNCS:
+            continue
+        x = node.args[0].meta["val"]
+        if node.target is ops.all_gather_start:
+            need = [_nbytes(node.meta["val"])]
+        elif node.target is ops.all_reduce_start:
+            need = [_nbytes(x)] * (2 if _nbytes(x) > oneshot else 1)
+        else:
+            need = [_nbytes(x)]
+        if need[0] == 0:
+            continue
+        bufs = [rt.alloc(b) for b in need]
+        total += sum(need)
+        kw = dict(node.kwargs)
+        kw["_buf"] = (bufs[0].offset, need[0]) + tuple(b.offset for b in bufs[1:])
+        node.kwargs = kw
+    gm.recompile()
+    return total
+
+
+def dispatch_compute(gm):
+    """Route bf16 `aten.mm` / `aten.addmm` nodes to the tcgen05 GEMM (sharded-op kernel dispatch)."""
+    from . import gemm
+    n = 0
+    for node in gm.graph.nodes:
+        if node.op != "call_function":
+            continue
+        val = node.meta.get("val")
+        if not isinstance(val, torch.Tensor) or val.dtype != torch.bfloat16:
+            continue
+        if node.target == aten.mm.default:
+            node.target = gemm.mm
+            n += 1
+        elif node.target == aten.addmm.default and not node.kwargs:
+            node.target = gemm.addmm
+            n += 1
+    gm.recompile()
+    return n
+
+
+def count_nodes(gm, ops=_default_ops):
+    hist = {}
+    for node in gm.graph.nodes:
+        if node.op == "call_function":
+            name = getattr(node.target, "__name__", str(node.target))
+            if node.target in ops.CUSTOM_FUNCS or "gemm" in getattr(node.target, "__module__", ""):
+                hist[name] = hist.get(name, 0) + 1
+    return hist

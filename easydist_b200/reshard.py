@@ -157,7 +157,7 @@ def scatter_wrapper(tensor, num_chunks, dim, indice):
     d = _norm_dim(dim, ndim)
     size = tensor.shape[d]
     block = -(-size // num_chunks) if size > 0 else 0
-    n_actual = -(-size // block) if block > 0 else 1
+    n_actual = -(-size // block) if block > 0 else num_chunks  # size 0: n empty chunks
     if indice >= n_actual or indice < 0:
         raise IndexError("tuple index out of range")
     lo = min(size, block * indice)

@@ -1,0 +1,103 @@
+"""TEST INFRASTRUCTURE: the ten reshard callables over torch.distributed (gloo) so that the
+host-side logic (lowering, data-parallel rewrites, executor) can be exercised with world_size 2 on
+CPU.  Semantics follow the oracle / the reference (sharding.py:94-163); the product binds
+easydist_b200.reshard (libedb.so) instead and has no CPU path."""
+from typing import List
+
+import torch
+import torch.distributed as dist
+from torch._subclasses.fake_tensor import FakeTensor
+
+_GROUPS = {}
+
+
+def _pg(ranks):
+    key = tuple(ranks)
+    if key not in _GROUPS:
+        _GROUPS[key] = dist.new_group(list(ranks), backend="gloo")
+    return _GROUPS[key]
+
+
+def _fake(t):
+    return isinstance(t, FakeTensor) or t.is_meta
+
+
+_OPS = {"sum": dist.ReduceOp.SUM, "max": dist.ReduceOp.MAX, "min": dist.ReduceOp.MIN,
+        "avg": dist.ReduceOp.SUM}
+
+
+def all_reduce_start(self, reduceOp: str, group: List[int], tag: str = "", *, _buf=None):
+    if _fake(self):
+        return torch.empty_like(self)
+    out = self.contiguous().clone()
+    acc = out.float() if out.dtype in (torch.bfloat16, torch.float16) else out
+    dist.all_reduce(acc, op=_OPS[reduceOp], group=_pg(group))
+    if reduceOp == "avg":
+        acc = acc * (1.0 / len(group))
+    return acc.to(self.dtype)
+
+
+def all_reduce_end(self, reduceOp, group, tag=""):
+    return self
+
+
+def all_gather_start(self, gather_dim: int, group: List[int], tag: str = "", *, _buf=None):
+    n = len(group)
+    shape = list(self.shape)
+    shape[gather_dim] *= n
+    if _fake(self):
+        return self.new_empty(shape)
+    parts = [torch.empty_like(self.contiguous()) for _ in range(n)]
+    dist.all_gather(parts, self.contiguous(), group=_pg(group))
+    return torch.cat(parts, dim=gather_dim)
+
+
+def all_gather_end(self, gather_dim, group, tag=""):
+    return self
+
+
+def scatter_wrapper(tensor, num_chunks, dim, indice):
+    return torch.ops.aten.chunk(tensor, num_chunks, dim)[indice].contiguous()
+
+
+def copy_wrapper(self, other):
+    return torch.ops.aten.copy_.default(self, other)
+
+
+def reduce_scatter_start(self, reduceOp: str, scatter_dim: int, group: List[int], tag: str = "", *,
+                         _buf=None, _scale=1.0, _out_dtype=None):
+    n = len(group)
+    assert self.size(scatter_dim) % n == 0
+    shape = list(self.shape)
+    shape[scatter_dim] //= n
+    if _fake(self):
+        return self.new_empty(shape, dtype=_out_dtype or self.dtype)
+    red = all_reduce_start(self, reduceOp, group)
+    me = list(group).index(dist.get_rank())
+    out = torch.chunk(red, n, scatter_dim)[me].contiguous()
+    if _scale != 1.0:
+        out = out * _scale
+    return out.to(_out_dtype or self.dtype)
+
+
+def reduce_scatter_end(self, reduceOp, scatter_dim, group, tag=""):
+    return self
+
+
+def all_to_all_start(tensor, gather_dim, scatter_dim, num_chunks, indice, ranks, tag="", *,
+                     _buf=None):
+    g = all_gather_start(tensor, gather_dim, ranks)
+    if _fake(tensor):
+        shape = list(g.shape)
+        shape[scatter_dim] //= num_chunks
+        return tensor.new_empty(shape)
+    return scatter_wrapper(g, num_chunks, scatter_dim, indice)
+
+
+def all_to_all_end(tensor, gather_dim, scatter_dim, num_chunks, indice, ranks, tag=""):
+    return tensor
+
+
+COMM_FUNCS = [all_reduce_start, all_gather_start, reduce_scatter_start, all_to_all_start]
+COMM_SYNC_FUNCS = [all_reduce_end, all_gather_end, reduce_scatter_end, all_to_all_end]
+CUSTOM_FUNCS = COMM_FUNCS + COMM_SYNC_FUNCS + [scatter_wrapper, copy_wrapper]

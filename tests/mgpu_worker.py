@@ -1,0 +1,276 @@
+"""Multi-GPU parity worker: one process per GPU (torchrun), compares every reshard kernel with the
+oracle on the same seeded inputs, bit for bit.  Launched by tests/test_gpu_multi.py and directly:
+
+    python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29531 \
+        tests/mgpu_worker.py [--bench]
+"""
+import argparse
+import os
+import sys
+import zlib
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from easydist_b200 import reshard, runtime  # noqa: E402
+from oracle import reshard_oracle as O  # noqa: E402  (tests may use the oracle as the checker)
+
+TORCH_DT = {"float32": torch.float32, "int64": torch.int64, "float16": torch.float16,
+            "bfloat16": torch.bfloat16, "int32": torch.int32, "uint8": torch.uint8,
+            "float64": torch.float64}
+
+
+def inputs_for(key, shape, dtype, world, lo=-8, hi=9):
+    """Integer-valued inputs of every rank (known to all ranks) so reductions are exact."""
+    out = []
+    for r in range(world):
+        rng = np.random.RandomState(zlib.crc32(key.encode()) % (2 ** 31 - 100000) + 1000 * r)
+        out.append(rng.randint(lo, hi, size=shape).astype(np.float32 if dtype == "bfloat16"
+                                                          else dtype))
+    return out
+
+
+def to_dev(x, dtype):
+    x = np.asarray(x)
+    t = torch.from_numpy(np.ascontiguousarray(x)).reshape(x.shape).cuda()
+    return t.to(TORCH_DT[dtype])
+
+
+def check_equal(got, want, what):
+    g = got.float().cpu().numpy() if got.dtype in (torch.bfloat16, torch.float16) else \
+        got.cpu().numpy()
+    w = want.astype(np.float32) if got.dtype in (torch.bfloat16, torch.float16) else want
+    if g.shape != tuple(w.shape) or not np.array_equal(g, w):
+        raise AssertionError(f"{what}: mismatch shape {g.shape} vs {w.shape}; "
+                             f"max|d|={np.abs(g.astype(np.float64) - w).max() if g.shape == w.shape else 'n/a'}")
+
+
+def run_cases(rank, world, group, tag=""):
+    n_ok = 0
+    shapes_ag = [((3, 4), 0), ((3, 4), 1), ((2, 3, 5), 2), ((7,), 0), ((64, 1024), 0),
+                 ((64, 1024), 1), ((5, 33), 1), ((2, 16, 128, 32), 2), ((1, 1, 16, 128), 2)]
+    for dtype in ("float32", "int64", "bfloat16", "uint8"):
+        for shape, dim in shapes_ag:
+            key = f"ag{tag}_{shape}_{dim}_{dtype}"
+            xs = inputs_for(key, shape, dtype, world, 0 if dtype == "uint8" else -8)
+            want = O.all_gather(xs, dim)[rank]
+            got = reshard.all_gather_start(to_dev(xs[rank], dtype), dim, group)
+            check_equal(got, want, key)
+            n_ok += 1
+    a2a = [((2, 4 * world), 0, 1), ((2 * world, 3), 1, 0), ((2, 3, 2 * world), 0, 2),
+           ((2, world, 5), 2, 1), ((2, 128, 16 * world), 0, 2), ((4, 128, 8 * world), 2, 0),
+           ((2, 32 * world, 128, 32), 0, 1), ((64 * world, 64), 1, 0)]
+    for dtype in ("float32", "bfloat16", "int64"):
+        for shape, g, s in a2a:
+            key = f"a2a{tag}_{shape}_{g}_{s}_{dtype}"
+            xs = inputs_for(key, shape, dtype, world)
+            want = O.all_to_all(xs, g, s)[rank]
+            got = reshard.all_to_all_start(to_dev(xs[rank], dtype), g, s, world, rank, group)
+            check_equal(got, want, key)
+            n_ok += 1
+    red_shapes = [((2 * world, 3), 0), ((3, 2 * world), 1), ((2, 3, world), 2),
+                  ((64 * world, 256), 0), ((16, 8 * world, 32), 1), ((1, 1024 * world), 1)]
+    for dtype in ("float32", "bfloat16", "float16", "int64", "int32", "float64"):
+        ops = ("sum", "max", "min") + (() if dtype.startswith("int") else ("avg",))
+        for op in ops:
+            for shape, dim in red_shapes:
+                key = f"rs{tag}_{shape}_{dim}_{dtype}_{op}"
+                # avg: multiples of `world` keep sum/world exact in every float dtype
+                xs = inputs_for(key, shape, dtype, world)
+                if op == "avg":
+                    xs = [x * world for x in xs]
+                want = O.reduce_scatter(xs, op, dim)[rank]
+                got = reshard.reduce_scatter_start(to_dev(xs[rank], dtype), op, dim, group)
+                check_equal(got, want, key)
+                n_ok += 1
+            for shape in [(5, 3), (), (1024,), (300, 1000), (1 << 20,)]:
+                key = f"ar{tag}_{shape}_{dtype}_{op}"
+                xs = inputs_for(key, shape, dtype, world)
+                if op == "avg":
+                    xs = [x * world for x in xs]
+                want = O.all_reduce(xs, op)[rank]
+                got = reshard.all_reduce_start(to_dev(xs[rank], dtype), op, group)
+                check_equal(got, want, key)
+                n_ok += 1
+    # fused scale + cast on reduce-scatter (gradient averaging into fp32)
+    xs = inputs_for("rs_cast", (8 * world, 64), "bfloat16", world)
+    want = O.reduce_scatter([x.astype(np.float32) for x in xs], "sum", 0)[rank] * 0.5
+    got = reshard.reduce_scatter_start(to_dev(xs[rank], "bfloat16"), "sum", 0, group, _scale=0.5,
+                                       _out_dtype=torch.float32)
+    check_equal(got, want, "rs_cast")
+    # halo exchange vs halo_padding (metashard/halo.py:33-55)
+    for shape, dim, halo in [((6, 5), 0, 2), ((4, 6, 3), 1, 1), ((3, 64), 1, 16)]:
+        xs = inputs_for(f"halo_{shape}", shape, "float32", world)
+        want = O.halo_padding(xs, halo, dim)[rank]
+        got = reshard.halo_exchange(to_dev(xs[rank], "float32"), dim, halo, group)
+        check_equal(got, want, f"halo {shape} {dim} {halo}")
+        n_ok += 1
+    return n_ok
+
+
+def run_p2p(rank, world, group):
+    """Partition P2P redistribution vs the oracle's restatement of sharding.py:336-474."""
+    n_ok = 0
+    mesh = np.arange(world).reshape(world)
+    g = np.arange(16 * 24, dtype=np.float32).reshape(16, 24)
+    for src, dst in [((O.S(0),), (O.S(1),)), ((O.S(1),), (O.S(0),)), ((O.S(0),), (O.R,)),
+                     ((O.R,), (O.S(1),))]:
+        loc = O.make_locals(g, mesh, src)
+        want = O.p2p_redistribute(loc, g.shape, mesh, src, dst)[rank]
+        sp = O.partitions_from_spec(src, g.shape, mesh)
+        tp = O.partitions_from_spec(dst, g.shape, mesh)
+        recv = O.gen_recv_meta(sp, tp).get(rank, [])
+        boxes = []
+        for it in recv:
+            s_part, t_part = sp[it.rank], tp[rank]
+            boxes.append((it.rank, [a - b for a, b in zip(it.start, s_part.start)],
+                          [a - b for a, b in zip(it.start, t_part.start)],
+                          [e - s for s, e in zip(it.start, it.end)]))
+        shapes = [[e - s for s, e in zip(p.start, p.end)] for p in sp]
+        dshape = [e - s for s, e in zip(tp[rank].start, tp[rank].end)]
+        got = reshard.box_exchange(to_dev(loc[rank], "float32"), dshape, boxes, shapes, group)
+        check_equal(got, want, f"p2p {src}->{dst}")
+        n_ok += 1
+    return n_ok
+
+
+def run_graph(rank, world, group):
+    """CUDA-graph capture + replay: epoch flags must keep working with static parameters."""
+    rt = runtime.get_runtime()
+    x = torch.zeros(64, 256, device="cuda")
+    buf_ag = rt.alloc(x.numel() * 4 * world)
+    buf_rs = rt.alloc(x.numel() * 4 * world)
+    buf_ar = rt.alloc(x.numel() * 4)
+
+    def step():
+        g = reshard.all_gather_start(x, 0, group, _buf=(buf_ag.offset, buf_ag.nbytes))
+        r = reshard.reduce_scatter_start(g, "sum", 0, group, _buf=(buf_rs.offset, buf_rs.nbytes))
+        a = reshard.all_reduce_start(r, "max", group, _buf=(buf_ar.offset, buf_ar.nbytes))
+        return g, r, a
+
+    def expect(vals):
+        g = np.concatenate([np.full((64, 256), v, np.float32) for v in vals])
+        return g, g[rank * 64:(rank + 1) * 64] * world, np.full((64, 256), max(vals) * world,
+                                                                np.float32)
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        x.fill_(float(rank + 1))
+        step()
+    torch.cuda.current_stream().wait_stream(s)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        outs = step()
+    for it in range(5):
+        x.fill_(float(rank + 1 + it))
+        graph.replay()
+        torch.cuda.synchronize()
+        for o, w in zip(outs, expect([r + 1 + it for r in range(world)])):
+            check_equal(o, w, f"graph replay {it}")
+    return 5
+
+
+def bench(rank, world, group):
+    rt = runtime.get_runtime()
+    res = []
+    sizes = [1 << k for k in range(10, 31, 2)]
+    for nbytes in sizes:
+        if nbytes * 2 > rt.heap_bytes // 8:
+            break
+        numel = nbytes // 2
+        shard = torch.randn(numel // world, device="cuda").bfloat16() if numel >= world else None
+        full = torch.randn(numel, device="cuda").bfloat16()
+        b1, b2, b3 = rt.alloc(nbytes), rt.alloc(nbytes), rt.alloc(nbytes)
+        nccl_out = torch.empty(numel, device="cuda", dtype=torch.bfloat16)
+        nccl_rs = torch.empty(numel // world, device="cuda", dtype=torch.bfloat16)
+
+        def timeit(f, iters=20):
+            for _ in range(3):
+                f()
+            dist.barrier()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(iters):
+                f()
+            e1.record()
+            torch.cuda.synchronize()
+            t = torch.tensor([e0.elapsed_time(e1) / iters], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return t.item()
+
+        row = {"bytes": nbytes}
+        f = (world - 1) / world
+        t = timeit(lambda: reshard.all_gather_start(shard, 0, group, _buf=(b1.offset, nbytes)))
+        row["ag_edb_GBs"] = nbytes * f / t / 1e6
+        t = timeit(lambda: dist.all_gather_into_tensor(nccl_out, shard))
+        row["ag_nccl_GBs"] = nbytes * f / t / 1e6
+        t = timeit(lambda: reshard.reduce_scatter_start(full, "sum", 0, group,
+                                                        _buf=(b2.offset, nbytes)))
+        row["rs_edb_GBs"] = nbytes * f / t / 1e6
+        t = timeit(lambda: dist.reduce_scatter_tensor(nccl_rs, full))
+        row["rs_nccl_GBs"] = nbytes * f / t / 1e6
+        t = timeit(lambda: reshard.all_reduce_start(full, "sum", group,
+                                                    _buf=(b2.offset, nbytes, b3.offset)))
+        row["ar_edb_GBs"] = 2 * nbytes * f / t / 1e6
+        row["ar_edb_us"] = t * 1e3
+        t = timeit(lambda: dist.all_reduce(full))
+        row["ar_nccl_GBs"] = 2 * nbytes * f / t / 1e6
+        row["ar_nccl_us"] = t * 1e3
+        res.append(row)
+        if rank == 0:
+            print("BENCH " + " ".join(f"{k}={v:.1f}" if isinstance(v, float) else f"{k}={v}"
+                                      for k, v in row.items()), flush=True)
+    return res
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--bench", action="store_true")
+    ap.add_argument("--heap-gb", type=float, default=8.0)
+    args = ap.parse_args()
+    rank = int(os.environ["RANK"])
+    world = int(os.environ["WORLD_SIZE"])
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    rt = runtime.init(rank, world, local, heap_bytes=int(args.heap_gb * (1 << 30)))
+    rt.set_option("spin_timeout_ms", 20000)
+    group = list(range(world))
+    n = run_cases(rank, world, group)
+    n += run_cases(rank, world, group, tag="b")  # second pass: epochs keep counting
+    n += run_p2p(rank, world, group)
+    n += run_graph(rank, world, group)
+    if world >= 4 and world % 2 == 0:
+        # 2-D mesh: groups along each mesh dim (ranks in mesh-coordinate order)
+        mesh = np.arange(world).reshape(2, world // 2)
+        coord = tuple(int(c) for c in np.argwhere(mesh == rank)[0])
+        for mdim in (0, 1):
+            grp = O.submesh_ranks(mesh, mdim, coord)
+            me = grp.index(rank)
+            xs = inputs_for(f"mesh{mdim}", (4 * len(grp), 6), "float32", world)
+            sub = [xs[r] for r in grp]
+            got = reshard.all_gather_start(to_dev(xs[rank], "float32"), 1, grp)
+            check_equal(got, O.all_gather(sub, 1)[me], f"2d mesh ag dim{mdim}")
+            got = reshard.reduce_scatter_start(to_dev(xs[rank], "float32"), "sum", 0, grp)
+            check_equal(got, O.reduce_scatter(sub, "sum", 0)[me], f"2d mesh rs dim{mdim}")
+            n += 2
+    torch.cuda.synchronize()
+    errs = rt.error_flags()
+    assert not any(errs), f"spin-wait timeouts recorded: {errs}"
+    dist.barrier()
+    if rank == 0:
+        print(f"MGPU_OK world={world} checks={n} launches={rt.launch_count()}", flush=True)
+    if args.bench:
+        bench(rank, world, group)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

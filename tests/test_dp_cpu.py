@@ -1,0 +1,111 @@
+"""Host-side logic of the data-parallel path with world_size 2 on CPU (gloo): tracing front-end,
+transform_ddp / transform_fsdp (compile_dp.py:55-198 equivalents), executor — against vanilla
+single-process PyTorch on the concatenated batch, the reference's own comparator
+(tests/test_torch/test_spmd.py:97-113, rtol=1e-4 atol=1e-5)."""
+import os
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+class Foo(torch.nn.Module):
+    """LayerNorm + Linear, the `Foo` model of tests/test_torch/test_spmd.py:31-40 (scaled down)."""
+
+    def __init__(self, d=32):
+        super().__init__()
+        self.norm = torch.nn.LayerNorm(d)
+        self.linear = torch.nn.Linear(d, d)
+
+    def forward(self, x):
+        return self.linear(self.norm(x)).relu()
+
+
+def train_step(input, model, opt):
+    out = model(input)
+    loss = out.mean()
+    loss.backward()
+    opt.step()
+    opt.zero_grad()
+    return loss
+
+
+def make_opt(kind, params):
+    if kind == "sgd":
+        return torch.optim.SGD(params, lr=0.1, momentum=0.9, foreach=True)
+    if kind == "sgd_plain":
+        return torch.optim.SGD(params, lr=0.1, foreach=True)
+    return torch.optim.Adam(params, lr=1e-2, foreach=True)
+
+
+def _worker(rank, world, port, mode, opt_kind, q):
+    os.environ["OMP_NUM_THREADS"] = "1"
+    torch.set_num_threads(1)
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank,
+                            world_size=world)
+    from easydist_b200 import api
+    from easydist_b200.device_mesh import set_device_mesh
+    from tests import gloo_ops
+    set_device_mesh([list(range(world))][0], ["dp"], rank=rank)
+    torch.manual_seed(0)
+    model = Foo()
+    ref_model = Foo()
+    ref_model.load_state_dict(model.state_dict())
+    opt = make_opt(opt_kind, model.parameters())
+    ref_opt = make_opt(opt_kind, ref_model.parameters())
+    g = torch.Generator().manual_seed(123)
+    batches = [torch.randn(world * 4, 32, generator=g) for _ in range(3)]
+    compiled = api._compile_dp(train_step, mode, "fake", (batches[0][rank * 4:(rank + 1) * 4], model,
+                                                         opt), {}, ops=gloo_ops, native=False)
+    ok = True
+    msg = ""
+    for b in batches:
+        loss = compiled(b[rank * 4:(rank + 1) * 4], model, opt)
+        ref_loss = train_step(b, ref_model, ref_opt)
+        # local loss is the mean over the local micro-batch; the global mean is their average
+        loss_all = loss.detach().clone()
+        dist.all_reduce(loss_all)
+        loss_all /= world
+        if not torch.allclose(loss_all, ref_loss.detach(), rtol=1e-4, atol=1e-5):
+            ok, msg = False, f"loss {loss_all} vs {ref_loss}"
+    params = compiled.named_parameters()
+    for name, p_ref in ref_model.named_parameters():
+        p = params[name]
+        if mode == "zero3":
+            parts = [torch.empty_like(p) for _ in range(world)]
+            dist.all_gather(parts, p.contiguous())
+            p = torch.cat(parts).view(p_ref.shape)
+        if not torch.allclose(p, p_ref.detach(), rtol=1e-4, atol=1e-5):
+            ok, msg = False, f"param {name} differs: {(p - p_ref).abs().max()}"
+    hist = compiled.info["comm_nodes"]
+    if rank == 0:
+        q.put((ok, msg, hist))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("mode,opt_kind", [("ddp", "sgd"), ("ddp", "sgd_plain"), ("zero2", "sgd"),
+                                           ("zero3", "sgd"), ("zero3", "sgd_plain"),
+                                           ("zero2", "sgd_plain")])
+def test_dp_modes_match_vanilla(mode, opt_kind):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29650 + abs(hash((mode, opt_kind))) % 200
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, mode, opt_kind, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(180)
+    assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
+    ok, msg, hist = q.get(timeout=5)
+    assert ok, msg
+    if mode == "ddp":
+        assert hist.get("all_reduce_start", 0) == 4      # one per parameter
+    if mode in ("zero2", "zero3"):
+        assert hist.get("reduce_scatter_start", 0) == 4
+        assert hist.get("all_gather_start", 0) >= 4

@@ -1,0 +1,140 @@
+"""Single-GPU parity tests (B200): every call goes through the C-ABI (ctypes -> libedb.so).
+  * local reshard ops and n=1 collectives vs the oracle (bit-exact)
+  * tcgen05 GEMM vs a plain PyTorch fp32 reference (floating point: tolerance stated below)
+"""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def rt():
+    from easydist_b200 import runtime
+    if not torch.cuda.is_available():
+        pytest.skip("no GPU")
+    r = runtime.init(rank=0, world=1, device=0, heap_bytes=2 << 30) \
+        if not runtime.is_initialized() else runtime.get_runtime()
+    return r
+
+
+def _np(t):
+    return t.float().cpu().numpy() if t.dtype in (torch.bfloat16, torch.float16) else t.cpu().numpy()
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.int64, torch.uint8])
+def test_scatter_matches_oracle(rt, dtype):
+    from easydist_b200 import reshard
+    from oracle import reshard_oracle as O
+    rng = np.random.RandomState(0)
+    for shape, dim, n in [((8, 6, 10), 0, 2), ((8, 6, 10), 1, 3), ((8, 6, 10), 2, 4), ((7,), 0, 3),
+                          ((5, 4096), 1, 8), ((4, 128, 1024), 2, 4), ((9, 2), 0, 4), ((0, 4), 0, 2)]:
+        x = rng.randint(0, 100, size=shape).astype(np.float32)
+        xt = torch.from_numpy(x).cuda().to(dtype)
+        pieces = O.chunk(x, n, dim)
+        for i in range(len(pieces)):
+            got = reshard.scatter_wrapper(xt, n, dim, i)
+            assert np.array_equal(_np(got), O.scatter(x, n, dim, i)), (shape, dim, n, i)
+        if len(pieces) < n:
+            with pytest.raises(IndexError):
+                reshard.scatter_wrapper(xt, n, dim, n - 1)
+
+
+def test_copy_wrapper(rt):
+    from easydist_b200 import reshard
+    for n in (1, 17, 4096, 1000003):
+        a = torch.zeros(n, device="cuda")
+        b = torch.randn(n, device="cuda")
+        assert reshard.copy_wrapper(a, b) is a
+        assert torch.equal(a, b)
+    a = torch.zeros(4, 4, device="cuda", dtype=torch.float32)
+    b = torch.ones(4, device="cuda", dtype=torch.bfloat16)
+    reshard.copy_wrapper(a, b)  # broadcasting + cast goes through aten.copy_
+    assert torch.equal(a, torch.ones(4, 4, device="cuda"))
+
+
+def test_collectives_world1_are_identities(rt):
+    from easydist_b200 import reshard
+    g = [0]
+    for dtype in (torch.float32, torch.bfloat16, torch.int64):
+        x = torch.randint(-8, 9, (4, 6, 8), device="cuda").to(dtype)
+        for d in range(3):
+            assert torch.equal(reshard.all_gather_start(x, d, g), x)
+            assert torch.equal(reshard.reduce_scatter_start(x, "sum", d, g), x)
+        assert torch.equal(reshard.all_reduce_start(x, "sum", g), x)
+        assert torch.equal(reshard.all_reduce_start(x, "max", g), x)
+        assert torch.equal(reshard.all_to_all_start(x, 0, 2, 1, 0, g), x)
+    xb = torch.randint(-8, 9, (16, 64), device="cuda").bfloat16()
+    y = reshard.reduce_scatter_start(xb, "sum", 1, g, _scale=0.25, _out_dtype=torch.float32)
+    assert torch.equal(y, xb.float() * 0.25)
+
+
+def test_box_copy_general_strides(rt):
+    """Strided N-D boxes (Partition boxes, sharding.py:427-446) vs numpy slicing."""
+    from easydist_b200 import _lib
+    from easydist_b200._lib import check, i64_array
+    rng = np.random.RandomState(1)
+    src = rng.randint(0, 1000, size=(6, 10, 14)).astype(np.int32)
+    s = torch.from_numpy(src).cuda()
+    for (lo, ext) in [((1, 2, 3), (4, 5, 6)), ((0, 0, 0), (6, 10, 14)), ((5, 9, 13), (1, 1, 1)),
+                      ((0, 3, 0), (6, 2, 14)), ((2, 0, 1), (3, 10, 9))]:
+        d = torch.zeros(ext, dtype=torch.int32, device="cuda")
+        sstr = [st * 4 for st in s.stride()]
+        dstr = [st * 4 for st in d.stride()]
+        off = sum(l * st for l, st in zip(lo, sstr))
+        check(rt.lib.edb_box_copy_local(d.data_ptr(), i64_array(dstr), s.data_ptr() + off,
+                                        i64_array(sstr), i64_array(ext), 3, 4, rt.stream()))
+        want = src[lo[0]:lo[0] + ext[0], lo[1]:lo[1] + ext[1], lo[2]:lo[2] + ext[2]]
+        assert np.array_equal(d.cpu().numpy(), want), (lo, ext)
+
+
+GEMM_SHAPES = [(128, 128, 64), (128, 256, 128), (256, 512, 256), (384, 200, 136), (100, 72, 40),
+               (4096, 1024, 1024), (1024, 4096, 1024), (512, 1024, 4096), (640, 3072, 1024)]
+
+
+@pytest.mark.parametrize("a_k", [True, False])
+@pytest.mark.parametrize("b_k", [True, False])
+def test_gemm_matches_fp32_reference(rt, a_k, b_k):
+    """bf16 x bf16 -> fp32 accumulate -> bf16.  Tolerance: the fp32 reference rounded to bf16 may
+    differ from ours by accumulation order only: |err| <= 2^-7 * |ref| + 1e-2 (1 bf16 ulp)."""
+    from easydist_b200 import gemm
+    torch.manual_seed(0)
+    for (M, N, K) in GEMM_SHAPES:
+        if (not a_k and M % 8) or N % 8 or K % 8:
+            continue
+        A = torch.randn(M, K, device="cuda", dtype=torch.bfloat16)
+        B = torch.randn(K, N, device="cuda", dtype=torch.bfloat16)
+        a = A if a_k else A.t().contiguous().t()
+        b = B.t().contiguous().t() if b_k else B
+        gemm.reset_stats()
+        c = gemm.mm(a, b)
+        assert gemm.stats()["edb_gemm"] == 1, (M, N, K, gemm.stats())
+        ref = A.float() @ B.float()
+        err = (c.float() - ref).abs()
+        tol = ref.abs() * 2 ** -7 + 1e-2
+        assert bool((err <= tol).all()), (M, N, K, float(err.max()))
+
+
+def test_gemm_exact_on_integer_inputs(rt):
+    """Size-independent property: small-integer operands make every product and partial sum
+    exactly representable, so the result must equal the fp32 reference bit for bit."""
+    from easydist_b200 import gemm
+    torch.manual_seed(1)
+    for (M, N, K) in [(4096, 1024, 1024), (256, 4096, 512)]:
+        A = torch.randint(-2, 3, (M, K), device="cuda").bfloat16()
+        B = torch.randint(-2, 3, (K, N), device="cuda").bfloat16()
+        c = gemm.mm(A, B.t().contiguous().t())
+        ref = (A.float() @ B.float())
+        assert float(ref.abs().max()) < 256  # representable in bf16
+        assert torch.equal(c.float(), ref)
+
+
+def test_gemm_unsupported_shapes_route_to_aten(rt):
+    from easydist_b200 import gemm
+    A = torch.randn(64, 50, device="cuda", dtype=torch.bfloat16)   # K % 8 != 0
+    B = torch.randn(50, 24, device="cuda", dtype=torch.bfloat16)
+    gemm.reset_stats()
+    c = gemm.mm(A, B)
+    assert gemm.stats()["aten_mm"] == 1
+    assert torch.allclose(c.float(), (A.float() @ B.float()), atol=0.5, rtol=0.05)
