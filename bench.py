@@ -1,0 +1,316 @@
+#!/usr/bin/env python
+"""bench.py — train_step throughput of the data-parallel hot path (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this backend (libedb.so kernels)
+    python bench.py --impl reference --gpus N ...            # the reference's CPU path (oracle port)
+
+Workload (config.workload): GPT-2 medium (L24 H1024 16 heads), bf16 params/activations, 512-token
+synthetic sequences, 8 sequences per GPU (weak scaling), SGD(momentum 0.9, foreach) — BASELINE.json
+configs[1] ("GPT-2 medium auto-SPMD, bf16, synthetic 512-seq batches").  One step = forward +
+backward + optimizer update of one global batch through `easydist_compile`'s compiled graph.
+
+Printed keys (one JSON line from rank 0): see the bench contract in the task statement;
+`value` = samples/s with inputs resident in HBM, `e2e` = the same through the public API with
+pinned-host inputs copied H2D and the loss read back D2H every step, `roofline` = the dominant
+kernel (tcgen05 GEMM) against the measured bf16 peak, `cpu_baseline` = the oracle port on the
+host cores (bounded sample).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="edb", choices=["edb", "reference"])
+    ap.add_argument("--model", default="gpt2-medium")
+    ap.add_argument("--mode", default="zero3", choices=["ddp", "zero2", "zero3"])
+    ap.add_argument("--batch-per-gpu", type=int, default=8)
+    ap.add_argument("--seq", type=int, default=512)
+    ap.add_argument("--attn", default="sdpa", choices=["sdpa", "unfused"])
+    ap.add_argument("--no-cuda-graph", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sample-seqs", type=int, default=2)
+    ap.add_argument("--heap-gb", type=float, default=12.0)
+    return ap.parse_args()
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return {"bf16_tflops": p["bf16_tflops"], "bf16_tflops_sustained": p["bf16_tflops_sustained"],
+                "hbm_gbs": p["hbm_gbs"], "source": "measured (MEASURED_PEAKS.json)"}
+    return {"bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "hbm_gbs": 6650.0,
+            "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (recipe's clocks line)."""
+
+    def __init__(self, index=0):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "200",
+                 "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL,
+                text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names)
+                   if any(len(r) > 3 + i and r[3 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+# ---- the reference arm / cpu baseline: oracle port on host cores ------------------------------------
+
+
+def cpu_train_step_throughput(args, n_seqs, steps=1):
+    """The reference's path on CPU is ATen-CPU compute + gloo collectives driven by the FX graph
+    (SURVEY.md §8d).  The oracle port runs the same train step (same model, fp32 on CPU — the
+    reference's CPU runs are fp32) on the host cores; at world 1 there is no collective."""
+    import torch
+    from oracle import train_oracle
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    t, loss = train_oracle.time_cpu_train_step(args.model, args.attn, n_seqs, args.seq, steps)
+    return {"value": n_seqs * steps / t, "unit": "samples/s", "cores": cores, "kind": "port",
+            "sample": f"{steps} step(s) of {n_seqs} x {args.seq}-token sequences, fp32, "
+                      f"torch CPU eager ({cores} threads), {t:.1f} s", "loss": loss}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    base = cpu_train_step_throughput(args, args.cpu_sample_seqs, steps=max(1, min(args.steps, 2)))
+    line = {
+        "impl": "reference", "metric": "train_step_throughput", "value": base["value"],
+        "unit": "samples/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * args.cpu_sample_seqs / base["value"], "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, args.gpus),
+        "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": base["value"], "unit": "samples/s", "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, world):
+    return {"workload": f"{args.model} train_step (fwd+bwd+SGD-momentum), bf16, seq {args.seq}, "
+                        f"{args.batch_per_gpu} seq/GPU",
+            "global_batch": args.batch_per_gpu * world, "seq_len": args.seq,
+            "parallelism": f"{args.mode} dp{world}", "attention": args.attn,
+            "l2_policy": "per-step working set (weights+activations > 2 GB) exceeds the 126 MB L2",
+            "cuda_graph": not args.no_cuda_graph}
+
+
+# ---- this backend -----------------------------------------------------------------------------------------
+
+
+def gemm_roofline(torch, gemm, calls, peaks, sustained):
+    """Dominant kernel = the tcgen05 GEMM.  Replays the step's GEMM launches (exact shapes and
+    operand layouts recorded from the compiled graph) back to back on the current stream with
+    CUDA events around the whole list; operands of consecutive launches differ and sum to far more
+    than L2.  achieved = algorithmic FLOPs (2*M*N*K per launch) / measured time."""
+    if not calls:
+        return None
+    ops = []
+    flops = 0
+    for (M, N, K, a_k, b_k) in calls:
+        A = torch.randn(M, K, device="cuda", dtype=torch.bfloat16)
+        B = torch.randn(K, N, device="cuda", dtype=torch.bfloat16)
+        a = A if a_k else A.t().contiguous().t()
+        b = B.t().contiguous().t() if b_k else B
+        ops.append((a, b))
+        flops += 2 * M * N * K
+    for a, b in ops[:8]:
+        gemm.mm(a, b)
+    torch.cuda.synchronize()
+    reps = 3
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        for a, b in ops:
+            gemm.mm(a, b)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    achieved = flops / ms / 1e9  # TFLOP/s
+    peak = peaks["bf16_tflops_sustained"] if sustained else peaks["bf16_tflops"]
+    return {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+            "frac": achieved / peak, "traffic": None, "kernel": "edb::k_gemm_bf16",
+            "launches_per_step": len(calls), "avg_launch_us": 1e3 * ms / len(calls),
+            "gemm_ms_per_step": ms, "flops_per_step": flops,
+            "peak_source": peaks["source"] + (", sustained figure (kernel runs inside a long step)"
+                                              if sustained else ", burst figure")}
+
+
+def run_edb(args):
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert world == args.gpus, f"launched with WORLD_SIZE={world} but --gpus {args.gpus}"
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from easydist_b200 import gemm, runtime
+    from easydist_b200.api import easydist_compile
+    from easydist_b200.device_mesh import set_device_mesh
+    from easydist_b200.workloads import (GPT2, GPT2_CONFIGS, gpt2_train_step, synthetic_tokens,
+                                         train_flops_per_step)
+    import dataclasses
+    rt = runtime.init(rank, world, local, heap_bytes=int(args.heap_gb * (1 << 30)))
+    set_device_mesh(list(range(world)), ["dp"], rank=rank)
+    cfg = dataclasses.replace(GPT2_CONFIGS[args.model], attn=args.attn,
+                              block_size=max(args.seq, GPT2_CONFIGS[args.model].block_size))
+    torch.manual_seed(0)
+    model = GPT2(cfg).to(device="cuda", dtype=torch.bfloat16)
+    opt = torch.optim.SGD(model.parameters(), lr=1e-3, momentum=0.9, foreach=True)
+    B, S = args.batch_per_gpu, args.seq
+    n_batches = 4
+    host = [synthetic_tokens(cfg, B, S, seed=1000 * b + rank) for b in range(n_batches)]
+    host = [(t.pin_memory(), y.pin_memory()) for t, y in host]
+    dev = [(t.cuda(), y.cuda()) for t, y in host]
+    step_fn = easydist_compile(gpt2_train_step, parallel_mode=args.mode, tracing_mode="fake",
+                               cuda_graph=not args.no_cuda_graph)
+    launches0 = rt.launch_count()
+    gemm.reset_stats()
+    t0 = time.time()
+    loss = step_fn(dev[0][0], dev[0][1], model, opt)  # compile + eager warm-up (+ graph capture)
+    torch.cuda.synchronize()
+    compile_s = time.time() - t0
+    info = step_fn.compiled_func.info
+    # kernels of ours per step: counted on the eager warm-up step (graph replays launch the same)
+    stats = gemm.stats()
+    passes = 1 if args.no_cuda_graph else 2  # warm-up + capture both go through the host calls
+    launches_per_step = (rt.launch_count() - launches0) // passes
+    gemm_calls_per_step = stats["edb_gemm"] // passes
+    aten_mm_per_step = stats["aten_mm"] // passes
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(n_steps, e2e):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        last = None
+        for i in range(n_steps):
+            if e2e:
+                t_h, y_h = host[i % n_batches]
+                t_d = t_h.to("cuda", non_blocking=True)
+                y_d = y_h.to("cuda", non_blocking=True)
+                last = step_fn(t_d, y_d, model, opt)
+                last = float(last)  # device -> host read of the step's result
+            else:
+                t_d, y_d = dev[i % n_batches]
+                last = step_fn(t_d, y_d, model, opt)
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item(), float(last)
+
+    for _ in range(max(3, args.warmup)):
+        step_fn(dev[0][0], dev[0][1], model, opt)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms_total, loss_v = timed(args.steps, e2e=False)
+    clocks = sampler.stop() if rank == 0 else None
+    ms_e2e, _ = timed(args.steps, e2e=True)
+    errs = rt.error_flags()
+    assert not any(errs), f"collective spin-wait timeouts: {errs}"
+    gbatch = B * world
+    value = gbatch * args.steps / (ms_total / 1e3)
+    e2e_value = gbatch * args.steps / (ms_e2e / 1e3)
+    ms_per_step = ms_total / args.steps
+    peaks = measured_peaks()
+    # GEMM shapes of one step, recorded by the dispatcher during the eager warm-up
+    calls = gemm.recorded_calls()[:gemm_calls_per_step]
+    roof = gemm_roofline(torch, gemm, calls, peaks, sustained=True) if rank == 0 else None
+    step_flops = train_flops_per_step(cfg, B, S)
+    line = {
+        "metric": "train_step_throughput", "value": value, "unit": "samples/s", "n_gpus": world,
+        "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_per_step,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+        "data": "synthetic", "config": workload_config(args, world),
+        "tokens_per_s": value * S,
+        "model_tflops_per_gpu": step_flops / (ms_per_step / 1e3) / 1e12,
+        "e2e": {"value": e2e_value, "unit": "samples/s",
+                "h2d_bytes_per_step": 2 * B * S * 8, "d2h_bytes_per_step": 2,
+                "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": launches_per_step * args.steps,
+        "gpu_launches_per_step": launches_per_step,
+        "dispatch": {"edb_gemm_per_step": gemm_calls_per_step, "aten_mm_per_step": aten_mm_per_step,
+                     "comm_nodes": info.get("comm_nodes"), "symm_bytes": info.get("symm_bytes")},
+        "clocks": clocks, "loss": loss_v, "compile_s": compile_s,
+    }
+    if roof:
+        roof["share_of_step"] = roof["gemm_ms_per_step"] / ms_per_step
+        line["roofline"] = roof
+    if rank == 0:
+        if not args.no_cpu_baseline and world == 1:
+            try:
+                line["cpu_baseline"] = {k: v for k, v in cpu_train_step_throughput(
+                    args, args.cpu_sample_seqs).items() if k != "loss"}
+            except Exception as e:  # the baseline must never sink the measurement
+                line["cpu_baseline"] = {"error": repr(e)}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_edb(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -136,7 +136,7 @@ struct ReduceDesc {
 int make_box(Box* out, const void* src, const int64_t* src_strides, void* dst,
              const int64_t* dst_strides, const int64_t* extents, int ndim, int elem_size, int peer);
 int fill_flagctx(FlagCtx* f, int gid);
-int grid_for_bytes(size_t bytes, int threads);
+int grid_for_bytes(size_t bytes, int threads, int max_ctas_per_sm);
 
 inline size_t dtype_size(int dt) {
   switch (dt) {

@@ -347,7 +347,7 @@ struct ReduceLaunch {
 };
 
 template <typename In, typename Out, int OP>
-__global__ void __launch_bounds__(kThreads) k_reduce(const __grid_constant__ ReduceLaunch L) {
+__global__ void __launch_bounds__(kThreads, 3) k_reduce(const __grid_constant__ ReduceLaunch L) {
   __shared__ uint64_t s_q;
   __shared__ int s_last;
   const ReduceDesc& d = L.d;
@@ -378,14 +378,26 @@ __global__ void __launch_bounds__(kThreads) k_reduce(const __grid_constant__ Red
 
 // ---- host helpers --------------------------------------------------------------------------------
 
-int grid_for_bytes(size_t bytes, int threads) {
+// Kernels whose CTAs spin on flags written by other CTAs (of this or a peer GPU) must be fully
+// co-resident, otherwise resident CTAs wait forever for CTAs that cannot be scheduled.  The grid
+// is therefore capped by the occupancy of the exact kernel being launched.
+int grid_for_bytes(size_t bytes, int threads, int max_ctas_per_sm) {
   Runtime& r = rt();
   const size_t per_cta = (size_t)threads * 16 * 4;
   size_t want = (bytes + per_cta - 1) / per_cta;
-  const size_t cap = (size_t)r.sm_count * (size_t)std::max<int64_t>(1, r.copy_ctas_per_sm);
+  int64_t per_sm = std::max<int64_t>(1, r.copy_ctas_per_sm);
+  if (max_ctas_per_sm > 0 && per_sm > max_ctas_per_sm) per_sm = max_ctas_per_sm;
+  const size_t cap = (size_t)r.sm_count * (size_t)per_sm;
   if (want > cap) want = cap;
   if (want < 1) want = 1;
   return (int)want;
+}
+
+template <typename K> static int occupancy_of(K kernel) {
+  int n = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, kThreads, 0) != cudaSuccess || n < 1)
+    n = 1;
+  return n;
 }
 
 static int pick_vec(uintptr_t bits) {
@@ -520,20 +532,28 @@ static size_t box_bytes(const Box& b) {
 static int launch_gather(const GatherDesc& d, bool flags, cudaStream_t st) {
   size_t bytes = 0;
   for (int b = 0; b < d.n_boxes; ++b) bytes += box_bytes(d.box[b]);
-  const int grid = grid_for_bytes(bytes, kThreads);
+  static const int occ_gather = occupancy_of(k_gather);
+  const int grid = grid_for_bytes(bytes, kThreads, flags ? occ_gather : 0);
   if (flags) k_gather<<<grid, kThreads, 0, st>>>(d);
   else k_local_copy<<<grid, kThreads, 0, st>>>(d);
   count_launch();
   return cuda_check(cudaGetLastError(), "reshard kernel launch");
 }
 
+template <typename In, typename Out, int OP>
+static void launch_reduce_kernel(const ReduceLaunch& L, size_t bytes, cudaStream_t st) {
+  static const int occ = occupancy_of(k_reduce<In, Out, OP>);
+  const int grid = grid_for_bytes(bytes, kThreads, occ);
+  k_reduce<In, Out, OP><<<grid, kThreads, 0, st>>>(L);
+}
+
 template <typename In, typename Out>
-static int launch_reduce_op(const ReduceLaunch& L, int grid, cudaStream_t st) {
+static int launch_reduce_op(const ReduceLaunch& L, size_t bytes, cudaStream_t st) {
   switch (L.d.redop) {
     case EDB_SUM:
-    case EDB_AVG: k_reduce<In, Out, EDB_SUM><<<grid, kThreads, 0, st>>>(L); break;
-    case EDB_MAX: k_reduce<In, Out, EDB_MAX><<<grid, kThreads, 0, st>>>(L); break;
-    case EDB_MIN: k_reduce<In, Out, EDB_MIN><<<grid, kThreads, 0, st>>>(L); break;
+    case EDB_AVG: launch_reduce_kernel<In, Out, EDB_SUM>(L, bytes, st); break;
+    case EDB_MAX: launch_reduce_kernel<In, Out, EDB_MAX>(L, bytes, st); break;
+    case EDB_MIN: launch_reduce_kernel<In, Out, EDB_MIN>(L, bytes, st); break;
     default: return set_error(EDB_E_INVALID, "bad reduce op %d", L.d.redop);
   }
   count_launch();
@@ -555,7 +575,7 @@ static int launch_reduce(ReduceLaunch& L, cudaStream_t st) {
   L.vec = ((bits & 15) == 0 && (obits & (oalign - 1)) == 0) ? 1 : 0;
   const size_t bytes = (size_t)(d.inner * d.ext[0] * d.ext[1] * d.ext[2] * d.ext[3]) * d.n_src +
                        (d.has_in ? box_bytes(d.in) : 0);
-  const int grid = grid_for_bytes(bytes, kThreads);
+  const size_t grid = bytes;  // the launcher sizes the grid from the byte count + occupancy
   const int key = d.dtype * 16 + d.out_dtype;
   switch (key) {
     case EDB_F32 * 16 + EDB_F32: return launch_reduce_op<float, float>(L, grid, st);

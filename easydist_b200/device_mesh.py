@@ -69,7 +69,7 @@ _MESH = None
 
 
 def set_device_mesh(mesh, dim_names=None, rank=None):
-    """Accepts an array of ranks, a shape tuple (ranks 0..n-1 row-major), a torch DeviceMesh or
+    """Accepts an array/list of ranks, a shape TUPLE (ranks 0..n-1 row-major), a torch DeviceMesh or
     the reference's NDDeviceMesh (duck typed: `.mesh` tensor + `.mesh_dim_names`)."""
     global _MESH
     if isinstance(mesh, DeviceMesh):
@@ -80,7 +80,7 @@ def set_device_mesh(mesh, dim_names=None, rank=None):
         arr = np.asarray(mesh.mesh.cpu().numpy() if hasattr(mesh.mesh, "cpu") else mesh.mesh)
         _MESH = DeviceMesh(arr, names, rank)
         return _MESH
-    if isinstance(mesh, (tuple, list)) and all(isinstance(v, int) for v in mesh) and \
+    if isinstance(mesh, tuple) and all(isinstance(v, int) for v in mesh) and \
             dim_names is not None and len(dim_names) == len(mesh):
         arr = np.arange(int(np.prod(mesh))).reshape(mesh)
         _MESH = DeviceMesh(arr, dim_names, rank)

@@ -15,6 +15,7 @@ from ._lib import check
 from .runtime import get_runtime
 
 _stats = {"edb_gemm": 0, "aten_mm": 0, "unsupported": {}}
+_calls = []  # (M, N, K, a_kmajor, b_kmajor) of the native launches since reset_stats()
 
 
 def stats():
@@ -26,6 +27,11 @@ def reset_stats():
     _stats["edb_gemm"] = 0
     _stats["aten_mm"] = 0
     _stats["unsupported"] = {}
+    del _calls[:]
+
+
+def recorded_calls():
+    return list(_calls)
 
 
 def _operand_layout(t, inner_is_dim1):
@@ -84,6 +90,8 @@ def mm(a, b):
     check(lib.edb_gemm_bf16(out.data_ptr(), a.data_ptr(), b.data_ptr(), M, N, K, lda, ldb, N,
                             1 if a_k else 0, 1 if b_k else 0, 0, stream))
     _stats["edb_gemm"] += 1
+    if len(_calls) < 8192:
+        _calls.append((M, N, K, bool(a_k), bool(b_k)))
     return out
 
 

@@ -240,7 +240,7 @@ def main():
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     rt = runtime.init(rank, world, local, heap_bytes=int(args.heap_gb * (1 << 30)))
-    rt.set_option("spin_timeout_ms", 20000)
+    rt.set_option("spin_timeout_ms", 4000)
     group = list(range(world))
     n = run_cases(rank, world, group)
     n += run_cases(rank, world, group, tag="b")  # second pass: epochs keep counting
