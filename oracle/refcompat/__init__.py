@@ -41,11 +41,11 @@ def _torch_shims():
         names = {}
 
     def _Partial(reduce_op="sum"):
-        return pt_new.Partial(names.get(reduce_op, reduce_op))
+        op = names.get(reduce_op, reduce_op)
+        return pt_new.Partial(op if isinstance(op, str) else "sum")
 
     for mod in (pt_new, pt_old):
-        if not hasattr(mod, "_Partial"):
-            mod._Partial = _Partial
+        mod._Partial = _Partial  # 2.11 keeps a `_Partial` alias that no longer takes reduce_op
 
     # (5) CPU plumbing: compile_auto.py:126 queries the CUDA device unconditionally
     if not torch.cuda.is_available():

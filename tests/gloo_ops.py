@@ -11,9 +11,24 @@ from torch._subclasses.fake_tensor import FakeTensor
 _GROUPS = {}
 
 
+def init_groups(mesh):
+    """dist.new_group is collective over the WORLD: create every mesh-dim sub-group on every rank
+    in one global order before any op needs it (mesh: numpy array of ranks)."""
+    import numpy as np
+    mesh = np.asarray(mesh)
+    for mdim in range(mesh.ndim):
+        moved = np.moveaxis(mesh, mdim, -1).reshape(-1, mesh.shape[mdim])
+        for row in moved:
+            key = tuple(int(r) for r in row)
+            if key not in _GROUPS:
+                _GROUPS[key] = dist.new_group(list(key), backend="gloo")
+
+
 def _pg(ranks):
     key = tuple(ranks)
     if key not in _GROUPS:
+        if len(key) != dist.get_world_size():
+            raise RuntimeError(f"group {key} was not created by init_groups(mesh)")
         _GROUPS[key] = dist.new_group(list(ranks), backend="gloo")
     return _GROUPS[key]
 

@@ -1,0 +1,155 @@
+"""Reference-in-the-loop parity worker (CPU container only; needs /root/reference).
+
+Runs the UNMODIFIED reference's auto path (annotation -> MetaIR -> AutoFlow ILP) on 2 gloo ranks
+twice on the same model, inputs and plan:
+   A. with the reference's own lowering + NCCL/gloo functional collectives (sharding.py), and
+   B. with `compile_auto.sharding_transform` rebound to easydist_b200.lowering.sharding_transform
+      (the drop-in hook of INTEGRATION.md §3), comm callables bound to tests/gloo_ops.py because
+      the product ops need a GPU,
+and compares both with vanilla PyTorch step by step (outputs, params, optimizer state), i.e. the
+reference's own comparator tests/test_torch/test_spmd.py:54-113.  Optionally records the plan and
+the traced graph as a fixture for the GPU box (tests/golden/auto_plan_*.pt).
+"""
+import copy
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+
+
+class Foo(torch.nn.Module):
+    def __init__(self, d=64):
+        super().__init__()
+        self.norm = torch.nn.LayerNorm(d)
+        self.linear = torch.nn.Linear(d, d)
+
+    def forward(self, x):
+        return self.linear(self.norm(x)).relu()
+
+
+def train_step(input, model, opt):
+    out = model(input)
+    loss = out.mean()
+    loss.backward()
+    opt.step()
+    opt.zero_grad()
+    return out
+
+
+def main():
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    mesh_shape = tuple(int(v) for v in os.environ.get("EDB_TEST_MESH", str(world)).split("x"))
+    record = os.environ.get("EDB_RECORD", "")
+    torch.set_num_threads(1)
+    dist.init_process_group("gloo")
+    from oracle import refcompat
+    refcompat.install()
+    from easydist import easydist_setup
+    from easydist.torch.api import easydist_compile
+    from easydist.torch.device_mesh import set_device_mesh
+    import easydist.torch.compile_auto as ref_auto
+    from torch.distributed.device_mesh import DeviceMesh
+    easydist_setup(backend="torch", device="cpu", allow_tf32=False)
+    names = [f"spmd{i}" for i in range(len(mesh_shape))]
+    tmesh = DeviceMesh("cpu", torch.arange(world).reshape(mesh_shape), mesh_dim_names=names)
+    set_device_mesh(tmesh)
+
+    from easydist_b200 import lowering, metair
+    from easydist_b200.device_mesh import set_device_mesh as edb_set_mesh
+    from tests import gloo_ops
+    my_mesh = edb_set_mesh(torch.arange(world).reshape(mesh_shape).numpy(), names, rank=rank)
+    gloo_ops.init_groups(my_mesh.mesh)
+
+    torch.manual_seed(42)
+    model0 = Foo()
+    g = torch.Generator().manual_seed(7)
+    batches = [torch.randn(16, 64, generator=g) for _ in range(3)]
+
+    def run(variant):
+        model = copy.deepcopy(model0)
+        opt = torch.optim.SGD(model.parameters(), lr=0.1, momentum=0.9, foreach=True)
+        saved = {}
+        if variant == "B":
+            orig = ref_auto.sharding_transform
+
+            def mine(fx_module, opt_strategy, state_io_map):
+                if record and rank == 0:
+                    saved["plan"] = metair.plan_to_json(metair.plan_from_reference(opt_strategy))
+                return lowering.sharding_transform(fx_module, opt_strategy, state_io_map,
+                                                   ops=gloo_ops, mesh=my_mesh)
+            ref_auto.sharding_transform = mine
+        try:
+            step = easydist_compile(train_step, "auto", "fake", cuda_graph=False)
+            outs = [step(b, model, opt).detach().clone() for b in batches]
+        finally:
+            if variant == "B":
+                ref_auto.sharding_transform = orig
+        cf = step.compiled_func
+        hist = {}
+        for n in cf.graph.graph.nodes:
+            if n.op == "call_function":
+                nm = getattr(n.target, "__name__", str(n.target))
+                if any(k in nm for k in ("all_", "reduce_scatter", "scatter_wrapper", "copy_wrapper")):
+                    hist[nm] = hist.get(nm, 0) + 1
+        return outs, cf, hist, saved
+
+    # vanilla
+    vmodel = copy.deepcopy(model0)
+    vopt = torch.optim.SGD(vmodel.parameters(), lr=0.1, momentum=0.9, foreach=True)
+    vouts = [train_step(b, vmodel, vopt).detach().clone() for b in batches]
+
+    outs_a, cf_a, hist_a, _ = run("A")
+    outs_b, cf_b, hist_b, saved = run("B")
+
+    def full(cf, name, like):
+        """Reassemble a (possibly sharded) parameter for comparison: all_gather along every dim
+        whose local size differs from the global one."""
+        p = cf.named_parameters()[name]
+        p = p.to_local() if hasattr(p, "to_local") else p
+        for d in range(like.dim()):
+            if p.shape[d] != like.shape[d]:
+                parts = [torch.empty_like(p) for _ in range(world)]
+                dist.all_gather(parts, p.contiguous())
+                p = torch.cat(parts, dim=d)
+                # de-duplicate when the mesh shards this dim on a sub-group only
+                if p.shape[d] != like.shape[d]:
+                    p = p.narrow(d, 0, like.shape[d])
+        return p
+
+    ok = True
+    msgs = []
+    for i in range(len(batches)):
+        for tag, o in (("A", outs_a[i]), ("B", outs_b[i])):
+            if not torch.allclose(o, vouts[i], rtol=1e-4, atol=1e-5):
+                ok = False
+                msgs.append(f"step {i} output {tag} vs vanilla: {(o - vouts[i]).abs().max()}")
+        if not torch.equal(outs_a[i], outs_b[i]):
+            d = (outs_a[i] - outs_b[i]).abs().max().item()
+            if d > 1e-6:
+                ok = False
+                msgs.append(f"step {i} A vs B differ by {d}")
+    if len(mesh_shape) == 1:
+        for name, p_ref in vmodel.named_parameters():
+            for tag, cf in (("A", cf_a), ("B", cf_b)):
+                p = full(cf, name, p_ref)
+                if p.shape != p_ref.shape or not torch.allclose(p, p_ref.detach(), rtol=1e-4,
+                                                                atol=1e-5):
+                    ok = False
+                    msgs.append(f"param {name} {tag} differs")
+    if rank == 0:
+        print(f"AUTO_PARITY ok={ok} hist_ref={hist_a} hist_b200={hist_b} {msgs}", flush=True)
+        if record and "plan" in saved:
+            with open(record, "w") as f:
+                f.write(saved["plan"])
+    dist.barrier()
+    dist.destroy_process_group()
+    if not ok:
+        sys.exit(1)
+
+
+if __name__ == "__main__":
+    main()
