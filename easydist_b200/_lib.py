@@ -64,8 +64,8 @@ SIGNATURES = {
     "edb_halo_exchange": (c_int, [c_int, c_void_p, c_uint64, c_void_p, _I64P, c_int, c_int, c_int,
                                   c_int, c_void_p]),
     "edb_symm_guard": (c_int, [c_int, c_void_p]),
-    "edb_gemm_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64,
-                              c_int64, c_int64, c_int, c_int, c_int, c_void_p]),
+    "edb_gemm_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64,
+                              c_int64, c_int64, c_int64, c_int, c_int, c_int, c_void_p]),
     "edb_ag_gemm_bf16": (c_int, [c_int, c_void_p, c_void_p, c_uint64, c_uint64, c_int64, c_int64,
                                  c_int64, c_int64, c_int64, c_void_p]),
     "edb_gemm_rs_bf16": (c_int, [c_int, c_void_p, c_uint64, c_void_p, c_void_p, c_int64, c_int64,

@@ -63,6 +63,7 @@ def _finish(gm, params, buffers, named_states, args, kwargs, ops, native):
     """Local metas -> static symmetric buffers -> GEMM dispatch."""
     lowering.propagate_local_meta(gm, _flat_inputs(params, buffers, named_states, args, kwargs))
     info = {"comm_nodes": lowering.count_nodes(gm, ops)}
+    info["reinplaced_updates"] = lowering.reinplace_optimizer_updates(gm)
     if native:
         from .runtime import get_runtime
         info["symm_bytes"] = lowering.assign_static_buffers(gm, get_runtime(), ops)

@@ -35,7 +35,10 @@ template <int BN> struct TileCfg {
   static constexpr int kStageBytes = kSmemABytes + kSmemBBytes;
   static constexpr int kStages = (BN == 256) ? 4 : 6;
   static constexpr int kTmemCols = 2 * BN;  // two accumulator stages
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int kEpiBufBytes = BM * 64 * 2;  // one 128 x 64 bf16 store box (128B swizzle)
+  static constexpr int kEpiBufs = 2;
+  static constexpr int kSmemBytes =
+      kStages * kStageBytes + kEpiBufs * kEpiBufBytes + 1024 /*align*/ + 256 /*barriers*/;
 };
 
 // ---- PTX wrappers ------------------------------------------------------------------------------------
@@ -95,6 +98,25 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* ba
       "%4}], [%2];" ::"r"(smem_u32(smem)),
       "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* smem, int c0,
+                                             int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map),
+      "r"(smem_u32(smem)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() {
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+template <int N> __device__ __forceinline__ void tma_store_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void tma_store_wait_all() {
+  asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+__device__ __forceinline__ void epi_bar_sync() {
+  asm volatile("bar.sync 1, 128;" ::: "memory");
 }
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
@@ -176,6 +198,7 @@ __host__ __device__ constexpr uint32_t make_idesc(int m, int n, bool a_mn, bool 
 
 struct GemmParams {
   __nv_bfloat16* C;
+  const __nv_bfloat16* bias;  // optional [N] row vector added in the epilogue (aten.addmm)
   int64_t ldc;
   int M, N, K;
   int m_tiles, n_tiles;
@@ -186,7 +209,7 @@ struct GemmParams {
 template <int BN, bool A_KMAJOR, bool B_KMAJOR>
 __global__ void __launch_bounds__(kGemmThreads, 1)
     k_gemm_bf16(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                const GemmParams p) {
+                const __grid_constant__ CUtensorMap tmap_c, const GemmParams p) {
   using Cfg = TileCfg<BN>;
   constexpr int kStages = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
@@ -194,7 +217,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
                                              ~static_cast<uintptr_t>(1023));
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + kStages * kSmemABytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::kStageBytes);
+  uint8_t* smem_epi = smem + kStages * Cfg::kStageBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_epi + Cfg::kEpiBufs * Cfg::kEpiBufBytes);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + kStages;
   uint64_t* tmem_full = bars + 2 * kStages;
@@ -209,6 +233,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmap_a);
     prefetch_tmap(&tmap_b);
+    prefetch_tmap(&tmap_c);
   }
   if (warp == 1) {
     if (lane == 0) {
@@ -307,50 +332,79 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
       }
     }
   } else {
-    // ===== epilogue warps 2..5 =====
-    const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+    // ===== epilogue warps 2..5: TMEM -> registers -> bf16 -> swizzled smem -> TMA store =====
+    const int quad = warp & 3;            // TMEM lane quadrant this warp may access
+    const int row_in_tile = quad * 32 + lane;
+    const bool issuer = (warp == 2 && lane == 0);
     int as = 0;
     uint32_t aphase = 0;
+    int ebuf = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
       const int m_blk = t % p.m_tiles, n_blk = t / p.m_tiles;
       mbar_wait(&tmem_full[as], aphase);
       tcgen05_fence_after();
-      const int row = m_blk * BM + quad * 32 + lane;
-      const bool row_ok = row < p.M;
-      __nv_bfloat16* crow = p.C + (int64_t)row * p.ldc + (int64_t)n_blk * BN;
-      const int n_left = p.N - n_blk * BN;  // valid columns in this tile (multiple of 8)
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        uint32_t v[32];
+      for (int c0 = 0; c0 < BN; c0 += 64) {
+        uint32_t v[64];
         const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BN + c0);
         tmem_ld_32x32b_x32(taddr, v);
+        tmem_ld_32x32b_x32(taddr + 32, v + 32);
         tmem_ld_wait();
-        if (row_ok) {
+        if (c0 + 64 >= BN) {
+          // all of this warp's accumulator columns are in registers: hand the TMEM stage back
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty[as]);
+        }
+        // the staging buffer we are about to overwrite must have been read by its TMA store
+        if (issuer) tma_store_wait_read<Cfg::kEpiBufs - 1>();
+        epi_bar_sync();
+        uint8_t* buf = smem_epi + ebuf * Cfg::kEpiBufBytes;
+        uint8_t* rowp = buf + row_in_tile * 128;
+        if (p.bias != nullptr) {
+          const int col0 = n_blk * BN + c0;
 #pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            if (c0 + j < n_left) {
-              uint4 o;
-              __nv_bfloat162 h0 = __floats2bfloat162_rn(__uint_as_float(v[j + 0]), __uint_as_float(v[j + 1]));
-              __nv_bfloat162 h1 = __floats2bfloat162_rn(__uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
-              __nv_bfloat162 h2 = __floats2bfloat162_rn(__uint_as_float(v[j + 4]), __uint_as_float(v[j + 5]));
-              __nv_bfloat162 h3 = __floats2bfloat162_rn(__uint_as_float(v[j + 6]), __uint_as_float(v[j + 7]));
-              o.x = *reinterpret_cast<uint32_t*>(&h0);
-              o.y = *reinterpret_cast<uint32_t*>(&h1);
-              o.z = *reinterpret_cast<uint32_t*>(&h2);
-              o.w = *reinterpret_cast<uint32_t*>(&h3);
-              *reinterpret_cast<uint4*>(crow + c0 + j) = o;
+          for (int j = 0; j < 8; ++j) {
+            if (col0 + 8 * j < p.N) {  // N % 8 == 0 whenever a bias is passed
+              const uint4 braw = __ldg(reinterpret_cast<const uint4*>(p.bias + col0 + 8 * j));
+              const __nv_bfloat162* bb = reinterpret_cast<const __nv_bfloat162*>(&braw);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float2 f = __bfloat1622float2(bb[e]);
+                v[8 * j + 2 * e] = __float_as_uint(__uint_as_float(v[8 * j + 2 * e]) + f.x);
+                v[8 * j + 2 * e + 1] = __float_as_uint(__uint_as_float(v[8 * j + 2 * e + 1]) + f.y);
+              }
             }
           }
         }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          uint4 o;
+          __nv_bfloat162 h0 = __floats2bfloat162_rn(__uint_as_float(v[8 * j + 0]), __uint_as_float(v[8 * j + 1]));
+          __nv_bfloat162 h1 = __floats2bfloat162_rn(__uint_as_float(v[8 * j + 2]), __uint_as_float(v[8 * j + 3]));
+          __nv_bfloat162 h2 = __floats2bfloat162_rn(__uint_as_float(v[8 * j + 4]), __uint_as_float(v[8 * j + 5]));
+          __nv_bfloat162 h3 = __floats2bfloat162_rn(__uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7]));
+          o.x = *reinterpret_cast<uint32_t*>(&h0);
+          o.y = *reinterpret_cast<uint32_t*>(&h1);
+          o.z = *reinterpret_cast<uint32_t*>(&h2);
+          o.w = *reinterpret_cast<uint32_t*>(&h3);
+          // 128-byte swizzle: 16-byte chunk j of row r lives at chunk (j ^ (r & 7))
+          *reinterpret_cast<uint4*>(rowp + ((j ^ (row_in_tile & 7)) << 4)) = o;
+        }
+        fence_proxy_async();
+        epi_bar_sync();
+        if (issuer) {
+          tma_store_2d(&tmap_c, buf, n_blk * BN + c0, m_blk * BM);
+          tma_store_commit();
+        }
+        ebuf ^= 1;
       }
-      tcgen05_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[as]);
       if (++as == 2) {
         as = 0;
         aphase ^= 1;
       }
     }
+    if (issuer) tma_store_wait_all();
   }
 
   tcgen05_fence_before();
@@ -399,8 +453,8 @@ static int make_tmap(CUtensorMap* map, const void* base, int64_t inner, int64_t 
 }
 
 template <int BN, bool AK, bool BK_>
-static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p,
-                       cudaStream_t st) {
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc,
+                       const GemmParams& p, cudaStream_t st) {
   using Cfg = TileCfg<BN>;
   static bool configured = false;
   auto kern = k_gemm_bf16<BN, AK, BK_>;
@@ -410,7 +464,7 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmP
   }
   const int tiles = p.m_tiles * p.n_tiles;
   const int grid = tiles < rt().sm_count ? tiles : rt().sm_count;
-  kern<<<grid, kGemmThreads, Cfg::kSmemBytes, st>>>(ta, tb, p);
+  kern<<<grid, kGemmThreads, Cfg::kSmemBytes, st>>>(ta, tb, tc, p);
   count_launch();
   return cuda_check(cudaGetLastError(), "k_gemm_bf16 launch");
 }
@@ -433,19 +487,21 @@ using namespace edb;
 
 extern "C" {
 
-int edb_gemm_bf16(void* C, const void* A, const void* B, int64_t M, int64_t N, int64_t K,
-                  int64_t lda, int64_t ldb, int64_t ldc, int a_kmajor, int b_kmajor,
+int edb_gemm_bf16(void* C, const void* A, const void* B, const void* bias, int64_t M, int64_t N,
+                  int64_t K, int64_t lda, int64_t ldb, int64_t ldc, int a_kmajor, int b_kmajor,
                   int accumulate_into_c, void* stream) {
   if (accumulate_into_c) return set_error(EDB_E_UNSUPPORTED, "edb_gemm_bf16: accumulate_into_c");
+  if (bias && ((N & 7) || ((uintptr_t)bias & 15)))
+    return set_error(EDB_E_UNSUPPORTED, "edb_gemm_bf16: bias needs N %% 8 == 0 and 16-byte alignment");
   if (M <= 0 || N <= 0 || K <= 0) return set_error(EDB_E_UNSUPPORTED, "edb_gemm_bf16: empty problem");
   if (M > 0x7fffffff || N > 0x7fffffff || K > 0x7fffffff)
     return set_error(EDB_E_UNSUPPORTED, "edb_gemm_bf16: dimension too large");
   if (((uintptr_t)A | (uintptr_t)B | (uintptr_t)C) & 15)
     return set_error(EDB_E_UNSUPPORTED, "edb_gemm_bf16: base pointers must be 16-byte aligned");
-  if ((lda | ldb | ldc | N) & 7)
-    return set_error(EDB_E_UNSUPPORTED, "edb_gemm_bf16: lda/ldb/ldc/N must be multiples of 8");
-  if ((a_kmajor && (K & 7)) || (!a_kmajor && (M & 7)))
-    return set_error(EDB_E_UNSUPPORTED, "edb_gemm_bf16: A inner extent must be a multiple of 8");
+  // TMA: global strides must be multiples of 16 bytes; extents (M, N, K) may be anything — boxes
+  // that run past an extent are zero-filled on load and clipped on store.
+  if ((lda | ldb | ldc) & 7)
+    return set_error(EDB_E_UNSUPPORTED, "edb_gemm_bf16: lda/ldb/ldc must be multiples of 8");
   Runtime& r = rt();
   int sms = r.sm_count;
   if (!r.inited) {
@@ -463,8 +519,12 @@ int edb_gemm_bf16(void* C, const void* A, const void* B, int64_t M, int64_t N, i
   if (b_kmajor) rc = make_tmap(&tb, B, K, N, ldb, BK, bn);
   else rc = make_tmap(&tb, B, N, K, ldb, 64, BK);
   if (rc) return rc;
+  CUtensorMap tc;
+  rc = make_tmap(&tc, C, N, M, ldc, 64, BM);
+  if (rc) return rc;
   GemmParams p;
   p.C = static_cast<__nv_bfloat16*>(C);
+  p.bias = static_cast<const __nv_bfloat16*>(bias);
   p.ldc = ldc;
   p.M = (int)M;
   p.N = (int)N;
@@ -474,14 +534,14 @@ int edb_gemm_bf16(void* C, const void* A, const void* B, int64_t M, int64_t N, i
   cudaStream_t st = (cudaStream_t)stream;
   const int key = (bn == 256 ? 4 : 0) | (a_kmajor ? 2 : 0) | (b_kmajor ? 1 : 0);
   switch (key) {
-    case 7: return launch_gemm<256, true, true>(ta, tb, p, st);
-    case 6: return launch_gemm<256, true, false>(ta, tb, p, st);
-    case 5: return launch_gemm<256, false, true>(ta, tb, p, st);
-    case 4: return launch_gemm<256, false, false>(ta, tb, p, st);
-    case 3: return launch_gemm<128, true, true>(ta, tb, p, st);
-    case 2: return launch_gemm<128, true, false>(ta, tb, p, st);
-    case 1: return launch_gemm<128, false, true>(ta, tb, p, st);
-    default: return launch_gemm<128, false, false>(ta, tb, p, st);
+    case 7: return launch_gemm<256, true, true>(ta, tb, tc, p, st);
+    case 6: return launch_gemm<256, true, false>(ta, tb, tc, p, st);
+    case 5: return launch_gemm<256, false, true>(ta, tb, tc, p, st);
+    case 4: return launch_gemm<256, false, false>(ta, tb, tc, p, st);
+    case 3: return launch_gemm<128, true, true>(ta, tb, tc, p, st);
+    case 2: return launch_gemm<128, true, false>(ta, tb, tc, p, st);
+    case 1: return launch_gemm<128, false, true>(ta, tb, tc, p, st);
+    default: return launch_gemm<128, false, false>(ta, tb, tc, p, st);
   }
 }
 

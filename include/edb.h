@@ -155,15 +155,17 @@ int edb_symm_guard(int gid, void* stream);
 
 /* ---- dense compute on the path (sharded-op kernel dispatch) ------------------------------- */
 
-/* C[M,N] (bf16, row-major, ldc) = A·B with fp32 accumulation on tcgen05 tensor cores.
+/* C[M,N] (bf16, row-major, ldc) = A·B (+ bias) with fp32 accumulation on tcgen05 tensor cores.
  *   a_kmajor: A is [M,K] row-major (lda = elements between rows)   else A is stored [K,M] (lda between k rows)
  *   b_kmajor: B is [N,K] row-major (i.e. C = A·Bᵀ, nn.Linear fwd)  else B is stored [K,N] (ldb between k rows)
  * Replaces the aten.mm.default nodes of the sharded graph (Linear fwd / dgrad / wgrad;
  * easydist/torch/passes/fix_bias.py turns addmm into mm+add first).
- * Requirements: 16-byte aligned bases, lda/ldb/ldc multiples of 8 elements.  Returns
+ *   bias: NULL, or a bf16 row vector [N] added to every row in the epilogue (aten.addmm.default)
+ * Requirements: 16-byte aligned bases, lda/ldb/ldc multiples of 8 elements (TMA stride rule);
+ * M, N, K themselves are arbitrary (tail boxes are zero-filled / clipped).  Returns
  * EDB_E_UNSUPPORTED (=2) for shapes it does not cover so the host can dispatch elsewhere. */
-int edb_gemm_bf16(void* C, const void* A, const void* B, int64_t M, int64_t N, int64_t K,
-                  int64_t lda, int64_t ldb, int64_t ldc, int a_kmajor, int b_kmajor,
+int edb_gemm_bf16(void* C, const void* A, const void* B, const void* bias, int64_t M, int64_t N,
+                  int64_t K, int64_t lda, int64_t ldb, int64_t ldc, int a_kmajor, int b_kmajor,
                   int accumulate_into_c, void* stream);
 
 /* all-gather fused into the consuming GEMM: B (weights [N,K], K-major) is sharded S(0) over the

@@ -130,11 +130,56 @@ def test_gemm_exact_on_integer_inputs(rt):
         assert torch.equal(c.float(), ref)
 
 
-def test_gemm_unsupported_shapes_route_to_aten(rt):
+def test_gemm_unaligned_extents_run_natively(rt):
+    """Leading dimensions that break TMA's 16-byte stride rule (vocab 50257 of the GPT-2 LM head)
+    are handled by padded staging, not by falling back to cuBLAS: forward (N unaligned), dgrad
+    (K unaligned, A row stride unaligned) and wgrad (M unaligned, A column-major)."""
     from easydist_b200 import gemm
-    A = torch.randn(64, 50, device="cuda", dtype=torch.bfloat16)   # K % 8 != 0
+    torch.manual_seed(2)
+    V, H, T = 50257, 256, 384
+    x = torch.randn(T, H, device="cuda", dtype=torch.bfloat16)
+    W = (torch.randn(V, H, device="cuda") * 0.05).bfloat16()
+    dl = (torch.randn(T, V, device="cuda") * 0.05).bfloat16()
+
+    def close(c, ref):
+        err = (c.float() - ref).abs()
+        return bool((err <= ref.abs() * 2 ** -7 + 2e-2).all())
+
+    gemm.reset_stats()
+    logits = gemm.mm(x, W.t())                     # [T,V] = x @ W^T
+    assert logits.shape == (T, V) and close(logits, x.float() @ W.float().t())
+    dx = gemm.mm(dl, W)                            # [T,H] = dl @ W      (K = 50257)
+    assert close(dx, dl.float() @ W.float())
+    dW = gemm.mm(dl.t(), x)                        # [V,H] = dl^T @ x    (M = 50257, A col-major)
+    assert close(dW, dl.float().t() @ x.float())
+    st = gemm.stats()
+    assert st["edb_gemm"] == 3 and st["aten_mm"] == 0 and st["padded_operands"] >= 2, st
+    # small odd sizes
+    A = torch.randn(64, 50, device="cuda", dtype=torch.bfloat16)
     B = torch.randn(50, 24, device="cuda", dtype=torch.bfloat16)
+    assert close(gemm.mm(A, B), A.float() @ B.float())
+
+
+def test_addmm_bias_fused_in_epilogue(rt):
+    from easydist_b200 import gemm
+    torch.manual_seed(3)
+    for (M, N, K) in [(256, 512, 128), (4096, 3072, 1024), (100, 72, 40)]:
+        a = torch.randn(M, K, device="cuda", dtype=torch.bfloat16)
+        w = torch.randn(N, K, device="cuda", dtype=torch.bfloat16)
+        bias = torch.randn(N, device="cuda", dtype=torch.bfloat16)
+        gemm.reset_stats()
+        c = gemm.addmm(bias, a, w.t())
+        assert gemm.stats()["edb_gemm"] == 1
+        ref = a.float() @ w.float().t() + bias.float()
+        err = (c.float() - ref).abs()
+        assert bool((err <= ref.abs() * 2 ** -7 + 2e-2).all()), (M, N, K, float(err.max()))
+
+
+def test_non_bf16_goes_to_aten(rt):
+    from easydist_b200 import gemm
+    A = torch.randn(64, 48, device="cuda")
+    B = torch.randn(48, 24, device="cuda")
     gemm.reset_stats()
     c = gemm.mm(A, B)
-    assert gemm.stats()["aten_mm"] == 1
-    assert torch.allclose(c.float(), (A.float() @ B.float()), atol=0.5, rtol=0.05)
+    assert gemm.stats()["aten_mm"] == 1 and gemm.stats()["edb_gemm"] == 0
+    assert torch.allclose(c, A @ B, atol=1e-4, rtol=1e-4)
