@@ -66,8 +66,8 @@ SIGNATURES = {
     "edb_symm_guard": (c_int, [c_int, c_void_p]),
     "edb_gemm_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64,
                               c_int64, c_int64, c_int64, c_int, c_int, c_int, c_void_p]),
-    "edb_ag_gemm_bf16": (c_int, [c_int, c_void_p, c_void_p, c_uint64, c_uint64, c_int64, c_int64,
-                                 c_int64, c_int64, c_int64, c_void_p]),
+    "edb_ag_gemm_bf16": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_uint64, c_uint64, c_int64,
+                                 c_int64, c_int64, c_int64, c_int64, c_void_p]),
     "edb_gemm_rs_bf16": (c_int, [c_int, c_void_p, c_uint64, c_void_p, c_void_p, c_int64, c_int64,
                                  c_int64, c_int64, c_int64, c_int, c_int, c_float, c_int,
                                  c_void_p]),

@@ -59,10 +59,29 @@ def _flat_inputs(params, buffers, named_states, args, kwargs):
     return pytree.tree_flatten((params, buffers, named_states, args, kwargs))[0]
 
 
-def _finish(gm, params, buffers, named_states, args, kwargs, ops, native):
-    """Local metas -> static symmetric buffers -> GEMM dispatch."""
-    lowering.propagate_local_meta(gm, _flat_inputs(params, buffers, named_states, args, kwargs))
-    info = {"comm_nodes": lowering.count_nodes(gm, ops)}
+def _finish(gm, params, buffers, named_states, args, kwargs, ops, native, io=None, ranks=None,
+            fuse=True):
+    """Local metas -> (fusions) -> static symmetric buffers -> GEMM dispatch."""
+    flat = _flat_inputs(params, buffers, named_states, args, kwargs)
+    lowering.propagate_local_meta(gm, flat)
+    info = {}
+    if native and fuse and io is not None and ranks is not None and len(ranks) > 1:
+        from .runtime import get_runtime
+        rt = get_runtime()
+        rehomed, nf = lowering.fuse_collective_gemms(gm, io, rt, ranks, ops)
+        info["fused"] = nf
+        # parameter shards read by peers must live at their symmetric offsets
+        name_of = {ph.name: io.param_names[i] for i, ph in enumerate(io.param_ph)}
+        for ph_name, buf in rehomed.items():
+            pname = name_of[ph_name]
+            t = params[pname]
+            home = buf.tensor(t.dtype, t.shape)
+            home.copy_(t)
+            params[pname] = home
+        if rehomed:
+            lowering.propagate_local_meta(gm, _flat_inputs(params, buffers, named_states, args,
+                                                           kwargs))
+    info["comm_nodes"] = lowering.count_nodes(gm, ops)
     info["reinplaced_updates"] = lowering.reinplace_optimizer_updates(gm)
     if native:
         from .runtime import get_runtime
@@ -74,7 +93,7 @@ def _finish(gm, params, buffers, named_states, args, kwargs, ops, native):
 
 
 def _compile_dp(func, parallel_mode, tracing_mode, args, kwargs, *, ops=_default_ops,
-                native=True):
+                native=True, fuse=True):
     """ddp / zero2 / zero3 (reference: _compile_dp, compile_dp.py:201-381)."""
     mode = parallel_mode.replace("b200_", "")
     assert mode in DP_MODES, parallel_mode
@@ -106,7 +125,8 @@ def _compile_dp(func, parallel_mode, tracing_mode, args, kwargs, *, ops=_default
                     flat_states[i] = ops.scatter_wrapper(flat_states[i].detach().flatten(), n, 0,
                                                          my_index)
             named_states = pytree.tree_unflatten(flat_states, spec)
-    info = _finish(gm, params, buffers, named_states, args, kwargs, ops, native)
+    info = _finish(gm, params, buffers, named_states, args, kwargs, ops, native, io=io,
+                   ranks=ranks, fuse=fuse)
     info.update(mode=mode, dp_size=n)
     return EDCompiledFunc(gm, params, buffers, named_states, info=info)
 

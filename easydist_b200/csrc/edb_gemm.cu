@@ -204,17 +204,248 @@ struct GemmParams {
   int m_tiles, n_tiles;
 };
 
+// Fusion modes of the GEMM kernel
+//   MODE_PLAIN : C = A.B
+//   MODE_AG    : B (weights, [N,K] K-major) is sharded S(0) over the group; a few "comm" CTAs pull the
+//                peer shards over NVLink with TMA bulk copies into the local gathered buffer while
+//                the MMA CTAs start on the local shard and pick up chunks as their flags arrive
+//                (all_gather_end -> aten.mm of the sharded graph in one kernel)
+//   MODE_RS    : the partial product C is reduce-scattered over its rows: the epilogue TMA-stores
+//                every tile straight into the owner's receive slot over NVLink (own rows last),
+//                per-chunk flags tell the owner when a source is complete, and the tail of the same
+//                kernel reduces the n slots in rank order with scale + cast
+//                (aten.mm -> reduce_scatter_start in one kernel)
+enum { MODE_PLAIN = 0, MODE_AG = 1, MODE_RS = 2 };
+constexpr int F_TILECNT = 96;  // flag-block words [96,104): per-chunk completion counters
+
+struct FusedArgs {
+  FlagCtx f;
+  int n_comm;  // MODE_AG: number of comm CTAs at the end of the grid
+  // MODE_AG
+  const char* shard_src[kMaxGroup];  // member p's shard (peer mapped); [me] is local
+  char* full_dst;                    // local gathered buffer
+  int64_t shard_bytes;
+  // MODE_RS
+  char* recv_base;      // my receive buffer: n slots of chunk_bytes
+  int64_t chunk_bytes;  // (M/n) * N * 2
+  void* rs_dst;
+  float rs_scale;
+  int rs_out_dtype;
+  int tiles_per_chunk;
+};
+
+struct CMaps {
+  CUtensorMap m[kMaxGroup];  // MODE_RS: store map of member p's receive slot [me]; MODE_AG: m[0] = local shard
+};
+
+template <int MODE>
+__device__ __forceinline__ void tile_coords(int t, const GemmParams& p, const FusedArgs& fa,
+                                            int& m_blk, int& n_blk, int& chunk) {
+  if (MODE == MODE_AG) {
+    const int ntc = p.n_tiles / fa.f.n;  // n-tiles per chunk
+    const int tpc = p.m_tiles * ntc;
+    const int ci = t / tpc, w = t - ci * tpc;
+    chunk = (fa.f.me + ci) % fa.f.n;  // own shard first: it needs no transfer
+    n_blk = chunk * ntc + w / p.m_tiles;
+    m_blk = w % p.m_tiles;
+  } else if (MODE == MODE_RS) {
+    const int mtc = p.m_tiles / fa.f.n;  // m-tiles per chunk
+    const int tpc = mtc * p.n_tiles;
+    const int ci = t / tpc, w = t - ci * tpc;
+    chunk = (fa.f.me + 1 + ci) % fa.f.n;  // own rows last: their reduction needs the peers anyway
+    m_blk = chunk * mtc + w % mtc;
+    n_blk = w / mtc;
+  } else {
+    chunk = 0;
+    m_blk = t % p.m_tiles;
+    n_blk = t / p.m_tiles;
+  }
+}
+
+__device__ __forceinline__ void bulk_load(void* smem, const void* gsrc, uint32_t bytes,
+                                          uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+          "r"(smem_u32(smem)),
+      "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void bulk_store(void* gdst, const void* smem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst),
+               "r"(smem_u32(smem)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_all() {
+  asm volatile("fence.proxy.async;" ::: "memory");
+}
+__device__ __forceinline__ void spin_wait_gpu(const uint64_t* flag, uint64_t target) {
+  if (ld_acquire_gpu(flag) >= target) return;
+  const uint64_t t0 = globaltimer_ns();
+  uint32_t spins = 0;
+  while (ld_acquire_gpu(flag) < target) {
+    __nanosleep(32);
+    if ((++spins & 0xfff) == 0 && globaltimer_ns() - t0 > 4000000000ull) {
+      printf("edb fused gemm watchdog: block %d stuck on chunk flag\n", blockIdx.x);
+      asm volatile("trap;");
+    }
+  }
+}
+
+// MODE_AG comm CTA: one thread drives a TMA bulk-copy ring  peer HBM -> smem -> local HBM.
+__device__ __forceinline__ void ag_comm_role(const FusedArgs& fa, uint8_t* smem, int comm_idx,
+                                             uint64_t q) {
+  constexpr int S = 8, D = 4, SLOT = 16384;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + S * SLOT);
+  const FlagCtx& f = fa.f;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < S; ++s) mbar_init(&full[s], 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
+  if (threadIdx.x != 0) return;
+  if (comm_idx == 0) {
+    // my shard was written by earlier kernels of this stream: publish it
+    __threadfence_system();
+    for (int pidx = 0; pidx < f.n; ++pidx)
+      if (pidx != f.me) st_release_sys(f.peer[pidx] + F_READY + f.me, q);
+  }
+  uint32_t n_load = 0, n_store = 0;
+  const int64_t per = ((fa.shard_bytes + fa.n_comm - 1) / fa.n_comm + SLOT - 1) / SLOT * SLOT;
+  const int64_t lo = (int64_t)comm_idx * per;
+  const int64_t hi = lo + per < fa.shard_bytes ? lo + per : fa.shard_bytes;
+  const int64_t nblk = hi > lo ? (hi - lo + SLOT - 1) / SLOT : 0;
+  for (int k = 0; k < f.n; ++k) {
+    const int c = (f.me + k) % f.n;
+    if (c != f.me) spin_wait_sys(f.local + F_READY + c, q, f.timeout_ns, f.local + F_ERR);
+    const char* src = fa.shard_src[c] + lo;
+    char* dst = fa.full_dst + (int64_t)c * fa.shard_bytes + lo;
+    for (int64_t i = 0; i < nblk + D; ++i) {
+      if (i < nblk) {
+        const uint32_t slot = n_load % S;
+        if (n_load >= (uint32_t)S) tma_store_wait_read<S - D - 1>();
+        const int64_t left = hi - lo - i * SLOT;
+        const uint32_t bytes = (uint32_t)(left < SLOT ? left : SLOT);
+        mbar_expect_tx(&full[slot], bytes);
+        bulk_load(smem + slot * SLOT, src + i * SLOT, bytes, &full[slot]);
+        ++n_load;
+      }
+      if (i >= D) {
+        const int64_t j = i - D;
+        const uint32_t slot = n_store % S;
+        mbar_wait(&full[slot], (n_store / S) & 1);
+        const int64_t left = hi - lo - j * SLOT;
+        const uint32_t bytes = (uint32_t)(left < SLOT ? left : SLOT);
+        bulk_store(dst + j * SLOT, smem + slot * SLOT, bytes);
+        tma_store_commit();
+        ++n_store;
+      }
+    }
+    tma_store_wait_all();
+    fence_proxy_async_all();
+    __threadfence();
+    const unsigned long long prev =
+        atomicAdd(reinterpret_cast<unsigned long long*>(f.local + F_TILECNT + c), 1ULL);
+    if (prev == (unsigned long long)fa.n_comm - 1) {
+      f.local[F_TILECNT + c] = 0;
+      __threadfence();
+      st_release_gpu(f.local + F_CHUNK + c, q);
+    }
+  }
+  // end of the op: DONE to the peers, SEQ locally — but only after every CTA of this launch has
+  // read the old SEQ (slow starters would otherwise compute the wrong op number)
+  const unsigned long long prev =
+      atomicAdd(reinterpret_cast<unsigned long long*>(f.local + F_CNT_B), 1ULL);
+  if (prev == (unsigned long long)fa.n_comm - 1) {
+    f.local[F_CNT_B] = 0;
+    while (ld_acquire_gpu(f.local + F_CNT_C) < (uint64_t)gridDim.x) __nanosleep(64);
+    f.local[F_CNT_C] = 0;
+    __threadfence_system();
+    for (int pidx = 0; pidx < f.n; ++pidx)
+      if (pidx != f.me) st_release_sys(f.peer[pidx] + F_DONE + f.me, q);
+    st_release_gpu(f.local + F_SEQ, q);
+  }
+}
+
+template <typename Out>
+__device__ __forceinline__ void rs_tail_reduce(const FusedArgs& fa, uint64_t tid, uint64_t nthr) {
+  const int64_t nvec = fa.chunk_bytes / 16;  // 8 bf16 per vector
+  const int n = fa.f.n;
+  Out* out = static_cast<Out*>(fa.rs_dst);
+  for (int64_t i = tid; i < nvec; i += nthr) {
+    float acc[8];
+    {
+      const uint4 r = *reinterpret_cast<const uint4*>(fa.recv_base + i * 16);
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 v = __bfloat1622float2(h[e]);
+        acc[2 * e] = v.x;
+        acc[2 * e + 1] = v.y;
+      }
+    }
+    for (int s = 1; s < n; ++s) {
+      const uint4 r = *reinterpret_cast<const uint4*>(fa.recv_base + (int64_t)s * fa.chunk_bytes + i * 16);
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 v = __bfloat1622float2(h[e]);
+        acc[2 * e] += v.x;
+        acc[2 * e + 1] += v.y;
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] *= fa.rs_scale;
+    if (sizeof(Out) == 4) {
+      float4* o = reinterpret_cast<float4*>(out) + 2 * i;
+      o[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+      o[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+    } else {
+      uint4 o;
+      __nv_bfloat162 h0 = __floats2bfloat162_rn(acc[0], acc[1]);
+      __nv_bfloat162 h1 = __floats2bfloat162_rn(acc[2], acc[3]);
+      __nv_bfloat162 h2 = __floats2bfloat162_rn(acc[4], acc[5]);
+      __nv_bfloat162 h3 = __floats2bfloat162_rn(acc[6], acc[7]);
+      o.x = *reinterpret_cast<uint32_t*>(&h0);
+      o.y = *reinterpret_cast<uint32_t*>(&h1);
+      o.z = *reinterpret_cast<uint32_t*>(&h2);
+      o.w = *reinterpret_cast<uint32_t*>(&h3);
+      reinterpret_cast<uint4*>(out)[i] = o;
+    }
+  }
+}
+
 // ---- kernel ------------------------------------------------------------------------------------------
 
-template <int BN, bool A_KMAJOR, bool B_KMAJOR>
+template <int BN, bool A_KMAJOR, bool B_KMAJOR, int MODE>
 __global__ void __launch_bounds__(kGemmThreads, 1)
     k_gemm_bf16(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                const __grid_constant__ CUtensorMap tmap_c, const GemmParams p) {
+                const __grid_constant__ CUtensorMap tmap_c, const GemmParams p,
+                const __grid_constant__ FusedArgs fa, const __grid_constant__ CMaps cm) {
   using Cfg = TileCfg<BN>;
   constexpr int kStages = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
+  __shared__ uint64_t s_q;
+  __shared__ int s_last;
+  uint64_t q = 0;
+  const int n_gemm_ctas = (MODE == MODE_AG) ? (int)gridDim.x - fa.n_comm : (int)gridDim.x;
+
+  if (MODE == MODE_RS) {
+    q = begin_op(fa.f, &s_q);  // WAR guard: peers are done with my buffers of earlier ops
+  } else if (MODE == MODE_AG) {
+    if (threadIdx.x == 0) {
+      s_q = ld_relaxed_gpu(fa.f.local + F_SEQ) + 1;
+      atomicAdd(reinterpret_cast<unsigned long long*>(fa.f.local + F_CNT_C), 1ULL);
+    }
+    __syncthreads();
+    q = s_q;
+    if ((int)blockIdx.x >= n_gemm_ctas) {
+      ag_comm_role(fa, smem, (int)blockIdx.x - n_gemm_ctas, q);
+      return;
+    }
+  }
+
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + kStages * kSmemABytes;
   uint8_t* smem_epi = smem + kStages * Cfg::kStageBytes;
@@ -260,8 +491,22 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-        const int m_blk = t % p.m_tiles, n_blk = t / p.m_tiles;
+      int ready_chunk = -1;
+      for (int t = blockIdx.x; t < num_tiles; t += n_gemm_ctas) {
+        int m_blk, n_blk, chunk;
+        tile_coords<MODE>(t, p, fa, m_blk, n_blk, chunk);
+        const CUtensorMap* bmap = &tmap_b;
+        int b_row = n_blk * BN;
+        if (MODE == MODE_AG) {
+          if (chunk == fa.f.me) {
+            bmap = &cm.m[0];  // my own shard: no transfer needed
+            b_row = (n_blk - chunk * (p.n_tiles / fa.f.n)) * BN;
+          } else if (chunk != ready_chunk) {
+            spin_wait_gpu(fa.f.local + F_CHUNK + chunk, q);
+            fence_proxy_async_all();
+            ready_chunk = chunk;
+          }
+        }
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
@@ -277,12 +522,11 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
                           kb * BK);
           }
           if (B_KMAJOR) {
-            tma_load_2d(&tmap_b, &full_bar[stage], sb, kb * BK, n_blk * BN);
+            tma_load_2d(bmap, &full_bar[stage], sb, kb * BK, b_row);
           } else {
 #pragma unroll
             for (int h = 0; h < BN / 64; ++h)
-              tma_load_2d(&tmap_b, &full_bar[stage], sb + h * (64 * BK * 2), n_blk * BN + h * 64,
-                          kb * BK);
+              tma_load_2d(bmap, &full_bar[stage], sb + h * (64 * BK * 2), b_row + h * 64, kb * BK);
           }
           if (++stage == kStages) {
             stage = 0;
@@ -298,7 +542,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
     uint32_t phase = 0;
     int as = 0;
     uint32_t aphase = 0;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+    for (int t = blockIdx.x; t < num_tiles; t += n_gemm_ctas) {
       mbar_wait(&tmem_empty[as], aphase ^ 1);
       tcgen05_fence_after();
       const uint32_t tmem_d = tmem_base + as * BN;
@@ -339,8 +583,15 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
     int as = 0;
     uint32_t aphase = 0;
     int ebuf = 0;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-      const int m_blk = t % p.m_tiles, n_blk = t / p.m_tiles;
+    for (int t = blockIdx.x; t < num_tiles; t += n_gemm_ctas) {
+      int m_blk, n_blk, chunk;
+      tile_coords<MODE>(t, p, fa, m_blk, n_blk, chunk);
+      const CUtensorMap* cmap = &tmap_c;
+      int c_row = m_blk * BM;
+      if (MODE == MODE_RS) {
+        cmap = &cm.m[chunk];  // receive slot [me] of the rank that owns these rows
+        c_row = (m_blk - chunk * (p.m_tiles / fa.f.n)) * BM;
+      }
       mbar_wait(&tmem_full[as], aphase);
       tcgen05_fence_after();
 #pragma unroll 1
@@ -394,10 +645,24 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
         fence_proxy_async();
         epi_bar_sync();
         if (issuer) {
-          tma_store_2d(&tmap_c, buf, n_blk * BN + c0, m_blk * BM);
+          tma_store_2d(cmap, buf, n_blk * BN + c0, c_row);
           tma_store_commit();
         }
         ebuf ^= 1;
+      }
+      if (MODE == MODE_RS && issuer) {
+        // this tile now sits (or is in flight to) its owner: count it, and when the last tile of
+        // the chunk has landed tell the owner that source `me` is complete
+        tma_store_wait_all();
+        fence_proxy_async_all();
+        __threadfence_system();
+        const unsigned long long prev = atomicAdd(
+            reinterpret_cast<unsigned long long*>(fa.f.local + F_TILECNT + chunk), 1ULL);
+        if (prev == (unsigned long long)fa.tiles_per_chunk - 1) {
+          fa.f.local[F_TILECNT + chunk] = 0;
+          __threadfence_system();
+          st_release_sys(fa.f.peer[chunk] + F_CHUNK + fa.f.me, q);
+        }
       }
       if (++as == 2) {
         as = 0;
@@ -412,6 +677,18 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
   if (warp == 1) {
     tcgen05_fence_after();
     tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+
+  if (MODE == MODE_RS) {
+    // ===== tail: reduce my rows from the n receive slots (all local), rank order =====
+    if (threadIdx.x < fa.f.n)
+      spin_wait_sys(fa.f.local + F_CHUNK + threadIdx.x, q, fa.f.timeout_ns, fa.f.local + F_ERR);
+    __syncthreads();
+    const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t nthr = (uint64_t)gridDim.x * blockDim.x;
+    if (fa.rs_out_dtype == EDB_F32) rs_tail_reduce<float>(fa, tid, nthr);
+    else rs_tail_reduce<__nv_bfloat16>(fa, tid, nthr);
+    finish_op(fa.f, q, &s_last, gridDim.x);
   }
 }
 
@@ -452,21 +729,37 @@ static int make_tmap(CUtensorMap* map, const void* base, int64_t inner, int64_t 
   return EDB_OK;
 }
 
-template <int BN, bool AK, bool BK_>
+template <int BN, bool AK, bool BK_, int MODE>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc,
-                       const GemmParams& p, cudaStream_t st) {
+                       const GemmParams& p, const FusedArgs& fa, const CMaps& cm, int grid,
+                       cudaStream_t st) {
   using Cfg = TileCfg<BN>;
   static bool configured = false;
-  auto kern = k_gemm_bf16<BN, AK, BK_>;
+  auto kern = k_gemm_bf16<BN, AK, BK_, MODE>;
   if (!configured) {
     EDB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     configured = true;
   }
-  const int tiles = p.m_tiles * p.n_tiles;
-  const int grid = tiles < rt().sm_count ? tiles : rt().sm_count;
-  kern<<<grid, kGemmThreads, Cfg::kSmemBytes, st>>>(ta, tb, tc, p);
+  kern<<<grid, kGemmThreads, Cfg::kSmemBytes, st>>>(ta, tb, tc, p, fa, cm);
   count_launch();
   return cuda_check(cudaGetLastError(), "k_gemm_bf16 launch");
+}
+
+template <int MODE>
+static int dispatch_gemm(int bn, bool a_k, bool b_k, const CUtensorMap& ta, const CUtensorMap& tb,
+                         const CUtensorMap& tc, const GemmParams& p, const FusedArgs& fa,
+                         const CMaps& cm, int grid, cudaStream_t st) {
+  const int key = (bn == 256 ? 4 : 0) | (a_k ? 2 : 0) | (b_k ? 1 : 0);
+  switch (key) {
+    case 7: return launch_gemm<256, true, true, MODE>(ta, tb, tc, p, fa, cm, grid, st);
+    case 6: return launch_gemm<256, true, false, MODE>(ta, tb, tc, p, fa, cm, grid, st);
+    case 5: return launch_gemm<256, false, true, MODE>(ta, tb, tc, p, fa, cm, grid, st);
+    case 4: return launch_gemm<256, false, false, MODE>(ta, tb, tc, p, fa, cm, grid, st);
+    case 3: return launch_gemm<128, true, true, MODE>(ta, tb, tc, p, fa, cm, grid, st);
+    case 2: return launch_gemm<128, true, false, MODE>(ta, tb, tc, p, fa, cm, grid, st);
+    case 1: return launch_gemm<128, false, true, MODE>(ta, tb, tc, p, fa, cm, grid, st);
+    default: return launch_gemm<128, false, false, MODE>(ta, tb, tc, p, fa, cm, grid, st);
+  }
 }
 
 static int pick_bn(int64_t M, int64_t N, int sms) {
@@ -481,6 +774,34 @@ static int pick_bn(int64_t M, int64_t N, int sms) {
   return (e256 + 0.05 >= e128) ? 256 : 128;
 }
 
+static int check_operands(const void* A, const void* B, const void* C, const void* bias, int64_t M,
+                          int64_t N, int64_t K, int64_t lda, int64_t ldb, int64_t ldc,
+                          const char* who) {
+  if (M <= 0 || N <= 0 || K <= 0) return set_error(EDB_E_UNSUPPORTED, "%s: empty problem", who);
+  if (M > 0x7fffffff || N > 0x7fffffff || K > 0x7fffffff)
+    return set_error(EDB_E_UNSUPPORTED, "%s: dimension too large", who);
+  if (((uintptr_t)A | (uintptr_t)B | (uintptr_t)C) & 15)
+    return set_error(EDB_E_UNSUPPORTED, "%s: base pointers must be 16-byte aligned", who);
+  // TMA: global strides must be multiples of 16 bytes; extents (M, N, K) may be anything — boxes
+  // that run past an extent are zero-filled on load and clipped on store.
+  if ((lda | ldb | ldc) & 7)
+    return set_error(EDB_E_UNSUPPORTED, "%s: lda/ldb/ldc must be multiples of 8", who);
+  if (bias && ((N & 7) || ((uintptr_t)bias & 15)))
+    return set_error(EDB_E_UNSUPPORTED, "%s: bias needs N %% 8 == 0 and 16-byte alignment", who);
+  return EDB_OK;
+}
+
+static int sm_count_now() {
+  Runtime& r = rt();
+  if (!r.inited) {
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess)
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    r.sm_count = sms;
+  }
+  return r.sm_count;
+}
+
 }  // namespace edb
 
 using namespace edb;
@@ -491,35 +812,17 @@ int edb_gemm_bf16(void* C, const void* A, const void* B, const void* bias, int64
                   int64_t K, int64_t lda, int64_t ldb, int64_t ldc, int a_kmajor, int b_kmajor,
                   int accumulate_into_c, void* stream) {
   if (accumulate_into_c) return set_error(EDB_E_UNSUPPORTED, "edb_gemm_bf16: accumulate_into_c");
-  if (bias && ((N & 7) || ((uintptr_t)bias & 15)))
-    return set_error(EDB_E_UNSUPPORTED, "edb_gemm_bf16: bias needs N %% 8 == 0 and 16-byte alignment");
-  if (M <= 0 || N <= 0 || K <= 0) return set_error(EDB_E_UNSUPPORTED, "edb_gemm_bf16: empty problem");
-  if (M > 0x7fffffff || N > 0x7fffffff || K > 0x7fffffff)
-    return set_error(EDB_E_UNSUPPORTED, "edb_gemm_bf16: dimension too large");
-  if (((uintptr_t)A | (uintptr_t)B | (uintptr_t)C) & 15)
-    return set_error(EDB_E_UNSUPPORTED, "edb_gemm_bf16: base pointers must be 16-byte aligned");
-  // TMA: global strides must be multiples of 16 bytes; extents (M, N, K) may be anything — boxes
-  // that run past an extent are zero-filled on load and clipped on store.
-  if ((lda | ldb | ldc) & 7)
-    return set_error(EDB_E_UNSUPPORTED, "edb_gemm_bf16: lda/ldb/ldc must be multiples of 8");
-  Runtime& r = rt();
-  int sms = r.sm_count;
-  if (!r.inited) {
-    int dev = 0;
-    EDB_CUDA(cudaGetDevice(&dev));
-    EDB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    r.sm_count = sms;
-  }
+  int rc = check_operands(A, B, C, bias, M, N, K, lda, ldb, ldc, "edb_gemm_bf16");
+  if (rc) return rc;
+  const int sms = sm_count_now();
   const int bn = pick_bn(M, N, sms);
-  CUtensorMap ta, tb;
-  int rc;
+  CUtensorMap ta, tb, tc;
   if (a_kmajor) rc = make_tmap(&ta, A, K, M, lda, BK, BM);
   else rc = make_tmap(&ta, A, M, K, lda, 64, BK);
   if (rc) return rc;
   if (b_kmajor) rc = make_tmap(&tb, B, K, N, ldb, BK, bn);
   else rc = make_tmap(&tb, B, N, K, ldb, 64, BK);
   if (rc) return rc;
-  CUtensorMap tc;
   rc = make_tmap(&tc, C, N, M, ldc, 64, BM);
   if (rc) return rc;
   GemmParams p;
@@ -531,33 +834,138 @@ int edb_gemm_bf16(void* C, const void* A, const void* B, const void* bias, int64
   p.K = (int)K;
   p.m_tiles = (int)((M + BM - 1) / BM);
   p.n_tiles = (int)((N + bn - 1) / bn);
-  cudaStream_t st = (cudaStream_t)stream;
-  const int key = (bn == 256 ? 4 : 0) | (a_kmajor ? 2 : 0) | (b_kmajor ? 1 : 0);
-  switch (key) {
-    case 7: return launch_gemm<256, true, true>(ta, tb, tc, p, st);
-    case 6: return launch_gemm<256, true, false>(ta, tb, tc, p, st);
-    case 5: return launch_gemm<256, false, true>(ta, tb, tc, p, st);
-    case 4: return launch_gemm<256, false, false>(ta, tb, tc, p, st);
-    case 3: return launch_gemm<128, true, true>(ta, tb, tc, p, st);
-    case 2: return launch_gemm<128, true, false>(ta, tb, tc, p, st);
-    case 1: return launch_gemm<128, false, true>(ta, tb, tc, p, st);
-    default: return launch_gemm<128, false, false>(ta, tb, tc, p, st);
-  }
+  FusedArgs fa;
+  memset(&fa, 0, sizeof(fa));
+  CMaps cm;
+  memset(&cm, 0, sizeof(cm));
+  const int tiles = p.m_tiles * p.n_tiles;
+  const int grid = tiles < sms ? tiles : sms;
+  return dispatch_gemm<MODE_PLAIN>(bn, a_kmajor != 0, b_kmajor != 0, ta, tb, tc, p, fa, cm, grid,
+                                   (cudaStream_t)stream);
 }
 
-int edb_ag_gemm_bf16(int gid, void* C, const void* A, uint64_t b_shard_off, uint64_t b_full_off,
-                     int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldc, void* stream) {
-  (void)gid; (void)C; (void)A; (void)b_shard_off; (void)b_full_off; (void)M; (void)N; (void)K;
-  (void)lda; (void)ldc; (void)stream;
-  return set_error(EDB_E_UNSUPPORTED, "edb_ag_gemm_bf16: not built yet");
+int edb_ag_gemm_bf16(int gid, void* C, const void* A, const void* bias, uint64_t b_shard_off,
+                     uint64_t b_full_off, int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldc,
+                     void* stream) {
+  FusedArgs fa;
+  memset(&fa, 0, sizeof(fa));
+  int rc = fill_flagctx(&fa.f, gid);
+  if (rc) return rc;
+  Runtime& r = rt();
+  const Group& g = r.groups[gid];
+  const int n = g.n, me = g.me;
+  if (N % n) return set_error(EDB_E_UNSUPPORTED, "edb_ag_gemm_bf16: N %% group size != 0");
+  const int64_t rows = N / n;
+  int bn = 0;
+  if (rows % 256 == 0) bn = 256;
+  else if (rows % 128 == 0) bn = 128;
+  else return set_error(EDB_E_UNSUPPORTED, "edb_ag_gemm_bf16: shard rows %lld not a multiple of 128",
+                        (long long)rows);
+  if (K & 7) return set_error(EDB_E_UNSUPPORTED, "edb_ag_gemm_bf16: K must be a multiple of 8");
+  const size_t shard_bytes = (size_t)rows * K * 2;
+  if (b_shard_off < kUserOffset || b_shard_off + shard_bytes > r.heap_bytes || (b_shard_off & 15) ||
+      b_full_off < kUserOffset || b_full_off + shard_bytes * n > r.heap_bytes || (b_full_off & 1023))
+    return set_error(EDB_E_INVALID, "edb_ag_gemm_bf16: bad symmetric offsets");
+  const char* shard = r.heap + b_shard_off;
+  char* full = r.heap + b_full_off;
+  rc = check_operands(A, full, C, bias, M, N, K, lda, K, ldc, "edb_ag_gemm_bf16");
+  if (rc) return rc;
+  CUtensorMap ta, tb, tc;
+  rc = make_tmap(&ta, A, K, M, lda, BK, BM);
+  if (rc) return rc;
+  rc = make_tmap(&tb, full, K, N, K, BK, bn);
+  if (rc) return rc;
+  rc = make_tmap(&tc, C, N, M, ldc, 64, BM);
+  if (rc) return rc;
+  CMaps cm;
+  memset(&cm, 0, sizeof(cm));
+  rc = make_tmap(&cm.m[0], shard, K, rows, K, BK, bn);
+  if (rc) return rc;
+  GemmParams p;
+  p.C = static_cast<__nv_bfloat16*>(C);
+  p.bias = static_cast<const __nv_bfloat16*>(bias);
+  p.ldc = ldc;
+  p.M = (int)M;
+  p.N = (int)N;
+  p.K = (int)K;
+  p.m_tiles = (int)((M + BM - 1) / BM);
+  p.n_tiles = (int)(N / bn);
+  const int sms = r.sm_count;
+  int n_comm = (int)r.comm_ctas;
+  if (n_comm < 1) n_comm = 1;
+  if (n_comm > sms / 4) n_comm = sms / 4;
+  if (n == 1) n_comm = 1;
+  fa.n_comm = n_comm;
+  for (int pidx = 0; pidx < n; ++pidx) fa.shard_src[pidx] = r.peer_heap[g.ranks[pidx]] + b_shard_off;
+  fa.shard_src[me] = shard;
+  fa.full_dst = full;
+  fa.shard_bytes = (int64_t)shard_bytes;
+  const int tiles = p.m_tiles * p.n_tiles;
+  int gemm_ctas = sms - n_comm;
+  if (gemm_ctas > tiles) gemm_ctas = tiles;
+  return dispatch_gemm<MODE_AG>(bn, true, true, ta, tb, tc, p, fa, cm, gemm_ctas + n_comm,
+                                (cudaStream_t)stream);
 }
 
-int edb_gemm_rs_bf16(int gid, void* dst, uint64_t c_stage_off, const void* A, const void* B,
+int edb_gemm_rs_bf16(int gid, void* dst, uint64_t recv_off, const void* A, const void* B,
                      int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb, int a_kmajor,
                      int b_kmajor, float post_scale, int out_dtype, void* stream) {
-  (void)gid; (void)dst; (void)c_stage_off; (void)A; (void)B; (void)M; (void)N; (void)K; (void)lda;
-  (void)ldb; (void)a_kmajor; (void)b_kmajor; (void)post_scale; (void)out_dtype; (void)stream;
-  return set_error(EDB_E_UNSUPPORTED, "edb_gemm_rs_bf16: not built yet");
+  FusedArgs fa;
+  memset(&fa, 0, sizeof(fa));
+  int rc = fill_flagctx(&fa.f, gid);
+  if (rc) return rc;
+  Runtime& r = rt();
+  const Group& g = r.groups[gid];
+  const int n = g.n, me = g.me;
+  if (M % n || (M / n) % BM)
+    return set_error(EDB_E_UNSUPPORTED, "edb_gemm_rs_bf16: rows per rank must be a multiple of 128");
+  if (N & 7) return set_error(EDB_E_UNSUPPORTED, "edb_gemm_rs_bf16: N must be a multiple of 8");
+  if (out_dtype != EDB_BF16 && out_dtype != EDB_F32)
+    return set_error(EDB_E_UNSUPPORTED, "edb_gemm_rs_bf16: out dtype must be bf16 or f32");
+  const int64_t rows = M / n;
+  const size_t chunk_bytes = (size_t)rows * N * 2;
+  if (recv_off < kUserOffset || recv_off + chunk_bytes * n > r.heap_bytes || (recv_off & 1023))
+    return set_error(EDB_E_INVALID, "edb_gemm_rs_bf16: bad symmetric offset");
+  char* recv = r.heap + recv_off;
+  rc = check_operands(A, B, recv, nullptr, M, N, K, lda, ldb, N, "edb_gemm_rs_bf16");
+  if (rc) return rc;
+  const int sms = r.sm_count;
+  const int bn = pick_bn(M, N, sms);
+  CUtensorMap ta, tb, tc;
+  if (a_kmajor) rc = make_tmap(&ta, A, K, M, lda, BK, BM);
+  else rc = make_tmap(&ta, A, M, K, lda, 64, BK);
+  if (rc) return rc;
+  if (b_kmajor) rc = make_tmap(&tb, B, K, N, ldb, BK, bn);
+  else rc = make_tmap(&tb, B, N, K, ldb, 64, BK);
+  if (rc) return rc;
+  CMaps cm;
+  memset(&cm, 0, sizeof(cm));
+  for (int pidx = 0; pidx < n; ++pidx) {
+    // rows owned by member pidx land in ITS receive buffer, slot [me]
+    char* slot = r.peer_heap[g.ranks[pidx]] + recv_off + (size_t)me * chunk_bytes;
+    rc = make_tmap(&cm.m[pidx], slot, N, rows, N, 64, BM);
+    if (rc) return rc;
+  }
+  tc = cm.m[me];
+  GemmParams p;
+  p.C = reinterpret_cast<__nv_bfloat16*>(recv);
+  p.bias = nullptr;
+  p.ldc = N;
+  p.M = (int)M;
+  p.N = (int)N;
+  p.K = (int)K;
+  p.m_tiles = (int)(M / BM);
+  p.n_tiles = (int)((N + bn - 1) / bn);
+  fa.recv_base = recv;
+  fa.chunk_bytes = (int64_t)chunk_bytes;
+  fa.rs_dst = dst;
+  fa.rs_scale = post_scale;
+  fa.rs_out_dtype = out_dtype;
+  fa.tiles_per_chunk = (p.m_tiles / n) * p.n_tiles;
+  const int tiles = p.m_tiles * p.n_tiles;
+  const int grid = tiles < sms ? tiles : sms;
+  return dispatch_gemm<MODE_RS>(bn, a_kmajor != 0, b_kmajor != 0, ta, tb, tc, p, fa, cm, grid,
+                                (cudaStream_t)stream);
 }
 
 }  // extern "C"

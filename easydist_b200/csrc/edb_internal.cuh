@@ -195,4 +195,65 @@ __device__ __forceinline__ bool spin_wait_sys(const uint64_t* flag, uint64_t tar
   return true;
 }
 
+// ---- flag protocol ---------------------------------------------------------------------------------
+
+// Returns the op number of this launch after the write-after-read guard.
+__device__ __forceinline__ uint64_t begin_op(const FlagCtx& f, uint64_t* s_q) {
+  if (threadIdx.x == 0) *s_q = ld_relaxed_gpu(f.local + F_SEQ) + 1;
+  if (threadIdx.x < 32) {
+    const int b = threadIdx.x >> 3, p = threadIdx.x & 7;
+    if (b < f.n_war && p < f.war_n[b] && p != f.war_me[b]) {
+      const uint64_t* blk = f.war_block[b];
+      const uint64_t seq = ld_relaxed_gpu(blk + F_SEQ);
+      spin_wait_sys(blk + F_DONE + p, seq, f.timeout_ns, f.local + F_ERR);
+    }
+  }
+  __syncthreads();
+  return *s_q;
+}
+
+// Grid-wide "everyone arrived" (no wait): the last CTA to arrive publishes `q` to word
+// `flag_base + me` of every member's flag block (its own included).
+__device__ __forceinline__ void grid_signal(const FlagCtx& f, int cnt_word, int flag_base,
+                                            uint64_t q, int* s_last, unsigned n_ctas) {
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned long long prev =
+        atomicAdd(reinterpret_cast<unsigned long long*>(f.local + cnt_word), 1ULL);
+    const int last = (prev == (unsigned long long)n_ctas - 1);
+    if (last) f.local[cnt_word] = 0;
+    __threadfence_system();
+    *s_last = last;
+  }
+  __syncthreads();
+  if (*s_last && threadIdx.x < f.n) st_release_sys(f.peer[threadIdx.x] + flag_base + f.me, q);
+}
+
+__device__ __forceinline__ void wait_flag(const FlagCtx& f, int flag_base, int p, uint64_t q) {
+  if (threadIdx.x == 0) spin_wait_sys(f.local + flag_base + p, q, f.timeout_ns, f.local + F_ERR);
+  __syncthreads();
+}
+
+__device__ __forceinline__ void finish_op(const FlagCtx& f, uint64_t q, int* s_last,
+                                          unsigned n_ctas) {
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned long long prev =
+        atomicAdd(reinterpret_cast<unsigned long long*>(f.local + F_CNT_B), 1ULL);
+    const int last = (prev == (unsigned long long)n_ctas - 1);
+    if (last) f.local[F_CNT_B] = 0;
+    __threadfence_system();
+    *s_last = last;
+  }
+  __syncthreads();
+  if (*s_last) {
+    if (threadIdx.x < f.n && threadIdx.x != f.me)
+      st_release_sys(f.peer[threadIdx.x] + F_DONE + f.me, q);
+    if (threadIdx.x == 0) st_release_gpu(f.local + F_SEQ, q);
+  }
+}
+
+
 }  // namespace edb

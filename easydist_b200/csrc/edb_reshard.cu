@@ -114,65 +114,6 @@ __device__ __forceinline__ void copy_box(const Box& b, uint64_t tid, uint64_t nt
   }
 }
 
-// ---- flag protocol ---------------------------------------------------------------------------------
-
-// Returns the op number of this launch after the write-after-read guard.
-__device__ __forceinline__ uint64_t begin_op(const FlagCtx& f, uint64_t* s_q) {
-  if (threadIdx.x == 0) *s_q = ld_relaxed_gpu(f.local + F_SEQ) + 1;
-  if (threadIdx.x < 32) {
-    const int b = threadIdx.x >> 3, p = threadIdx.x & 7;
-    if (b < f.n_war && p < f.war_n[b] && p != f.war_me[b]) {
-      const uint64_t* blk = f.war_block[b];
-      const uint64_t seq = ld_relaxed_gpu(blk + F_SEQ);
-      spin_wait_sys(blk + F_DONE + p, seq, f.timeout_ns, f.local + F_ERR);
-    }
-  }
-  __syncthreads();
-  return *s_q;
-}
-
-// Grid-wide "everyone arrived" (no wait): the last CTA to arrive publishes `q` to word
-// `flag_base + me` of every member's flag block (its own included).
-__device__ __forceinline__ void grid_signal(const FlagCtx& f, int cnt_word, int flag_base,
-                                            uint64_t q, int* s_last) {
-  __threadfence_system();
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    const unsigned long long prev =
-        atomicAdd(reinterpret_cast<unsigned long long*>(f.local + cnt_word), 1ULL);
-    const int last = (prev == (unsigned long long)gridDim.x - 1);
-    if (last) f.local[cnt_word] = 0;
-    __threadfence_system();
-    *s_last = last;
-  }
-  __syncthreads();
-  if (*s_last && threadIdx.x < f.n) st_release_sys(f.peer[threadIdx.x] + flag_base + f.me, q);
-}
-
-__device__ __forceinline__ void wait_flag(const FlagCtx& f, int flag_base, int p, uint64_t q) {
-  if (threadIdx.x == 0) spin_wait_sys(f.local + flag_base + p, q, f.timeout_ns, f.local + F_ERR);
-  __syncthreads();
-}
-
-__device__ __forceinline__ void finish_op(const FlagCtx& f, uint64_t q, int* s_last) {
-  __threadfence_system();
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    const unsigned long long prev =
-        atomicAdd(reinterpret_cast<unsigned long long*>(f.local + F_CNT_B), 1ULL);
-    const int last = (prev == (unsigned long long)gridDim.x - 1);
-    if (last) f.local[F_CNT_B] = 0;
-    __threadfence_system();
-    *s_last = last;
-  }
-  __syncthreads();
-  if (*s_last) {
-    if (threadIdx.x < f.n && threadIdx.x != f.me)
-      st_release_sys(f.peer[threadIdx.x] + F_DONE + f.me, q);
-    if (threadIdx.x == 0) st_release_gpu(f.local + F_SEQ, q);
-  }
-}
-
 // ---- kernels -----------------------------------------------------------------------------------------
 
 __global__ void __launch_bounds__(kThreads) k_local_copy(const __grid_constant__ GatherDesc d) {
@@ -188,13 +129,13 @@ __global__ void __launch_bounds__(kThreads) k_gather(const __grid_constant__ Gat
   const uint64_t nthr = (uint64_t)gridDim.x * blockDim.x;
   const uint64_t q = begin_op(d.f, &s_q);
   for (int b = 0; b < d.n_in; ++b) copy_box(d.box[b], tid, nthr);
-  grid_signal(d.f, F_CNT_A, F_READY, q, &s_last);
+  grid_signal(d.f, F_CNT_A, F_READY, q, &s_last, gridDim.x);
   for (int b = d.n_in; b < d.n_boxes; ++b) {
     const int p = d.box[b].peer;
     if (p >= 0 && p != d.f.me) wait_flag(d.f, F_READY, p, q);
     copy_box(d.box[b], tid, nthr);
   }
-  finish_op(d.f, q, &s_last);
+  finish_op(d.f, q, &s_last, gridDim.x);
 }
 
 __global__ void __launch_bounds__(32) k_guard(const __grid_constant__ FlagCtx f) {
@@ -358,7 +299,7 @@ __global__ void __launch_bounds__(kThreads, 3) k_reduce(const __grid_constant__ 
   if (multi) {
     q = begin_op(d.f, &s_q);
     if (d.has_in) copy_box(d.in, tid, nthr);
-    grid_signal(d.f, F_CNT_A, F_READY, q, &s_last);
+    grid_signal(d.f, F_CNT_A, F_READY, q, &s_last, gridDim.x);
     if (threadIdx.x < d.f.n && threadIdx.x != d.f.me)
       spin_wait_sys(d.f.local + F_READY + threadIdx.x, q, d.f.timeout_ns, d.f.local + F_ERR);
     __syncthreads();
@@ -366,13 +307,13 @@ __global__ void __launch_bounds__(kThreads, 3) k_reduce(const __grid_constant__ 
   reduce_rows<In, Out, OP>(d, L.dst_b, tid, nthr, L.vec != 0);
   if (multi) {
     if (d.two_shot) {
-      grid_signal(d.f, F_CNT_C, F_READY2, q, &s_last);
+      grid_signal(d.f, F_CNT_C, F_READY2, q, &s_last, gridDim.x);
       for (int b = 0; b < d.n_pull; ++b) {
         wait_flag(d.f, F_READY2, d.pull[b].peer, q);
         copy_box(d.pull[b], tid, nthr);
       }
     }
-    finish_op(d.f, q, &s_last);
+    finish_op(d.f, q, &s_last, gridDim.x);
   }
 }
 

@@ -428,6 +428,116 @@ def dispatch_compute(gm):
     return n
 
 
+def fuse_collective_gemms(gm, io, rt, ranks, ops=_default_ops):
+    """Peephole fusion of reshard edges into the adjacent GEMM (B200 runtime only):
+
+      all_gather(param shard) -> view -> t -> mm/addmm        ==>  ops.ag_mm   (AG + GEMM, one kernel)
+      mm -> flatten -> reduce_scatter(avg, dim 0)              ==>  ops.mm_rs   (GEMM + RS, one kernel)
+
+    Returns {placeholder name: SymmBuffer} for parameter shards that must live in the symmetric
+    heap (peers read them directly), after inserting a symm_guard in front of the optimizer."""
+    graph = gm.graph
+    n = len(ranks)
+    if n <= 1:
+        return {}, {"ag_mm": 0, "mm_rs": 0}
+    order = {nd: i for i, nd in enumerate(graph.nodes)}
+    rehomed = {}
+    n_ag = n_rs = 0
+    bf16 = torch.bfloat16
+
+    def val(nd):
+        return nd.meta.get("val") if isinstance(nd, Node) else None
+
+    # ---- all-gather + GEMM ---------------------------------------------------------------
+    for ag_s in [x for x in graph.nodes if x.op == "call_function" and x.target is ops.all_gather_start]:
+        ph = ag_s.args[0]
+        if not (isinstance(ph, Node) and ph.op == "placeholder" and ph in io.param_ph):
+            continue
+        if ag_s.args[1] != 0 or len(ag_s.users) != 1:
+            continue
+        ag_e = next(iter(ag_s.users))
+        if ag_e.target is not ops.all_gather_end or len(ag_e.users) != 1:
+            continue
+        v = next(iter(ag_e.users))
+        if v.target != aten.view.default or len(v.args[1]) != 2 or len(v.users) != 1:
+            continue
+        n_out, k_in = (int(d) for d in v.args[1])
+        t = next(iter(v.users))
+        if t.target != aten.t.default or not t.users:
+            continue
+        first = min(t.users, key=lambda u: order[u])
+        if first.target == aten.addmm.default and first.args[2] is t and not first.kwargs:
+            bias, x = first.args[0], first.args[1]
+        elif first.target == aten.mm.default and first.args[1] is t:
+            bias, x = None, first.args[0]
+        else:
+            continue
+        xv, pv = val(x), val(ph)
+        if xv is None or pv is None or xv.dtype != bf16 or pv.dtype != bf16 or xv.dim() != 2:
+            continue
+        if n_out % n or (n_out // n) % 128 or k_in % 8 or xv.shape[1] != k_in:
+            continue
+        if bias is not None and (val(bias) is None or val(bias).dim() != 1 or n_out % 8):
+            continue
+        shard = rehomed.get(ph.name) or rt.alloc(n_out // n * k_in * 2, align=1024)
+        full = rt.alloc(n_out * k_in * 2, align=1024)
+        rehomed[ph.name] = shard
+        with graph.inserting_before(first):
+            fused = graph.call_function(ops.ag_mm, args=(x, ph, list(ranks), n_out, k_in, bias),
+                                        kwargs={"_buf": (shard.offset, full.offset)})
+            out = graph.call_function(operator.getitem, args=(fused, 0))
+            wfull = graph.call_function(operator.getitem, args=(fused, 1))
+            t_new = graph.call_function(aten.t.default, args=(wfull,))
+        first.replace_all_uses_with(out)
+        graph.erase_node(first)
+        t.replace_all_uses_with(t_new)
+        for dead in (t, v, ag_e, ag_s):
+            graph.erase_node(dead)
+        n_ag += 1
+
+    # ---- GEMM + reduce-scatter -------------------------------------------------------------
+    for rs_s in [x for x in graph.nodes if x.op == "call_function" and x.target is ops.reduce_scatter_start]:
+        f = rs_s.args[0]
+        if rs_s.args[1] != "avg" or rs_s.args[2] != 0 or rs_s.kwargs:
+            continue
+        if not (isinstance(f, Node) and f.target == aten.flatten.using_ints and len(f.users) == 1):
+            continue
+        g = f.args[0]
+        if not (isinstance(g, Node) and g.target == aten.mm.default and len(g.users) == 1):
+            continue
+        a, b = g.args
+        av, bv = val(a), val(b)
+        if av is None or bv is None or av.dtype != bf16 or bv.dtype != bf16:
+            continue
+        M, N = av.shape[0], bv.shape[1]
+        if M % n or (M // n) % 128 or N % 8:
+            continue
+        if len(rs_s.users) != 1:
+            continue
+        rs_e = next(iter(rs_s.users))
+        recv = rt.alloc(M * N * 2, align=1024)
+        with graph.inserting_before(rs_s):
+            fused = graph.call_function(ops.mm_rs, args=(a, b, list(ranks)),
+                                        kwargs={"_buf": (recv.offset,), "_scale": 1.0 / n})
+        rs_e.replace_all_uses_with(fused)
+        for dead in (rs_e, rs_s, f, g):
+            graph.erase_node(dead)
+        n_rs += 1
+
+    # peers read parameter shards in place: keep the optimizer from overwriting them too early
+    if rehomed:
+        region = optimizer_region(gm, io)
+        if region:
+            anchor = region[0]
+            some_input = next((a_ for a_ in pytree.tree_flatten((anchor.args, anchor.kwargs))[0]
+                               if isinstance(a_, Node)), None)
+            with graph.inserting_before(anchor):
+                graph.call_function(ops.symm_guard, args=(some_input, list(ranks)))
+    graph.lint()
+    gm.recompile()
+    return rehomed, {"ag_mm": n_ag, "mm_rs": n_rs}
+
+
 def reinplace_optimizer_updates(gm):
     """Undo the functionalisation of optimizer updates where it is safe.
 
@@ -498,6 +608,8 @@ def count_nodes(gm, ops=_default_ops):
     for node in gm.graph.nodes:
         if node.op == "call_function":
             name = getattr(node.target, "__name__", str(node.target))
-            if node.target in ops.CUSTOM_FUNCS or "gemm" in getattr(node.target, "__module__", ""):
+            fused = getattr(ops, "FUSED_FUNCS", [])
+            if node.target in ops.CUSTOM_FUNCS or node.target in fused or \
+                    "gemm" in getattr(node.target, "__module__", ""):
                 hist[name] = hist.get(name, 0) + 1
     return hist

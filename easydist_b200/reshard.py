@@ -331,6 +331,69 @@ def box_exchange(tensor, dst_shape, boxes, peer_src_shapes, group, *, _buf=None)
     return out
 
 
+# ---- fused compute + collective (one kernel each) -----------------------------------------------------
+
+
+def symm_guard(x, group):
+    """Pass-through that makes the stream wait until no peer is still reading this rank's
+    symmetric buffers (inserted in front of producers that write symmetric memory in place, e.g.
+    the optimizer update of symmetric parameter shards)."""
+    if _is_fake(x) or len(group) <= 1:
+        return x
+    rt, gid, n, _ = _group(group)
+    check(rt.lib.edb_symm_guard(gid, rt.stream()))
+    return x
+
+
+def ag_mm(x, w_shard, group, n_out, k_in, bias=None, *, _buf):
+    """all_gather(weight shard, dim 0) fused into the consuming GEMM (all_gather_end -> aten.mm /
+    addmm of the sharded graph).  `w_shard`: this rank's rows [n_out/n, k_in] (flat or 2-D) living
+    at symmetric offset _buf[0]; _buf[1] = offset of the gathered [n_out, k_in] buffer that the
+    kernel's copy CTAs fill while the MMA CTAs already run.  Returns (x @ W^T (+ bias), W_full)."""
+    n = len(group)
+    if _is_fake(x):
+        return (x.new_empty((x.shape[0], n_out)), w_shard.new_empty((n_out, k_in)))
+    _require_cuda(x, "ag_mm")
+    rt, gid, n, me = _group(group)
+    shard_off, full_off = int(_buf[0]), int(_buf[1])
+    assert w_shard.data_ptr() == rt.heap_base + shard_off, "weight shard is not at its symmetric offset"
+    xc = x if (x.stride(1) == 1 and x.stride(0) % 8 == 0 and x.data_ptr() % 16 == 0) else x.contiguous()
+    M, K = xc.shape
+    assert K == k_in
+    out = torch.empty((M, n_out), dtype=torch.bfloat16, device=x.device)
+    check(rt.lib.edb_ag_gemm_bf16(gid, out.data_ptr(), xc.data_ptr(),
+                                  bias.data_ptr() if bias is not None else None, shard_off, full_off,
+                                  M, n_out, K, xc.stride(0), n_out, rt.stream()))
+    w_full = SymmBuffer(rt, full_off, n_out * k_in * 2).tensor(torch.bfloat16, (n_out, k_in))
+    return out, w_full
+
+
+def mm_rs(a, b, group, *, _buf, _scale=1.0, _out_dtype=None):
+    """aten.mm fused with reduce_scatter(dim 0): rank r gets rows [r*M/n, (r+1)*M/n) of
+    sum_over_ranks(a @ b) * _scale, flattened (mm -> flatten -> reduce_scatter_start of the
+    zero2/zero3 graphs).  Tiles are TMA-stored straight into the owner's receive slot over NVLink;
+    _buf[0] = symmetric offset of the receive buffer (M*N*2 bytes)."""
+    n = len(group)
+    M, K = a.shape
+    N = b.shape[1]
+    out_dtype = _out_dtype or torch.bfloat16
+    if _is_fake(a):
+        return a.new_empty((M // n * N,), dtype=out_dtype)
+    _require_cuda(a, "mm_rs")
+    from . import gemm as _gemm
+    rt, gid, n, me = _group(group)
+    pa, pb = _gemm._prepare(a, 1), _gemm._prepare(b, 0)
+    if pa is None or pb is None:
+        raise _lib.EdbUnsupported(_lib.EDB_E_UNSUPPORTED, "mm_rs: operand layout")
+    (ta, a_k, lda), (tb, b_k, ldb) = pa, pb
+    out = torch.empty((M // n * N,), dtype=out_dtype, device=a.device)
+    check(rt.lib.edb_gemm_rs_bf16(gid, out.data_ptr(), int(_buf[0]), ta.data_ptr(), tb.data_ptr(),
+                                  M, N, K, lda, ldb, 1 if a_k else 0, 1 if b_k else 0,
+                                  float(_scale), _TORCH_DTYPE_CODE[out_dtype], rt.stream()))
+    return out
+
+
 COMM_FUNCS = [all_reduce_start, all_gather_start, reduce_scatter_start, all_to_all_start]
 COMM_SYNC_FUNCS = [all_reduce_end, all_gather_end, reduce_scatter_end, all_to_all_end]
 CUSTOM_FUNCS = COMM_FUNCS + COMM_SYNC_FUNCS + [scatter_wrapper, copy_wrapper]
+FUSED_FUNCS = [ag_mm, mm_rs, symm_guard]

@@ -173,8 +173,9 @@ int edb_gemm_bf16(void* C, const void* A, const void* B, const void* bias, int64
  * copy CTAs pull the peer shards into the local gathered buffer `b_full_off` chunk by chunk while
  * the MMA CTAs start on the local shard and consume chunks as their flags arrive.
  * C[M,N] = A[M,K]·B_fullᵀ.  (all_gather_end -> aten.mm pattern) */
-int edb_ag_gemm_bf16(int gid, void* C, const void* A, uint64_t b_shard_off, uint64_t b_full_off,
-                     int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldc, void* stream);
+int edb_ag_gemm_bf16(int gid, void* C, const void* A, const void* bias, uint64_t b_shard_off,
+                     uint64_t b_full_off, int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldc,
+                     void* stream);
 
 /* GEMM fused with reduce-scatter: partial C[M,N] = A·B is produced tile by tile into the
  * symmetric stage `c_stage_off` (row-chunks destined for other ranks first); reduce CTAs of the

@@ -175,6 +175,107 @@ def run_graph(rank, world, group):
     return 5
 
 
+def run_fused(rank, world, group):
+    """Fused all-gather+GEMM and GEMM+reduce-scatter vs the unfused kernels: bit-exact (same
+    tile math, same reduction order)."""
+    from easydist_b200 import gemm
+    rt = runtime.get_runtime()
+    n_ok = 0
+    torch.manual_seed(1234)  # same on every rank: every rank knows every shard
+    for (M, N, K, with_bias) in [(512, 256 * world, 256, False), (4096, 1024, 1024, True),
+                                 (384, 128 * world, 1000 // 8 * 8, False), (4096, 4096, 1024, True)]:
+        if (N // world) % 128:
+            continue
+        W = (torch.randn(N, K, device="cuda") * 0.1).bfloat16()
+        x = torch.randn(M, K, device="cuda").bfloat16()
+        bias = torch.randn(N, device="cuda").bfloat16() if with_bias else None
+        rows = N // world
+        shard_buf = rt.alloc(rows * K * 2, align=1024)
+        full_buf = rt.alloc(N * K * 2, align=1024)
+        w_shard = shard_buf.tensor(torch.bfloat16, (rows, K))
+        for it in range(3):  # repeated: WAR guard + epochs
+            w_shard.copy_(W[rank * rows:(rank + 1) * rows] * (it + 1))
+            reshard.symm_guard(w_shard, group)
+            out, w_full = reshard.ag_mm(x, w_shard, group, N, K, bias,
+                                        _buf=(shard_buf.offset, full_buf.offset))
+            Wi = W * (it + 1)
+            ref = gemm.addmm(bias, x, Wi.t()) if with_bias else gemm.mm(x, Wi.t())
+            assert torch.equal(w_full, Wi), f"ag_mm gathered weight mismatch {(M, N, K)} it {it}"
+            assert torch.equal(out, ref), f"ag_mm output mismatch {(M, N, K)} it {it}: " \
+                f"{(out.float() - ref.float()).abs().max()}"
+            n_ok += 1
+    for (M, N, K) in [(128 * world, 256, 512), (1024, 1024, 4096), (4096, 1024, 4096),
+                      (256 * world, 4096, 1024)]:
+        if (M // world) % 128:
+            continue
+        g = torch.Generator(device="cuda").manual_seed(77)
+        a_all = [torch.randn(K, M, device="cuda", generator=g).bfloat16() for _ in range(world)]
+        b_all = [torch.randn(K, N, device="cuda", generator=g).bfloat16() for _ in range(world)]
+        recv = rt.alloc(M * N * 2, align=1024)
+        stage = rt.alloc(M * N * 2, align=1024)
+        for it in range(3):
+            a = a_all[rank].t()        # [M,K] column-major (dy^T of a wgrad)
+            b = b_all[rank]            # [K,N] row-major
+            got = reshard.mm_rs(a, b, group, _buf=(recv.offset,), _scale=1.0 / world)
+            part = gemm.mm(a, b)
+            want = reshard.reduce_scatter_start(part.flatten(), "avg", 0, group,
+                                                _buf=(stage.offset, M * N * 2))
+            assert torch.equal(got, want), f"mm_rs mismatch {(M, N, K)} it {it}: " \
+                f"{(got.float() - want.float()).abs().max()}"
+            n_ok += 1
+    return n_ok
+
+
+def bench_fused(rank, world, group):
+    from easydist_b200 import gemm
+    rt = runtime.get_runtime()
+
+    def timeit(f, iters=20):
+        for _ in range(3):
+            f()
+        dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            f()
+        e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1) / iters], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item() * 1e3
+
+    for (M, N, K) in [(4096, 1024, 1024), (4096, 4096, 1024), (4096, 1024, 4096), (4096, 3072, 1024)]:
+        rows = N // world
+        x = torch.randn(M, K, device="cuda").bfloat16()
+        shard_buf, full_buf = rt.alloc(rows * K * 2, align=1024), rt.alloc(N * K * 2, align=1024)
+        ag_buf = rt.alloc(N * K * 2, align=1024)
+        w_shard = shard_buf.tensor(torch.bfloat16, (rows, K))
+        w_shard.normal_()
+        t_fused = timeit(lambda: reshard.ag_mm(x, w_shard, group, N, K, None,
+                                                _buf=(shard_buf.offset, full_buf.offset)))
+
+        def unfused():
+            w = reshard.all_gather_start(w_shard, 0, group, _buf=(ag_buf.offset, N * K * 2))
+            return gemm.mm(x, w.t())
+        t_unf = timeit(unfused)
+        t_gemm = timeit(lambda: gemm.mm(x, full_buf.tensor(torch.bfloat16, (N, K)).t()))
+        # wgrad-like: dW[N,K] = dy^T[N,M] @ x[M,K], reduce-scattered over N
+        dy = torch.randn(M, N, device="cuda").bfloat16()
+        recv, stage = rt.alloc(N * K * 2, align=1024), rt.alloc(N * K * 2, align=1024)
+        t_rs_f = timeit(lambda: reshard.mm_rs(dy.t(), x, group, _buf=(recv.offset,), _scale=1.0 / world))
+
+        def unfused_rs():
+            part = gemm.mm(dy.t(), x)
+            return reshard.reduce_scatter_start(part.flatten(), "avg", 0, group,
+                                                _buf=(stage.offset, N * K * 2))
+        t_rs_u = timeit(unfused_rs)
+        if rank == 0:
+            print(f"FUSED M{M} N{N} K{K}: ag+gemm fused {t_fused:.1f}us unfused {t_unf:.1f}us "
+                  f"(gemm alone {t_gemm:.1f}us) | gemm+rs fused {t_rs_f:.1f}us unfused {t_rs_u:.1f}us",
+                  flush=True)
+
+
 def bench(rank, world, group):
     rt = runtime.get_runtime()
     res = []
@@ -246,6 +347,7 @@ def main():
     n += run_cases(rank, world, group, tag="b")  # second pass: epochs keep counting
     n += run_p2p(rank, world, group)
     n += run_graph(rank, world, group)
+    n += run_fused(rank, world, group)
     if world >= 4 and world % 2 == 0:
         # 2-D mesh: groups along each mesh dim (ranks in mesh-coordinate order)
         mesh = np.arange(world).reshape(2, world // 2)
@@ -267,6 +369,7 @@ def main():
     if rank == 0:
         print(f"MGPU_OK world={world} checks={n} launches={rt.launch_count()}", flush=True)
     if args.bench:
+        bench_fused(rank, world, group)
         bench(rank, world, group)
     dist.barrier()
     dist.destroy_process_group()
