@@ -39,6 +39,8 @@ def parse_args():
     ap.add_argument("--seq", type=int, default=512)
     ap.add_argument("--attn", default="sdpa", choices=["sdpa", "unfused"])
     ap.add_argument("--no-cuda-graph", action="store_true")
+    ap.add_argument("--no-fuse", action="store_true",
+                    help="keep all-gather / reduce-scatter as separate kernels (no AG+GEMM, GEMM+RS)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-seqs", type=int, default=2)
     ap.add_argument("--heap-gb", type=float, default=12.0)
@@ -211,7 +213,7 @@ def run_edb(args):
     host = [(t.pin_memory(), y.pin_memory()) for t, y in host]
     dev = [(t.cuda(), y.cuda()) for t, y in host]
     step_fn = easydist_compile(gpt2_train_step, parallel_mode=args.mode, tracing_mode="fake",
-                               cuda_graph=not args.no_cuda_graph)
+                               cuda_graph=not args.no_cuda_graph, fuse=not args.no_fuse)
     launches0 = rt.launch_count()
     gemm.reset_stats()
     t0 = time.time()
@@ -285,7 +287,8 @@ def run_edb(args):
         "gpu_launches": launches_per_step * args.steps,
         "gpu_launches_per_step": launches_per_step,
         "dispatch": {"edb_gemm_per_step": gemm_calls_per_step, "aten_mm_per_step": aten_mm_per_step,
-                     "comm_nodes": info.get("comm_nodes"), "symm_bytes": info.get("symm_bytes")},
+                     "comm_nodes": info.get("comm_nodes"), "fused": info.get("fused"),
+                     "symm_bytes": info.get("symm_bytes")},
         "clocks": clocks, "loss": loss_v, "compile_s": compile_s,
     }
     if roof:
