@@ -78,9 +78,8 @@ def _finish(gm, params, buffers, named_states, args, kwargs, ops, native, io=Non
             home = buf.tensor(t.dtype, t.shape)
             home.copy_(t)
             params[pname] = home
-        if rehomed:
-            lowering.propagate_local_meta(gm, _flat_inputs(params, buffers, named_states, args,
-                                                           kwargs))
+        lowering.propagate_local_meta(gm, _flat_inputs(params, buffers, named_states, args,
+                                                       kwargs))
     info["comm_nodes"] = lowering.count_nodes(gm, ops)
     info["reinplaced_updates"] = lowering.reinplace_optimizer_updates(gm)
     if native:
@@ -93,7 +92,7 @@ def _finish(gm, params, buffers, named_states, args, kwargs, ops, native, io=Non
 
 
 def _compile_dp(func, parallel_mode, tracing_mode, args, kwargs, *, ops=_default_ops,
-                native=True, fuse=True):
+                native=True, fuse=True, bucket_numel=None):
     """ddp / zero2 / zero3 (reference: _compile_dp, compile_dp.py:201-381)."""
     mode = parallel_mode.replace("b200_", "")
     assert mode in DP_MODES, parallel_mode
@@ -107,8 +106,11 @@ def _compile_dp(func, parallel_mode, tracing_mode, args, kwargs, *, ops=_default
         if mode == "ddp":
             lowering.transform_ddp(gm, io, ranks, ops)
         else:
+            if bucket_numel is None:
+                bucket_numel = 65536 if native else 0
             _, shard_info = lowering.transform_fsdp(gm, io, ranks, my_index,
-                                                    shard_param=(mode == "zero3"), ops=ops)
+                                                    shard_param=(mode == "zero3"), ops=ops,
+                                                    bucket_numel=bucket_numel)
     # pre-shard parameters (zero3) and optimizer states (zero2/zero3): flat 1/n shards
     # (compile_dp.py:330-343)
     with torch.no_grad():

@@ -275,7 +275,35 @@ def transform_ddp(gm, io, ranks, ops=_default_ops):
     return gm
 
 
-def transform_fsdp(gm, io, ranks, my_index, shard_param, ops=_default_ops):
+def _bucket_small_grads(gm, io, ranks, small, region, ops):
+    """One all-reduce(avg) for all small gradients: cat(flatten(g_i)) -> all_reduce -> views.
+    Same rule of thumb as the reference's comm_group pass (passes/comm_optimize.py:223-286 buckets
+    all-reduces below 1 MB into one flat buffer); their parameters stay replicated."""
+    graph = gm.graph
+    grads = [(ph, g) for ph, g in zip(io.param_ph, io.final_grads)
+             if ph in small and isinstance(g, Node)]
+    if not grads:
+        return
+    anchor = region[0]
+    with graph.inserting_before(anchor):
+        flats = [graph.call_function(aten.flatten.using_ints, args=(g,)) for _, g in grads]
+        cat = graph.call_function(aten.cat.default, args=(flats, 0))
+        s = graph.call_function(ops.all_reduce_start, args=(cat, "avg", list(ranks)))
+        e = graph.call_function(ops.all_reduce_end, args=(s, "avg", list(ranks)))
+        off = 0
+        pieces = []
+        for ph, g in grads:
+            shape = list(ph.meta["val"].shape)
+            numel = ph.meta["val"].numel()
+            sl = graph.call_function(aten.slice.Tensor, args=(e, 0, off, off + numel))
+            pieces.append(graph.call_function(aten.view.default, args=(sl, shape)))
+            off += numel
+    own = set(flats)
+    for (ph, g), piece in zip(grads, pieces):
+        g.replace_all_uses_with(piece, delete_user_cb=lambda u: u not in own)
+
+
+def transform_fsdp(gm, io, ranks, my_index, shard_param, ops=_default_ops, bucket_numel=0):
     """zero2 (shard_param=False) / zero3 (True), compile_dp.py:82-198: gradients are flattened and
     reduce-scattered(avg), optimizer states (and, for zero3, parameters) live as flat 1/n shards;
     zero3 all-gathers a parameter in front of each forward/backward use, zero2 scatters the
@@ -295,6 +323,12 @@ def transform_fsdp(gm, io, ranks, my_index, shard_param, ops=_default_ops):
                 f"zero2/zero3: optimizer op {node.target} is not elementwise over (param, grad, "
                 f"state); cannot run it on flat shards")
     shard_info = {}  # placeholder name -> original shape (for pre-sharding the state)
+    # parameters below `bucket_numel` elements are not sharded: their gradients travel in ONE
+    # bucketed all-reduce and they (and their optimizer state) stay replicated (0 = reference
+    # behaviour: everything is sharded tensor by tensor)
+    small = {ph for ph in io.param_ph if ph.meta["val"].numel() < bucket_numel}
+    if small:
+        _bucket_small_grads(gm, io, ranks, small, region, ops)
 
     def check_divisible(ph):
         numel = ph.meta["val"].numel()
@@ -303,7 +337,9 @@ def transform_fsdp(gm, io, ranks, my_index, shard_param, ops=_default_ops):
             raise AssertionError(f"{ph.name}: numel {numel} must be a multiple of group_size {n}")
 
     # (1) gradients: flatten + reduce_scatter(avg) along dim 0
-    for g in dict.fromkeys(x for x in io.final_grads if isinstance(x, Node)):
+    big_grads = [g for ph, g in zip(io.param_ph, io.final_grads)
+                 if isinstance(g, Node) and ph not in small]
+    for g in dict.fromkeys(big_grads):
         with graph.inserting_after(g):
             f = graph.call_function(aten.flatten.using_ints, args=(g,))
         with graph.inserting_after(f):
@@ -314,6 +350,8 @@ def transform_fsdp(gm, io, ranks, my_index, shard_param, ops=_default_ops):
 
     # (2) parameters
     for ph in io.param_ph:
+        if ph in small:
+            continue
         check_divisible(ph)
         shape = list(ph.meta["val"].shape)
         if shard_param:
@@ -347,7 +385,7 @@ def transform_fsdp(gm, io, ranks, my_index, shard_param, ops=_default_ops):
                     user.replace_input_with(ph, sc)
 
     # (3) optimizer states with the parameter's numel live as flat shards
-    param_numels = {ph.meta["val"].numel() for ph in io.param_ph}
+    param_numels = {ph.meta["val"].numel() for ph in io.param_ph if ph not in small}
     for ph, is_t in zip(io.state_ph, io.state_is_tensor):
         if not is_t:
             continue
@@ -503,13 +541,22 @@ def fuse_collective_gemms(gm, io, rt, ranks, ops=_default_ops):
         if not (isinstance(f, Node) and f.target == aten.flatten.using_ints and len(f.users) == 1):
             continue
         g = f.args[0]
-        if not (isinstance(g, Node) and g.target == aten.mm.default and len(g.users) == 1):
+        if not (isinstance(g, Node) and len(g.users) == 1):
             continue
-        a, b = g.args
-        av, bv = val(a), val(b)
+        # the weight gradient of a Linear is traced as t(mm(x^T, dy)): (A.B)^T = B^T.A^T
+        transposed = None
+        mm_node = g
+        if g.target == aten.t.default and isinstance(g.args[0], Node) and \
+                g.args[0].target == aten.mm.default and len(g.args[0].users) == 1:
+            transposed = g
+            mm_node = g.args[0]
+        if mm_node.target != aten.mm.default:
+            continue
+        a0, b0 = mm_node.args
+        av, bv = val(a0), val(b0)
         if av is None or bv is None or av.dtype != bf16 or bv.dtype != bf16:
             continue
-        M, N = av.shape[0], bv.shape[1]
+        M, N = (bv.shape[1], av.shape[0]) if transposed is not None else (av.shape[0], bv.shape[1])
         if M % n or (M // n) % 128 or N % 8:
             continue
         if len(rs_s.users) != 1:
@@ -517,11 +564,19 @@ def fuse_collective_gemms(gm, io, rt, ranks, ops=_default_ops):
         rs_e = next(iter(rs_s.users))
         recv = rt.alloc(M * N * 2, align=1024)
         with graph.inserting_before(rs_s):
+            if transposed is not None:
+                a = graph.call_function(aten.t.default, args=(b0,))
+                b = graph.call_function(aten.t.default, args=(a0,))
+                for nd, src in ((a, bv), (b, av)):
+                    nd.meta["val"] = src.t()
+            else:
+                a, b = a0, b0
             fused = graph.call_function(ops.mm_rs, args=(a, b, list(ranks)),
                                         kwargs={"_buf": (recv.offset,), "_scale": 1.0 / n})
         rs_e.replace_all_uses_with(fused)
-        for dead in (rs_e, rs_s, f, g):
-            graph.erase_node(dead)
+        for dead in (rs_e, rs_s, f, transposed, mm_node):
+            if dead is not None:
+                graph.erase_node(dead)
         n_rs += 1
 
     # peers read parameter shards in place: keep the optimizer from overwriting them too early

@@ -43,7 +43,7 @@ def make_opt(kind, params):
     return torch.optim.Adam(params, lr=1e-2, foreach=True)
 
 
-def _worker(rank, world, port, mode, opt_kind, q):
+def _worker(rank, world, port, mode, opt_kind, q, bucket=0):
     os.environ["OMP_NUM_THREADS"] = "1"
     torch.set_num_threads(1)
     dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank,
@@ -61,7 +61,8 @@ def _worker(rank, world, port, mode, opt_kind, q):
     g = torch.Generator().manual_seed(123)
     batches = [torch.randn(world * 4, 32, generator=g) for _ in range(3)]
     compiled = api._compile_dp(train_step, mode, "fake", (batches[0][rank * 4:(rank + 1) * 4], model,
-                                                         opt), {}, ops=gloo_ops, native=False)
+                                                         opt), {}, ops=gloo_ops, native=False,
+                               bucket_numel=bucket)
     ok = True
     msg = ""
     for b in batches:
@@ -76,7 +77,7 @@ def _worker(rank, world, port, mode, opt_kind, q):
     params = compiled.named_parameters()
     for name, p_ref in ref_model.named_parameters():
         p = params[name]
-        if mode == "zero3":
+        if mode == "zero3" and p.shape != p_ref.shape:
             parts = [torch.empty_like(p) for _ in range(world)]
             dist.all_gather(parts, p.contiguous())
             p = torch.cat(parts).view(p_ref.shape)
@@ -89,14 +90,16 @@ def _worker(rank, world, port, mode, opt_kind, q):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("mode,opt_kind", [("ddp", "sgd"), ("ddp", "sgd_plain"), ("zero2", "sgd"),
-                                           ("zero3", "sgd"), ("zero3", "sgd_plain"),
-                                           ("zero2", "sgd_plain")])
-def test_dp_modes_match_vanilla(mode, opt_kind):
+@pytest.mark.parametrize("mode,opt_kind,bucket", [("ddp", "sgd", 0), ("ddp", "sgd_plain", 0),
+                                                  ("zero2", "sgd", 0), ("zero3", "sgd", 0),
+                                                  ("zero3", "sgd_plain", 0), ("zero2", "sgd_plain", 0),
+                                                  ("zero3", "sgd", 100), ("zero2", "sgd", 100)])
+def test_dp_modes_match_vanilla(mode, opt_kind, bucket):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29650 + abs(hash((mode, opt_kind))) % 200
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, mode, opt_kind, q)) for r in range(2)]
+    port = 29650 + abs(hash((mode, opt_kind, bucket))) % 200
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, mode, opt_kind, q, bucket))
+             for r in range(2)]
     for p in procs:
         p.start()
     for p in procs:
@@ -106,6 +109,9 @@ def test_dp_modes_match_vanilla(mode, opt_kind):
     assert ok, msg
     if mode == "ddp":
         assert hist.get("all_reduce_start", 0) == 4      # one per parameter
-    if mode in ("zero2", "zero3"):
+    if mode in ("zero2", "zero3") and bucket == 0:
         assert hist.get("reduce_scatter_start", 0) == 4
         assert hist.get("all_gather_start", 0) >= 4
+    if bucket:
+        # only the 32x32 weight is sharded; the three small tensors share one all-reduce
+        assert hist.get("reduce_scatter_start", 0) == 1 and hist.get("all_reduce_start", 0) == 1
