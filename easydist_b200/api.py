@@ -60,14 +60,17 @@ def _flat_inputs(params, buffers, named_states, args, kwargs):
 
 
 def _finish(gm, params, buffers, named_states, args, kwargs, ops, native, io=None, ranks=None,
-            fuse=True):
+            fuse=True, fuse_rt=None):
     """Local metas -> (fusions) -> static symmetric buffers -> GEMM dispatch."""
     flat = _flat_inputs(params, buffers, named_states, args, kwargs)
     lowering.propagate_local_meta(gm, flat)
     info = {}
-    if native and fuse and io is not None and ranks is not None and len(ranks) > 1:
-        from .runtime import get_runtime
-        rt = get_runtime()
+    if (native or fuse_rt is not None) and fuse and io is not None and ranks is not None \
+            and len(ranks) > 1:
+        if fuse_rt is None:
+            from .runtime import get_runtime
+            fuse_rt = get_runtime()
+        rt = fuse_rt
         rehomed, nf = lowering.fuse_collective_gemms(gm, io, rt, ranks, ops)
         info["fused"] = nf
         # parameter shards read by peers must live at their symmetric offsets
@@ -92,7 +95,7 @@ def _finish(gm, params, buffers, named_states, args, kwargs, ops, native, io=Non
 
 
 def _compile_dp(func, parallel_mode, tracing_mode, args, kwargs, *, ops=_default_ops,
-                native=True, fuse=True, bucket_numel=None):
+                native=True, fuse=True, bucket_numel=None, fuse_rt=None):
     """ddp / zero2 / zero3 (reference: _compile_dp, compile_dp.py:201-381)."""
     mode = parallel_mode.replace("b200_", "")
     assert mode in DP_MODES, parallel_mode
@@ -103,11 +106,11 @@ def _compile_dp(func, parallel_mode, tracing_mode, args, kwargs, *, ops=_default
     n = len(ranks)
     shard_info = {}
     if n > 1:
+        if bucket_numel is None:
+            bucket_numel = 65536 if native else 0
         if mode == "ddp":
-            lowering.transform_ddp(gm, io, ranks, ops)
+            lowering.transform_ddp(gm, io, ranks, ops, bucket_numel=bucket_numel)
         else:
-            if bucket_numel is None:
-                bucket_numel = 65536 if native else 0
             _, shard_info = lowering.transform_fsdp(gm, io, ranks, my_index,
                                                     shard_param=(mode == "zero3"), ops=ops,
                                                     bucket_numel=bucket_numel)
@@ -128,7 +131,7 @@ def _compile_dp(func, parallel_mode, tracing_mode, args, kwargs, *, ops=_default
                                                          my_index)
             named_states = pytree.tree_unflatten(flat_states, spec)
     info = _finish(gm, params, buffers, named_states, args, kwargs, ops, native, io=io,
-                   ranks=ranks, fuse=fuse)
+                   ranks=ranks, fuse=fuse, fuse_rt=fuse_rt)
     info.update(mode=mode, dp_size=n)
     return EDCompiledFunc(gm, params, buffers, named_states, info=info)
 

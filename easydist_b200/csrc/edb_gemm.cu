@@ -30,10 +30,14 @@ constexpr int UMMA_K = 16;
 constexpr int kGemmThreads = 192;
 constexpr int kSmemABytes = BM * BK * 2;  // 16 KiB
 
-template <int BN> struct TileCfg {
-  static constexpr int kSmemBBytes = BN * BK * 2;
+// CL = 1: one CTA computes a 128 x BN tile.  CL = 2: a CTA pair computes a 256 x BN tile with
+// tcgen05.mma.cta_group::2 — each CTA stages its own 128 rows of A and HALF of the B tile, so a
+// stage is 16 KiB + BN*64 B instead of 16 KiB + BN*128 B: more stages in flight (the 1-CTA kernel
+// is bound by TMA latency x stage depth: 62% tensor-pipe at 8192^3) and 1.5x less L2->SM traffic.
+template <int BN, int CL = 1> struct TileCfg {
+  static constexpr int kSmemBBytes = (BN / CL) * BK * 2;
   static constexpr int kStageBytes = kSmemABytes + kSmemBBytes;
-  static constexpr int kStages = (BN == 256) ? 4 : 6;
+  static constexpr int kStages = (CL == 2) ? ((BN == 256) ? 6 : 8) : ((BN == 256) ? 4 : 6);
   static constexpr int kTmemCols = 2 * BN;  // two accumulator stages
   static constexpr int kEpiBufBytes = BM * 64 * 2;  // one 128 x 64 bf16 store box (128B swizzle)
   static constexpr int kEpiBufs = 2;
@@ -132,6 +136,54 @@ __device__ __forceinline__ void umma_commit_mcast(uint64_t* bar, uint16_t cta_ma
       "[%0], %1;" ::"r"(smem_u32(bar)),
       "h"(cta_mask)
       : "memory");
+}
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;  // shared::cluster address of the same offset in CTA rank 0
+__device__ __forceinline__ void tma_load_2d_2sm(const CUtensorMap* map, uint64_t* leader_bar,
+                                                void* smem, int c0, int c1) {
+  // executed by both CTAs of the pair; the transaction bytes update the LEADER's barrier
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(smem)),
+      "l"(map), "r"(smem_u32(leader_bar) & kPeerBitMask), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_f16_2cta(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
+                                              uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_2cta(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 "
+      "[%0], %1;" ::"r"(smem_u32(bar)),
+      "h"(cta_mask)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_on_leader(uint64_t* bar) {
+  asm volatile(
+      "{\n"
+      ".reg .b32 raddr;\n"
+      "mapa.shared::cluster.u32 raddr, %0, 0;\n"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [raddr];\n"
+      "}\n" ::"r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2cta(uint32_t* dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                   smem_u32(dst_smem)),
+               "r"(cols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2cta(uint32_t taddr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols)
+               : "memory");
 }
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -440,16 +492,18 @@ __device__ __forceinline__ void rs_tail_reduce(const FusedArgs& fa, uint64_t tid
 
 // ---- kernel ------------------------------------------------------------------------------------------
 
-// CL = 2: thread-block cluster of two CTAs working on vertically adjacent tiles (same n_blk).
-// Each CTA TMA-loads HALF of the shared B tile and multicasts it into both CTAs' shared memory, so
-// the L2 -> SM traffic per output tile drops from (16 + BN/8) KiB to (16 + BN/16) KiB per k-block;
-// the plain kernel is L2-bandwidth bound at K ~ 1024 (measured 670 TF/s at 4096x4096x1024).
+// CL = 2: thread-block cluster of two CTAs = one 256 x BN tile computed with cta_group::2 UMMA.
+// Both CTAs run the TMA producer (own 128 rows of A + own half of B, transaction bytes counted on
+// the leader's `full` barrier) and the epilogue (own 128 accumulator rows in own TMEM); only the
+// leader (cluster rank 0) issues the MMAs and multicasts `commit` to both CTAs' barriers.
+// (A multicast-only variant of this cluster shape was measured first: +4%, TMA multicast does not
+// save L2 reads at cluster size 2 — profiles/r01_gemm_vs_cublas_v3_cluster_multicast.log.)
 template <int BN, bool A_KMAJOR, bool B_KMAJOR, int MODE, int CL>
 __global__ void __launch_bounds__(kGemmThreads, 1)
     k_gemm_bf16(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                 const __grid_constant__ CUtensorMap tmap_c, const GemmParams p,
                 const __grid_constant__ FusedArgs fa, const __grid_constant__ CMaps cm) {
-  using Cfg = TileCfg<BN>;
+  using Cfg = TileCfg<BN, CL>;
   constexpr int kStages = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
@@ -503,16 +557,17 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
     if (lane == 0) {
       for (int s = 0; s < kStages; ++s) {
         mbar_init(&full_bar[s], 1);
-        mbar_init(&empty_bar[s], CL);  // CL == 2: both CTAs' MMA warps release the slot
+        mbar_init(&empty_bar[s], 1);
       }
       for (int s = 0; s < 2; ++s) {
         mbar_init(&tmem_full[s], 1);
-        mbar_init(&tmem_empty[s], 4);  // one arrive per epilogue warp
+        mbar_init(&tmem_empty[s], 4 * CL);  // one arrive per epilogue warp (of both CTAs if CL == 2)
       }
       fence_barrier_init();
     }
     __syncwarp();
-    tmem_alloc(tmem_slot, Cfg::kTmemCols);
+    if (CL == 2) tmem_alloc_2cta(tmem_slot, Cfg::kTmemCols);
+    else tmem_alloc(tmem_slot, Cfg::kTmemCols);
   }
   tcgen05_fence_before();
   __syncthreads();
@@ -549,9 +604,35 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
         }
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
           uint8_t* sa = smem_a + stage * kSmemABytes;
           uint8_t* sb = smem_b + stage * Cfg::kSmemBBytes;
+          if (CL == 2) {
+            // both CTAs' loads complete on the leader's barrier, which expects both stages' bytes
+            if (crank == 0) mbar_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
+            if (A_KMAJOR) {
+              tma_load_2d_2sm(&tmap_a, &full_bar[stage], sa, kb * BK, m_blk * BM);
+            } else {
+#pragma unroll
+              for (int h = 0; h < BM / 64; ++h)
+                tma_load_2d_2sm(&tmap_a, &full_bar[stage], sa + h * (64 * BK * 2),
+                                m_blk * BM + h * 64, kb * BK);
+            }
+            const int b_half = b_row + crank * (BN / 2);
+            if (B_KMAJOR) {
+              tma_load_2d_2sm(bmap, &full_bar[stage], sb, kb * BK, b_half);
+            } else {
+#pragma unroll
+              for (int h = 0; h < BN / 128; ++h)
+                tma_load_2d_2sm(bmap, &full_bar[stage], sb + h * (64 * BK * 2), b_half + h * 64,
+                                kb * BK);
+            }
+            if (++stage == kStages) {
+              stage = 0;
+              phase ^= 1;
+            }
+            continue;
+          }
+          mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
           if (A_KMAJOR) {
             tma_load_2d(&tmap_a, &full_bar[stage], sa, kb * BK, m_blk * BM);
           } else {
@@ -561,20 +642,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
               tma_load_2d(&tmap_a, &full_bar[stage], sa + h * (64 * BK * 2), m_blk * BM + h * 64,
                           kb * BK);
           }
-          if (CL == 2) {
-            // my half of the B tile, delivered to both CTAs of the cluster
-            if (B_KMAJOR) {
-              tma_load_2d_mcast(bmap, &full_bar[stage], sb + crank * (BN / 2) * 128, kb * BK,
-                                b_row + crank * (BN / 2), (uint16_t)3);
-            } else {
-#pragma unroll
-              for (int h = 0; h < BN / 128; ++h) {
-                const int hh = crank * (BN / 128) + h;
-                tma_load_2d_mcast(bmap, &full_bar[stage], sb + hh * (64 * BK * 2), b_row + hh * 64,
-                                  kb * BK, (uint16_t)3);
-              }
-            }
-          } else if (B_KMAJOR) {
+          if (B_KMAJOR) {
             tma_load_2d(bmap, &full_bar[stage], sb, kb * BK, b_row);
           } else {
 #pragma unroll
@@ -588,9 +656,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
         }
       }
     }
-  } else if (warp == 1) {
-    // ===== MMA issuer =====
-    constexpr uint32_t idesc = make_idesc(BM, BN, !A_KMAJOR, !B_KMAJOR);
+  } else if (warp == 1 && (CL == 1 || crank == 0)) {
+    // ===== MMA issuer (leader CTA only when CL == 2) =====
+    constexpr uint32_t idesc = make_idesc(BM * CL, BN, !A_KMAJOR, !B_KMAJOR);
     int stage = 0;
     uint32_t phase = 0;
     int as = 0;
@@ -612,12 +680,17 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
             else da = make_smem_desc(a_addr + k * UMMA_K * 128, 64 * BK * 2, 1024);
             if (B_KMAJOR) db = make_smem_desc(b_addr + k * UMMA_K * 2, 0, 1024);
             else db = make_smem_desc(b_addr + k * UMMA_K * 128, 64 * BK * 2, 1024);
-            umma_f16(tmem_d, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            if (CL == 2) umma_f16_2cta(tmem_d, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            else umma_f16(tmem_d, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
           }
-          // free the smem stage when these MMAs retire (in both CTAs when B is multicast)
-          if (CL == 2) umma_commit_mcast(&empty_bar[stage], (uint16_t)3);
-          else umma_commit(&empty_bar[stage]);
-          if (kb == k_blocks - 1) umma_commit(&tmem_full[as]);
+          // free the smem stage when these MMAs retire (in both CTAs of a pair)
+          if (CL == 2) {
+            umma_commit_2cta(&empty_bar[stage], (uint16_t)3);
+            if (kb == k_blocks - 1) umma_commit_2cta(&tmem_full[as], (uint16_t)3);
+          } else {
+            umma_commit(&empty_bar[stage]);
+            if (kb == k_blocks - 1) umma_commit(&tmem_full[as]);
+          }
         }
         __syncwarp();
         if (++stage == kStages) {
@@ -630,7 +703,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
         aphase ^= 1;
       }
     }
-  } else {
+  } else if (warp >= 2) {
     // ===== epilogue warps 2..5: TMEM -> registers -> bf16 -> swizzled smem -> TMA store =====
     const int quad = warp & 3;            // TMEM lane quadrant this warp may access
     const int row_in_tile = quad * 32 + lane;
@@ -666,7 +739,10 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
           // all of this warp's accumulator columns are in registers: hand the TMEM stage back
           tcgen05_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&tmem_empty[as]);
+          if (lane == 0) {
+            if (CL == 2) mbar_arrive_on_leader(&tmem_empty[as]);
+            else mbar_arrive(&tmem_empty[as]);
+          }
         }
         // the staging buffer we are about to overwrite must have been read by its TMA store
         if (issuer) tma_store_wait_read<Cfg::kEpiBufs - 1>();
@@ -738,7 +814,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
   if (CL == 2) cluster_sync_all();  // nobody leaves while the peer may still signal its barriers
   if (warp == 1) {
     tcgen05_fence_after();
-    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+    if (CL == 2) tmem_dealloc_2cta(tmem_base, Cfg::kTmemCols);
+    else tmem_dealloc(tmem_base, Cfg::kTmemCols);
   }
 
   if (MODE == MODE_RS) {
@@ -795,7 +872,7 @@ template <int BN, bool AK, bool BK_, int MODE, int CL>
 static int launch_gemm_cl(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc,
                           const GemmParams& p, const FusedArgs& fa, const CMaps& cm, int grid,
                           cudaStream_t st) {
-  using Cfg = TileCfg<BN>;
+  using Cfg = TileCfg<BN, CL>;
   static bool configured = false;
   auto kern = k_gemm_bf16<BN, AK, BK_, MODE, CL>;
   if (!configured) {

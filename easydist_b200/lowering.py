@@ -258,13 +258,22 @@ def optimizer_region(gm, io):
     return [n for n in gm.graph.nodes if n in region]
 
 
-def transform_ddp(gm, io, ranks, ops=_default_ops):
+def transform_ddp(gm, io, ranks, ops=_default_ops, bucket_numel=0):
     """ddp: all-reduce(avg) every final gradient before the optimizer consumes it
-    (compile_dp.py:55-79 does this for the gradient list of `_fused_adam`)."""
+    (compile_dp.py:55-79 does this for the gradient list of `_fused_adam`).  Gradients of
+    parameters below `bucket_numel` elements share one bucketed all-reduce."""
     ranks = list(ranks)
     if len(ranks) <= 1:
         return gm
-    for g in dict.fromkeys(x for x in io.final_grads if isinstance(x, Node)):
+    small = {ph for ph in io.param_ph if ph.meta["val"].numel() < bucket_numel}
+    if small:
+        region = optimizer_region(gm, io)
+        if region:
+            _bucket_small_grads(gm, io, ranks, small, region, ops)
+        else:
+            small = set()
+    big = [g for ph, g in zip(io.param_ph, io.final_grads) if isinstance(g, Node) and ph not in small]
+    for g in dict.fromkeys(big):
         with gm.graph.inserting_after(g):
             s = gm.graph.call_function(ops.all_reduce_start, args=(g, "avg", ranks))
         with gm.graph.inserting_after(s):
@@ -543,13 +552,15 @@ def fuse_collective_gemms(gm, io, rt, ranks, ops=_default_ops):
         g = f.args[0]
         if not (isinstance(g, Node) and len(g.users) == 1):
             continue
-        # the weight gradient of a Linear is traced as t(mm(x^T, dy)): (A.B)^T = B^T.A^T
-        transposed = None
+        # the weight gradient of a Linear reaches the optimizer through a chain of aten.t nodes
+        # (t(t(mm(dy^T, x))) in torch 2.11); an odd chain means (A.B)^T = B^T.A^T
+        t_chain = []
         mm_node = g
-        if g.target == aten.t.default and isinstance(g.args[0], Node) and \
-                g.args[0].target == aten.mm.default and len(g.args[0].users) == 1:
-            transposed = g
-            mm_node = g.args[0]
+        while mm_node.target == aten.t.default and isinstance(mm_node.args[0], Node) and \
+                len(mm_node.args[0].users) == 1:
+            t_chain.append(mm_node)
+            mm_node = mm_node.args[0]
+        transposed = t_chain[0] if len(t_chain) % 2 == 1 else None
         if mm_node.target != aten.mm.default:
             continue
         a0, b0 = mm_node.args
@@ -574,9 +585,8 @@ def fuse_collective_gemms(gm, io, rt, ranks, ops=_default_ops):
             fused = graph.call_function(ops.mm_rs, args=(a, b, list(ranks)),
                                         kwargs={"_buf": (recv.offset,), "_scale": 1.0 / n})
         rs_e.replace_all_uses_with(fused)
-        for dead in (rs_e, rs_s, f, transposed, mm_node):
-            if dead is not None:
-                graph.erase_node(dead)
+        for dead in [rs_e, rs_s, f] + t_chain + [mm_node]:
+            graph.erase_node(dead)
         n_rs += 1
 
     # peers read parameter shards in place: keep the optimizer from overwriting them too early

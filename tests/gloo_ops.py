@@ -113,6 +113,55 @@ def all_to_all_end(tensor, gather_dim, scatter_dim, num_chunks, indice, ranks, t
     return tensor
 
 
+# fused ops (semantics of easydist_b200.reshard.ag_mm / mm_rs / symm_guard) for CPU tests of the
+# fusion rewrite
+
+
+def symm_guard(x, group):
+    return x
+
+
+def ag_mm(x, w_shard, group, n_out, k_in, bias=None, *, _buf=None):
+    if _fake(x):
+        return x.new_empty((x.shape[0], n_out)), w_shard.new_empty((n_out, k_in))
+    w = all_gather_start(w_shard.reshape(-1), 0, group).view(n_out, k_in)
+    out = x @ w.t()
+    if bias is not None:
+        out = out + bias
+    return out, w
+
+
+def mm_rs(a, b, group, *, _buf=None, _scale=1.0, _out_dtype=None):
+    n = len(group)
+    if _fake(a):
+        return a.new_empty((a.shape[0] // n * b.shape[1],), dtype=_out_dtype or a.dtype)
+    part = (a @ b).flatten()
+    red = all_reduce_start(part, "sum", group)
+    me = list(group).index(dist.get_rank())
+    out = torch.chunk(red, n, 0)[me].contiguous() * _scale
+    return out.to(_out_dtype or a.dtype)
+
+
+class FakeSymmRuntime:
+    """Stands in for easydist_b200.runtime.Runtime in the fusion pass (offsets only)."""
+
+    class _Buf:
+        def __init__(self, offset, nbytes):
+            self.offset, self.nbytes = offset, nbytes
+
+        def tensor(self, dtype, shape):
+            return torch.empty(shape, dtype=dtype)
+
+    def __init__(self):
+        self._off = 1 << 20
+
+    def alloc(self, nbytes, align=256):
+        off = (self._off + align - 1) // align * align
+        self._off = off + nbytes
+        return FakeSymmRuntime._Buf(off, nbytes)
+
+
+FUSED_FUNCS = [ag_mm, mm_rs, symm_guard]
 COMM_FUNCS = [all_reduce_start, all_gather_start, reduce_scatter_start, all_to_all_start]
 COMM_SYNC_FUNCS = [all_reduce_end, all_gather_end, reduce_scatter_end, all_to_all_end]
 CUSTOM_FUNCS = COMM_FUNCS + COMM_SYNC_FUNCS + [scatter_wrapper, copy_wrapper]

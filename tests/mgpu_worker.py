@@ -229,21 +229,8 @@ def run_fused(rank, world, group):
 def bench_fused(rank, world, group):
     from easydist_b200 import gemm
     rt = runtime.get_runtime()
-
-    def timeit(f, iters=20):
-        for _ in range(3):
-            f()
-        dist.barrier()
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(iters):
-            f()
-        e1.record()
-        torch.cuda.synchronize()
-        t = torch.tensor([e0.elapsed_time(e1) / iters], device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return t.item() * 1e3
+    _t = _graph_timer(world)
+    timeit = lambda f: _t(f) * 1e3
 
     for (M, N, K) in [(4096, 1024, 1024), (4096, 4096, 1024), (4096, 1024, 4096), (4096, 3072, 1024)]:
         rows = N // world
@@ -276,54 +263,82 @@ def bench_fused(rank, world, group):
                   flush=True)
 
 
+def _graph_timer(world):
+    """Time `f` as the average of 10 captured calls per CUDA-graph replay (no Python / launch
+    overhead in the measurement), max over ranks."""
+
+    def timeit(f, reps=5):
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(3):
+                f()
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        dist.barrier()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            for _ in range(10):
+                f()
+        g.replay()
+        torch.cuda.synchronize()
+        dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            g.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1) / (reps * 10)], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item()  # ms per op
+    return timeit
+
+
 def bench(rank, world, group):
+    """Reshard microbench (BASELINE.json config 5): bus bandwidth (nccl-tests convention) of the
+    libedb kernels vs NCCL on the same GPUs, bf16, CUDA-graph replay timing."""
     rt = runtime.get_runtime()
+    timeit = _graph_timer(world)
     res = []
     sizes = [1 << k for k in range(10, 31, 2)]
     for nbytes in sizes:
-        if nbytes * 2 > rt.heap_bytes // 8:
+        if nbytes * 4 > rt.heap_bytes // 2:
             break
+        mark = rt.mark()
         numel = nbytes // 2
-        shard = torch.randn(numel // world, device="cuda").bfloat16() if numel >= world else None
+        shard = torch.randn(max(1, numel // world), device="cuda").bfloat16()
         full = torch.randn(numel, device="cuda").bfloat16()
         b1, b2, b3 = rt.alloc(nbytes), rt.alloc(nbytes), rt.alloc(nbytes)
-        nccl_out = torch.empty(numel, device="cuda", dtype=torch.bfloat16)
+        nccl_out = torch.empty(shard.numel() * world, device="cuda", dtype=torch.bfloat16)
         nccl_rs = torch.empty(numel // world, device="cuda", dtype=torch.bfloat16)
-
-        def timeit(f, iters=20):
-            for _ in range(3):
-                f()
-            dist.barrier()
-            torch.cuda.synchronize()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            for _ in range(iters):
-                f()
-            e1.record()
-            torch.cuda.synchronize()
-            t = torch.tensor([e0.elapsed_time(e1) / iters], device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            return t.item()
-
+        a2a_in = full.view(world, -1)
+        a2a_out = torch.empty_like(a2a_in)
         row = {"bytes": nbytes}
         f = (world - 1) / world
         t = timeit(lambda: reshard.all_gather_start(shard, 0, group, _buf=(b1.offset, nbytes)))
-        row["ag_edb_GBs"] = nbytes * f / t / 1e6
+        row["ag_edb_GBs"], row["ag_edb_us"] = nbytes * f / t / 1e6, t * 1e3
         t = timeit(lambda: dist.all_gather_into_tensor(nccl_out, shard))
-        row["ag_nccl_GBs"] = nbytes * f / t / 1e6
+        row["ag_nccl_GBs"], row["ag_nccl_us"] = nbytes * f / t / 1e6, t * 1e3
         t = timeit(lambda: reshard.reduce_scatter_start(full, "sum", 0, group,
                                                         _buf=(b2.offset, nbytes)))
-        row["rs_edb_GBs"] = nbytes * f / t / 1e6
+        row["rs_edb_GBs"], row["rs_edb_us"] = nbytes * f / t / 1e6, t * 1e3
         t = timeit(lambda: dist.reduce_scatter_tensor(nccl_rs, full))
-        row["rs_nccl_GBs"] = nbytes * f / t / 1e6
+        row["rs_nccl_GBs"], row["rs_nccl_us"] = nbytes * f / t / 1e6, t * 1e3
         t = timeit(lambda: reshard.all_reduce_start(full, "sum", group,
                                                     _buf=(b2.offset, nbytes, b3.offset)))
-        row["ar_edb_GBs"] = 2 * nbytes * f / t / 1e6
-        row["ar_edb_us"] = t * 1e3
+        row["ar_edb_GBs"], row["ar_edb_us"] = 2 * nbytes * f / t / 1e6, t * 1e3
         t = timeit(lambda: dist.all_reduce(full))
-        row["ar_nccl_GBs"] = 2 * nbytes * f / t / 1e6
-        row["ar_nccl_us"] = t * 1e3
+        row["ar_nccl_GBs"], row["ar_nccl_us"] = 2 * nbytes * f / t / 1e6, t * 1e3
+        if numel % (world * world) == 0 and numel >= world * world:
+            x2 = full.view(world, -1)  # S(0) local [world, c] -> S(1): true all-to-all
+            t = timeit(lambda: reshard.all_to_all_start(x2, 0, 1, world, rank, group,
+                                                        _buf=(b1.offset, nbytes)))
+            row["a2a_edb_GBs"], row["a2a_edb_us"] = nbytes * f / t / 1e6, t * 1e3
+            t = timeit(lambda: dist.all_to_all_single(a2a_out, a2a_in))
+            row["a2a_nccl_GBs"], row["a2a_nccl_us"] = nbytes * f / t / 1e6, t * 1e3
         res.append(row)
+        rt.reset(mark)
         if rank == 0:
             print("BENCH " + " ".join(f"{k}={v:.1f}" if isinstance(v, float) else f"{k}={v}"
                                       for k, v in row.items()), flush=True)
