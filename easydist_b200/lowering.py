@@ -103,10 +103,20 @@ def override_args(node, invars_strategy, mesh):
 
 
 def insert_comm_node(gm, node, var_, src_specs, tgt_specs, mesh, ops, planner="GREEDY",
-                     copy_innode=None):
+                     copy_innode=None, global_shape_of=None):
     """Emit the reshard steps turning `var_` (placement src_specs) into tgt_specs in front of
     `node` (sharding.py:704-809).  One step = one op on the flat rank group of one mesh dim."""
-    steps = planners.PLANNERS[planner](src_specs, tgt_specs)
+    p2p_left = None
+    if global_shape_of is None and isinstance(var_.meta.get("val"), torch.Tensor):
+        global_shape_of = var_.meta["val"].shape  # metas are still global while the pass runs
+    if planner == "P2P":
+        # single-collective steps first, the rest as one box exchange over the whole mesh
+        # (sharding.py:721-723, 795-802)
+        steps, reached = planners.plan_immediate(src_specs, tgt_specs)
+        if reached != tgt_specs:
+            p2p_left = reached
+    else:
+        steps = planners.PLANNERS[planner](src_specs, tgt_specs)
     coord = mesh.get_coordinate()
     graph = gm.graph
     for mdim, cur, tgt in steps:
@@ -136,6 +146,24 @@ def insert_comm_node(gm, node, var_, src_specs, tgt_specs, mesh, ops, planner="G
                 new = graph.call_function(ops.all_reduce_end, args=(s, *a))
             else:  # pragma: no cover
                 raise AssertionError(kind)
+        node.replace_input_with(var_, new)
+        var_ = new
+    if p2p_left is not None:
+        global_shape = [int(d) for d in global_shape_of]
+        srcs = planners.partitions_from_spec(p2p_left, global_shape, mesh)
+        tgts = planners.partitions_from_spec(tgt_specs, global_shape, mesh)
+        ranks = [p.rank for p in srcs]
+        me = ranks.index(mesh.get_rank())
+        boxes = []
+        for it in planners.recv_boxes(srcs, tgts[me]):
+            sp = srcs[ranks.index(it.rank)]
+            boxes.append((ranks.index(it.rank),
+                          [a - b for a, b in zip(it.start, sp.start)],
+                          [a - b for a, b in zip(it.start, tgts[me].start)],
+                          list(it.shape())))
+        with graph.inserting_before(node):
+            new = graph.call_function(ops.box_exchange, args=(
+                var_, list(tgts[me].shape()), boxes, [list(p.shape()) for p in srcs], ranks))
         node.replace_input_with(var_, new)
         var_ = new
     if copy_innode is not None:

@@ -125,3 +125,70 @@ def step_kind(cur, tgt):
         if cur.is_partial():
             return "all_reduce"
     return None
+
+
+# ---- Partition / P2P box planner (sharding.py:336-474) ------------------------------------------------
+
+
+class Partition:
+    """An N-D box [start, end) of the global tensor held by `rank`, plus the coordinates of the
+    partial (unreduced) mesh dims it belongs to (sharding.py:336-374)."""
+
+    __slots__ = ("start", "end", "rank", "partial")
+
+    def __init__(self, start, end, rank, partial=()):
+        self.start, self.end, self.rank, self.partial = tuple(start), tuple(end), int(rank), tuple(partial)
+
+    def shard(self, tensor_dim, shard_num, shard_idx):
+        s, e = self.start[tensor_dim], self.end[tensor_dim]
+        block = (e - s + shard_num - 1) // shard_num
+        ns, ne = min(s + block * shard_idx, e), min(s + block * (shard_idx + 1), e)
+        return Partition(self.start[:tensor_dim] + (ns,) + self.start[tensor_dim + 1:],
+                         self.end[:tensor_dim] + (ne,) + self.end[tensor_dim + 1:], self.rank,
+                         self.partial)
+
+    def intersect(self, src):
+        """Part of `self` that `src` can provide (None if empty or partial coords differ)."""
+        s = tuple(max(a, b) for a, b in zip(self.start, src.start))
+        e = tuple(min(a, b) for a, b in zip(self.end, src.end))
+        if any(a >= b for a, b in zip(s, e)) or src.partial != self.partial:
+            return None
+        return Partition(s, e, src.rank, src.partial)
+
+    def shape(self):
+        return tuple(e - s for s, e in zip(self.start, self.end))
+
+    def __repr__(self):
+        return f"{{{self.start}->{self.end} partial {self.partial} on rank{self.rank}}}"
+
+
+def partitions_from_spec(placements, global_shape, mesh):
+    """Partition of every rank of `mesh` (easydist_b200.device_mesh.DeviceMesh) under `placements`
+    (sharding.py:376-398 Partition.from_tensor_spec); returned in mesh order (row-major)."""
+    import numpy as np
+    parts = []
+    for idx in np.ndindex(*mesh.mesh.shape):
+        p = Partition((0,) * len(global_shape), tuple(int(v) for v in global_shape),
+                      int(mesh.mesh[idx]))
+        for mdim, pl in enumerate(placements):
+            if pl.is_shard():
+                p = p.shard(pl.dim, mesh.mesh.shape[mdim], idx[mdim])
+            elif pl.is_partial():
+                p = Partition(p.start, p.end, p.rank, p.partial + (idx[mdim],))
+        parts.append(p)
+    return parts
+
+
+def recv_boxes(src_parts, tgt_part):
+    """Boxes `tgt_part`'s rank must fetch: intersections with the sources ordered by rank distance
+    (stable), first provider of each distinct box wins (sharding.py:410-425 gen_recv_meta)."""
+    out, seen = [], set()
+    for src in sorted(src_parts, key=lambda x: abs(x.rank - tgt_part.rank)):
+        inter = tgt_part.intersect(src)
+        if inter is None:
+            continue
+        key = (inter.start, inter.end)
+        if key not in seen:
+            seen.add(key)
+            out.append(inter)
+    return out

@@ -142,6 +142,28 @@ def mm_rs(a, b, group, *, _buf=None, _scale=1.0, _out_dtype=None):
     return out.to(_out_dtype or a.dtype)
 
 
+def box_exchange(tensor, dst_shape, boxes, peer_src_shapes, group, *, _buf=None):
+    """Partition P2P redistribution over gloo: every member publishes its source partition, each
+    rank copies the boxes it needs (semantics of reshard.box_exchange / sharding.py:427-474)."""
+    if _fake(tensor):
+        return tensor.new_empty([int(s) for s in dst_shape])
+    n = len(group)
+    parts = [torch.empty([int(v) for v in shp], dtype=tensor.dtype) for shp in peer_src_shapes]
+    # partitions differ in shape: exchange them one broadcast per member
+    me = list(group).index(dist.get_rank())
+    for i, r in enumerate(group):
+        buf = tensor.contiguous().clone() if i == me else parts[i]
+        if buf.numel():
+            dist.broadcast(buf, src=r, group=_pg(group))
+        parts[i] = buf
+    out = tensor.new_empty([int(s) for s in dst_shape])
+    for (p_idx, s_start, d_start, ext) in boxes:
+        ssl = tuple(slice(a, a + e) for a, e in zip(s_start, ext))
+        dsl = tuple(slice(a, a + e) for a, e in zip(d_start, ext))
+        out[dsl] = parts[p_idx][ssl]
+    return out
+
+
 class FakeSymmRuntime:
     """Stands in for easydist_b200.runtime.Runtime in the fusion pass (offsets only)."""
 

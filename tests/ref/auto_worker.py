@@ -44,6 +44,7 @@ def main():
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     mesh_shape = tuple(int(v) for v in os.environ.get("EDB_TEST_MESH", str(world)).split("x"))
     record = os.environ.get("EDB_RECORD", "")
+    planner = os.environ.get("EDB_PLANNER", "GREEDY")
     torch.set_num_threads(1)
     dist.init_process_group("gloo")
     from oracle import refcompat
@@ -54,6 +55,8 @@ def main():
     import easydist.torch.compile_auto as ref_auto
     from torch.distributed.device_mesh import DeviceMesh
     easydist_setup(backend="torch", device="cpu", allow_tf32=False)
+    import easydist.config as mdconfig
+    mdconfig.experimental_sharding_transform = planner  # config.py:115-117
     names = [f"spmd{i}" for i in range(len(mesh_shape))]
     tmesh = DeviceMesh("cpu", torch.arange(world).reshape(mesh_shape), mesh_dim_names=names)
     set_device_mesh(tmesh)
@@ -80,7 +83,7 @@ def main():
                 if record and rank == 0:
                     saved["plan"] = metair.plan_to_json(metair.plan_from_reference(opt_strategy))
                 return lowering.sharding_transform(fx_module, opt_strategy, state_io_map,
-                                                   ops=gloo_ops, mesh=my_mesh)
+                                                   ops=gloo_ops, mesh=my_mesh, planner=planner)
             ref_auto.sharding_transform = mine
         try:
             step = easydist_compile(train_step, "auto", "fake", cuda_graph=False)
@@ -93,7 +96,10 @@ def main():
         for n in cf.graph.graph.nodes:
             if n.op == "call_function":
                 nm = getattr(n.target, "__name__", str(n.target))
-                if any(k in nm for k in ("all_", "reduce_scatter", "scatter_wrapper", "copy_wrapper")):
+                if "inner" in nm:
+                    nm = "box_exchange"  # the reference's do_p2p_comm_wrapper closure
+                if any(k in nm for k in ("all_", "reduce_scatter", "scatter_wrapper", "copy_wrapper",
+                                         "box_exchange")):
                     hist[nm] = hist.get(nm, 0) + 1
         return outs, cf, hist, saved
 

@@ -67,3 +67,23 @@ def test_device_mesh_groups():
     assert sub.shape == (2, 2) and sub.get_coordinate() == [0, 1]
     one = DeviceMesh([0], ["spmd0"], rank=0)   # world size 1 is allowed here
     assert one.size(0) == 1 and one.ranks_along(0) == [0]
+
+
+def test_product_partition_matches_reference_fixture():
+    """easydist_b200.planners.Partition / recv_boxes == Partition.from_tensor_spec / gen_recv_meta
+    of the reference (fixture generated from it)."""
+    with gzip.open(os.path.join(GOLDEN, "partition.json.gz"), "rt") as f:
+        cases = json.load(f)
+    enc = lambda p: [list(p.start), list(p.end), p.rank, list(p.partial)]
+    for c in cases[::7]:
+        mesh = DeviceMesh(np.arange(int(np.prod(c["mesh"]))).reshape(c["mesh"]),
+                          [f"spmd{i}" for i in range(len(c["mesh"]))], rank=0)
+        src = M.VarSPMDStrategy(*[_mk(t) for t in c["src"]])
+        dst = M.VarSPMDStrategy(*[_mk(t) for t in c["dst"]])
+        sp = planners.partitions_from_spec(src, c["gshape"], mesh)
+        tp = planners.partitions_from_spec(dst, c["gshape"], mesh)
+        assert [enc(p) for p in sp] == c["src_parts"]
+        assert [enc(p) for p in tp] == c["dst_parts"]
+        for t in tp:
+            got = [enc(p) for p in planners.recv_boxes(sp, t)]
+            assert got == c["recv"].get(str(t.rank), []), (c["mesh"], c["src"], c["dst"], t.rank)
