@@ -301,6 +301,8 @@ struct FusedArgs {
   const char* shard_src[kMaxGroup];  // member p's shard (peer mapped); [me] is local
   char* full_dst;                    // local gathered buffer
   int64_t shard_bytes;
+  int ag_rows;        // rows of B per shard (N / n)
+  int ag_first_tile;  // n-tile containing the first row of my shard
   // MODE_RS
   char* recv_base;      // my receive buffer: n slots of chunk_bytes
   int64_t chunk_bytes;  // (M/n) * N * 2
@@ -318,12 +320,12 @@ template <int MODE>
 __device__ __forceinline__ void tile_coords(int t, const GemmParams& p, const FusedArgs& fa,
                                             int& m_blk, int& n_blk, int& chunk) {
   if (MODE == MODE_AG) {
-    const int ntc = p.n_tiles / fa.f.n;  // n-tiles per chunk
-    const int tpc = p.m_tiles * ntc;
-    const int ci = t / tpc, w = t - ci * tpc;
-    chunk = (fa.f.me + ci) % fa.f.n;  // own shard first: it needs no transfer
-    n_blk = chunk * ntc + w / p.m_tiles;
-    m_blk = w % p.m_tiles;
+    // n-tiles in rotated order starting at the tile that holds my own shard (needs no transfer),
+    // then in the order the comm CTAs pull the peers' shards
+    const int ni = t / p.m_tiles;
+    n_blk = (fa.ag_first_tile + ni) % p.n_tiles;
+    m_blk = t - ni * p.m_tiles;
+    chunk = -1;  // a tile may span several shards: see the producer
   } else if (MODE == MODE_RS) {
     const int mtc = p.m_tiles / fa.f.n;  // m-tiles per chunk
     const int tpc = mtc * p.n_tiles;
@@ -593,13 +595,14 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
         const CUtensorMap* bmap = &tmap_b;
         int b_row = n_blk * BN;
         if (MODE == MODE_AG) {
-          if (chunk == fa.f.me) {
-            bmap = &cm.m[0];  // my own shard: no transfer needed
-            b_row = (n_blk - chunk * (p.n_tiles / fa.f.n)) * BN;
-          } else if (chunk != ready_chunk) {
-            spin_wait_gpu(fa.f.local + F_CHUNK + chunk, q);
+          const int c_lo = (n_blk * BN) / fa.ag_rows, c_hi = (n_blk * BN + BN - 1) / fa.ag_rows;
+          if (c_lo == fa.f.me && c_hi == fa.f.me) {
+            bmap = &cm.m[0];  // entirely inside my own shard: no transfer needed
+            b_row = n_blk * BN - fa.f.me * fa.ag_rows;
+          } else if (n_blk != ready_chunk) {
+            for (int c = c_lo; c <= c_hi; ++c) spin_wait_gpu(fa.f.local + F_CHUNK + c, q);
             fence_proxy_async_all();
-            ready_chunk = chunk;
+            ready_chunk = n_blk;
           }
         }
         for (int kb = 0; kb < k_blocks; ++kb) {
@@ -928,15 +931,12 @@ static int dispatch_gemm(int bn, bool a_k, bool b_k, const CUtensorMap& ta, cons
 }
 
 static int pick_bn(int64_t M, int64_t N, int sms) {
-  // fewer, larger tiles unless that leaves SMs idle: compare wave efficiency of BN=256 vs 128
-  auto eff = [&](int bn) {
-    const int64_t tiles = ((M + BM - 1) / BM) * ((N + bn - 1) / bn);
-    const int64_t waves = (tiles + sms - 1) / sms;
-    return (double)tiles / (double)(waves * sms);
-  };
-  if (N <= 128) return 128;
-  const double e256 = eff(256), e128 = eff(128);
-  return (e256 + 0.05 >= e128) ? 256 : 128;
+  // 128-wide tiles need 128 B/cycle of operand traffic per SM (A 16 KiB + B 16 KiB per 256 MMA
+  // cycles) and run at ~half the rate of 256-wide ones (96 B/cycle) even when they quantise better
+  // into waves (measured: profiles/r01_gemm_tile_cluster_sweep.log), so 256 unless N is tiny.
+  (void)M;
+  (void)sms;
+  return N <= 128 ? 128 : 256;
 }
 
 static int check_operands(const void* A, const void* B, const void* C, const void* bias, int64_t M,
@@ -980,8 +980,9 @@ int edb_gemm_bf16(void* C, const void* A, const void* B, const void* bias, int64
   int rc = check_operands(A, B, C, bias, M, N, K, lda, ldb, ldc, "edb_gemm_bf16");
   if (rc) return rc;
   const int sms = sm_count_now();
-  const int bn = pick_bn(M, N, sms);
-  // two-CTA clusters with multicast B whenever there are at least two tile rows
+  int bn = pick_bn(M, N, sms);
+  if (rt().gemm_force_bn == 128 || rt().gemm_force_bn == 256) bn = (int)rt().gemm_force_bn;
+  // CTA pairs (cta_group::2) whenever there are at least two tile rows
   const int cl = (rt().gemm_cluster >= 2 && M > BM) ? 2 : 1;
   CUtensorMap ta, tb, tc;
   if (a_kmajor) rc = make_tmap(&ta, A, K, M, lda, BK, BM);
@@ -1031,10 +1032,13 @@ int edb_ag_gemm_bf16(int gid, void* C, const void* A, const void* bias, uint64_t
   if (N % n) return set_error(EDB_E_UNSUPPORTED, "edb_ag_gemm_bf16: N %% group size != 0");
   const int64_t rows = N / n;
   int bn = 0;
-  if (rows % 256 == 0) bn = 256;
-  else if (rows % 128 == 0) bn = 128;
-  else return set_error(EDB_E_UNSUPPORTED, "edb_ag_gemm_bf16: shard rows %lld not a multiple of 128",
-                        (long long)rows);
+  if (N % 256 == 0) bn = 256;
+  else if (N % 128 == 0) bn = 128;
+  else return set_error(EDB_E_UNSUPPORTED, "edb_ag_gemm_bf16: N=%lld not a multiple of 128",
+                        (long long)N);
+  if (rows % 8)
+    return set_error(EDB_E_UNSUPPORTED, "edb_ag_gemm_bf16: shard rows %lld not a multiple of 8",
+                     (long long)rows);
   if (K & 7) return set_error(EDB_E_UNSUPPORTED, "edb_ag_gemm_bf16: K must be a multiple of 8");
   const size_t shard_bytes = (size_t)rows * K * 2;
   if (b_shard_off < kUserOffset || b_shard_off + shard_bytes > r.heap_bytes || (b_shard_off & 15) ||
@@ -1074,6 +1078,8 @@ int edb_ag_gemm_bf16(int gid, void* C, const void* A, const void* bias, uint64_t
   fa.shard_src[me] = shard;
   fa.full_dst = full;
   fa.shard_bytes = (int64_t)shard_bytes;
+  fa.ag_rows = (int)rows;
+  fa.ag_first_tile = (int)(((int64_t)me * rows) / bn);
   const int tiles = p.m_tiles * p.n_tiles;
   int gemm_ctas = sms - n_comm;
   if (gemm_ctas > tiles) gemm_ctas = tiles;

@@ -56,6 +56,7 @@ struct Runtime {
   int64_t copy_ctas_per_sm = 4;
   int64_t comm_ctas = 16;
   int64_t spin_timeout_ms = 10000;
+  int64_t gemm_force_bn = 0;  // tuning aid: 128 / 256 overrides the tile-width heuristic
   int64_t gemm_cluster = 2;  // 2: pair CTAs in clusters and multicast the B tile; 1: off
 };
 

@@ -208,6 +208,7 @@ int edb_set_option(const char* name, int64_t value) {
   else if (!strcmp(name, "comm_ctas")) r.comm_ctas = value;
   else if (!strcmp(name, "spin_timeout_ms")) r.spin_timeout_ms = value;
   else if (!strcmp(name, "gemm_cluster")) r.gemm_cluster = value;
+  else if (!strcmp(name, "gemm_force_bn")) r.gemm_force_bn = value;
   else return set_error(EDB_E_INVALID, "edb_set_option: unknown option '%s'", name);
   return EDB_OK;
 }
@@ -219,6 +220,7 @@ int edb_get_option(const char* name, int64_t* out) {
   else if (!strcmp(name, "comm_ctas")) *out = r.comm_ctas;
   else if (!strcmp(name, "spin_timeout_ms")) *out = r.spin_timeout_ms;
   else if (!strcmp(name, "gemm_cluster")) *out = r.gemm_cluster;
+  else if (!strcmp(name, "gemm_force_bn")) *out = r.gemm_force_bn;
   else if (!strcmp(name, "sm_count")) *out = r.sm_count;
   else if (!strcmp(name, "rank")) *out = r.rank;
   else if (!strcmp(name, "world")) *out = r.world;

@@ -550,7 +550,7 @@ def fuse_collective_gemms(gm, io, rt, ranks, ops=_default_ops):
         xv, pv = val(x), val(ph)
         if xv is None or pv is None or xv.dtype != bf16 or pv.dtype != bf16 or xv.dim() != 2:
             continue
-        if n_out % n or (n_out // n) % 128 or k_in % 8 or xv.shape[1] != k_in:
+        if n_out % n or n_out % 128 or (n_out // n) % 8 or k_in % 8 or xv.shape[1] != k_in:
             continue
         if bias is not None and (val(bias) is None or val(bias).dim() != 1 or n_out % 8):
             continue

@@ -184,7 +184,7 @@ def run_fused(rank, world, group):
     torch.manual_seed(1234)  # same on every rank: every rank knows every shard
     for (M, N, K, with_bias) in [(512, 256 * world, 256, False), (4096, 1024, 1024, True),
                                  (384, 128 * world, 1000 // 8 * 8, False), (4096, 4096, 1024, True)]:
-        if (N // world) % 128:
+        if N % world or N % 128:
             continue
         W = (torch.randn(N, K, device="cuda") * 0.1).bfloat16()
         x = torch.randn(M, K, device="cuda").bfloat16()
