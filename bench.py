@@ -108,7 +108,13 @@ def cpu_train_step_throughput(args, n_seqs, steps=1):
     reference's CPU runs are fp32) on the host cores; at world 1 there is no collective."""
     import torch
     from oracle import train_oracle
-    cores = os.cpu_count() or 1
+    try:
+        avail = len(os.sched_getaffinity(0))
+    except AttributeError:
+        avail = os.cpu_count() or 1
+    # eager PyTorch on CPU stops scaling (and oversubscribes cgroup-limited boxes) well before
+    # 128 threads: measured 88 s/step with 128 threads vs 4 s with 8 for the same sequence
+    cores = max(1, min(avail, int(os.environ.get("EDB_CPU_THREADS", "32"))))
     torch.set_num_threads(cores)
     t, loss = train_oracle.time_cpu_train_step(args.model, args.attn, n_seqs, args.seq, steps)
     return {"value": n_seqs * steps / t, "unit": "samples/s", "cores": cores, "kind": "port",
