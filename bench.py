@@ -181,11 +181,24 @@ def gemm_roofline(torch, gemm, calls, peaks, sustained):
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / reps
     achieved = flops / ms / 1e9  # TFLOP/s
+    # context only: what cuBLAS reaches on the very same list of GEMMs (same operands, same
+    # back-to-back replay); shapes cuBLAS cannot align (LM head, vocab 50257) hit its sm_75-class
+    # `align1` kernels
+    for a, b in ops[:8]:
+        torch.mm(a, b)
+    torch.cuda.synchronize()
+    e0.record()
+    for a, b in ops:
+        torch.mm(a, b)
+    e1.record()
+    torch.cuda.synchronize()
+    cublas_tf = flops / e0.elapsed_time(e1) / 1e9
     peak = peaks["bf16_tflops_sustained"] if sustained else peaks["bf16_tflops"]
     return {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
             "frac": achieved / peak, "traffic": None, "kernel": "edb::k_gemm_bf16",
             "launches_per_step": len(calls), "avg_launch_us": 1e3 * ms / len(calls),
             "gemm_ms_per_step": ms, "flops_per_step": flops,
+            "cublas_same_launch_list_tflops": cublas_tf,
             "peak_source": peaks["source"] + (", sustained figure (kernel runs inside a long step)"
                                               if sustained else ", burst figure")}
 

@@ -21,7 +21,14 @@ constexpr int kMaxGroups = EDB_MAX_GROUPS;
 // CUDA-graph replays.
 constexpr size_t kFlagBlockBytes = 1024;
 constexpr size_t kFlagAreaBytes = 64 * 1024;           // kMaxGroups blocks + spare
-constexpr size_t kScratchBytes = 1 << 20;              // per-rank scratch (tile counters etc.)
+constexpr size_t kScratchBytes = 8u << 20;             // per-rank scratch: low-latency packet buffers
+// Low-latency ("LL") small-message protocol: 8-byte packets {4 B payload, 4 B epoch} pushed into
+// the receivers' scratch with single 8-byte stores, so data and flag become visible together and
+// an op needs no fence, no flag round trip and no peer reads (NCCL's LL idea).  Per group slot
+// (first kLLGroups slots): 2 parities x kMaxGroup sources x kLLCapacity packets.
+constexpr int kLLGroups = 4;
+constexpr size_t kLLCapacity = 8192;                   // packets per (parity, source) = 32 KiB payload
+constexpr size_t kLLBytesPerGroup = 2 * 8 * kLLCapacity * 8;  // 1 MiB
 constexpr size_t kUserOffset = kFlagAreaBytes + kScratchBytes;
 
 enum FlagWord : int {
@@ -33,6 +40,8 @@ enum FlagWord : int {
   F_CNT_B = 26,
   F_CNT_C = 27,
   F_ERR = 28,     // != 0: a spin wait timed out (value = op number)
+  F_LLSEQ = 29,   // sequence number of the low-latency ops of this group
+  F_CNT_LL = 30,  // last-block counter of the LL kernels
   F_CHUNK = 32,   // [32..95] per-chunk flags for fused kernels (written by peers / local CTAs)
 };
 
@@ -56,6 +65,7 @@ struct Runtime {
   int64_t copy_ctas_per_sm = 4;
   int64_t comm_ctas = 16;
   int64_t spin_timeout_ms = 10000;
+  int64_t ll_max_bytes = 0;  // payload per rank up to which the LL protocol is used (0 = off)
   int64_t gemm_force_bn = 0;  // tuning aid: 128 / 256 overrides the tile-width heuristic
   int64_t gemm_cluster = 2;  // 2: pair CTAs in clusters and multicast the B tile; 1: off
 };
@@ -76,6 +86,9 @@ void count_launch();
     if (!(cond)) return ::edb::set_error(EDB_E_INVALID, __VA_ARGS__); \
   } while (0)
 
+inline char* ll_region(char* heap, int slot) {
+  return heap + kFlagAreaBytes + (size_t)slot * kLLBytesPerGroup;
+}
 inline uint64_t* flag_block(char* heap, int slot) {
   return reinterpret_cast<uint64_t*>(heap + (size_t)slot * kFlagBlockBytes);
 }
@@ -139,6 +152,9 @@ int make_box(Box* out, const void* src, const int64_t* src_strides, void* dst,
              const int64_t* dst_strides, const int64_t* extents, int ndim, int elem_size, int peer);
 int fill_flagctx(FlagCtx* f, int gid);
 int grid_for_bytes(size_t bytes, int threads, int max_ctas_per_sm);
+// edb_ll.cu: low-latency path; returns -1 when the op is not eligible (caller uses the flag path)
+int ll_try(int gid, int mode, void* dst, const void* src, int64_t in_bytes, int64_t outer,
+           int64_t row_bytes, int dtype, int redop, float scale, cudaStream_t st);
 
 inline size_t dtype_size(int dt) {
   switch (dt) {

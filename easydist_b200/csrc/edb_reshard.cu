@@ -606,9 +606,14 @@ int edb_all_gather(int gid, uint64_t dst_off, const void* src, const int64_t* lo
   if (total == 0) return EDB_OK;
   rc = check_symm(dst_off, total, "edb_all_gather");
   if (rc) return rc;
+  char* out_me = r.heap + dst_off;
+  {
+    const int ll = ll_try(gid, /*LL_ALL_GATHER*/ 1, out_me, src, outer * rowb, outer, rowb, 0, 0, 1.0f,
+                          (cudaStream_t)stream);
+    if (ll >= 0) return ll;
+  }
   const int64_t ext[2] = {outer, rowb};
   const int64_t s_src[2] = {rowb, 1}, s_out[2] = {rowb * n, 1};
-  char* out_me = r.heap + dst_off;
   rc = make_box(&d.box[0], src, s_src, out_me + (int64_t)me * rowb, s_out, ext, 2, 1, -1);
   if (rc) return rc;
   d.n_in = 1;
@@ -811,6 +816,12 @@ int edb_reduce_scatter(int gid, void* dst, uint64_t stage_off, const void* src,
   const int64_t chunk_b = c * inner_el * (int64_t)es;
   const int64_t total = outer * chunk_b * n;
   if (total == 0) return EDB_OK;
+  if (src && out_dtype == dtype) {
+    const float sc = post_scale * (redop == EDB_AVG ? 1.0f / (float)n : 1.0f);
+    const int ll = ll_try(gid, /*LL_REDUCE_SCATTER*/ 2, dst, src, total, outer, chunk_b, dtype, redop,
+                          sc, (cudaStream_t)stream);
+    if (ll >= 0) return ll;
+  }
   if (n > 1 || !src) {
     rc = check_symm(stage_off, (size_t)total, "edb_reduce_scatter");
     if (rc) return rc;
@@ -861,6 +872,11 @@ int edb_all_reduce(int gid, void* dst, uint64_t stage_off, uint64_t stage2_off, 
               "edb_all_reduce: avg on integer dtype");
   const int64_t total = numel * (int64_t)es;
   if (total == 0) return EDB_OK;
+  if (src) {
+    const int ll = ll_try(gid, /*LL_ALL_REDUCE*/ 0, dst, src, total, 1, total, dtype, redop,
+                          redop == EDB_AVG ? 1.0f / (float)n : 1.0f, (cudaStream_t)stream);
+    if (ll >= 0) return ll;
+  }
   if (n > 1 || !src) {
     rc = check_symm(stage_off, (size_t)total, "edb_all_reduce");
     if (rc) return rc;

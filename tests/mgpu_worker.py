@@ -138,10 +138,11 @@ def run_p2p(rank, world, group):
     return n_ok
 
 
-def run_graph(rank, world, group):
-    """CUDA-graph capture + replay: epoch flags must keep working with static parameters."""
+def run_graph(rank, world, group, rows=64):
+    """CUDA-graph capture + replay: epoch flags must keep working with static parameters
+    (rows=64: flag protocol, 64 KiB messages; rows=4: low-latency packet protocol when enabled)."""
     rt = runtime.get_runtime()
-    x = torch.zeros(64, 256, device="cuda")
+    x = torch.zeros(rows, 256, device="cuda")
     buf_ag = rt.alloc(x.numel() * 4 * world)
     buf_rs = rt.alloc(x.numel() * 4 * world)
     buf_ar = rt.alloc(x.numel() * 4)
@@ -153,9 +154,9 @@ def run_graph(rank, world, group):
         return g, r, a
 
     def expect(vals):
-        g = np.concatenate([np.full((64, 256), v, np.float32) for v in vals])
-        return g, g[rank * 64:(rank + 1) * 64] * world, np.full((64, 256), max(vals) * world,
-                                                                np.float32)
+        g = np.concatenate([np.full((rows, 256), v, np.float32) for v in vals])
+        return g, g[rank * rows:(rank + 1) * rows] * world, np.full((rows, 256),
+                                                                    max(vals) * world, np.float32)
     s = torch.cuda.Stream()
     s.wait_stream(torch.cuda.current_stream())
     with torch.cuda.stream(s):
@@ -349,6 +350,8 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--bench", action="store_true")
     ap.add_argument("--heap-gb", type=float, default=8.0)
+    ap.add_argument("--ll-bytes", type=int, default=-1,
+                    help="override the low-latency protocol threshold (0 = off)")
     args = ap.parse_args()
     rank = int(os.environ["RANK"])
     world = int(os.environ["WORLD_SIZE"])
@@ -357,11 +360,14 @@ def main():
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     rt = runtime.init(rank, world, local, heap_bytes=int(args.heap_gb * (1 << 30)))
     rt.set_option("spin_timeout_ms", 4000)
+    if args.ll_bytes >= 0:
+        rt.set_option("ll_max_bytes", args.ll_bytes)
     group = list(range(world))
     n = run_cases(rank, world, group)
     n += run_cases(rank, world, group, tag="b")  # second pass: epochs keep counting
     n += run_p2p(rank, world, group)
     n += run_graph(rank, world, group)
+    n += run_graph(rank, world, group, rows=4)
     n += run_fused(rank, world, group)
     if world >= 4 and world % 2 == 0:
         # 2-D mesh: groups along each mesh dim (ranks in mesh-coordinate order)
