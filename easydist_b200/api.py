@@ -136,22 +136,18 @@ def _compile_dp(func, parallel_mode, tracing_mode, args, kwargs, *, ops=_default
     return EDCompiledFunc(gm, params, buffers, named_states, info=info)
 
 
-def _compile_auto(func, tracing_mode, args, kwargs, *, plan=None, ops=_default_ops, native=True,
-                  planner="GREEDY"):
-    """Auto-SPMD with a given plan: {node_name: {'strategy': NodeSPMDStrategy}} in the vocabulary
-    of easydist_b200.metair (or the reference's own objects).  The plan is what the reference's
-    AutoFlow solver emits (compile_auto.py:93-186); producing it stays the reference's job."""
-    if plan is None:
-        raise NotImplementedError(
-            "parallel_mode='auto' needs a sharding plan: use easydist_b200.api.register() to run "
-            "behind the reference's solver, or pass plan=<recorded plan>")
-    from . import metair as M
-    params, buffers, named_states, gm, module, opt = trace_train_step(func, args, kwargs,
-                                                                      tracing_mode)
-    io = GraphIO(gm, params, buffers, named_states)
-    mesh = get_device_mesh("spmd")
+def _lower_auto(gm, plan, state_io_map, params, buffers, named_states, args, kwargs, *, ops, native,
+                planner, mesh):
+    """Shared tail of the auto path: lower with the plan, shard state and inputs locally, finish."""
+    n_p, n_b = len(params), len(buffers)
+    flat_states, spec = pytree.tree_flatten(named_states)
+    placeholders = [n for n in gm.graph.nodes if n.op == "placeholder"]
+    param_ph = placeholders[:n_p]
+    buffer_ph = placeholders[n_p:n_p + n_b]
+    state_ph = placeholders[n_p + n_b:n_p + n_b + len(flat_states)]
+    input_phs = placeholders[n_p + n_b + len(flat_states):]
     plan = lowering._normalise_plan(plan)
-    lowering.sharding_transform(gm, plan, io.state_io_map(), ops=ops, mesh=mesh, planner=planner)
+    lowering.sharding_transform(gm, plan, state_io_map, ops=ops, mesh=mesh, planner=planner)
     env = gm._edb_shard_env
 
     def shard_local(t, ph):
@@ -165,14 +161,12 @@ def _compile_auto(func, tracing_mode, args, kwargs, *, plan=None, ops=_default_o
         return t
 
     with torch.no_grad():
-        params = {k: shard_local(v.detach(), ph) for (k, v), ph in zip(params.items(), io.param_ph)}
+        params = {k: shard_local(v.detach(), ph) for (k, v), ph in zip(params.items(), param_ph)}
         buffers = {k: shard_local(v.detach(), ph) for (k, v), ph in zip(buffers.items(),
-                                                                       io.buffer_ph)}
-        flat_states, spec = pytree.tree_flatten(named_states)
+                                                                       buffer_ph)}
         flat_states = [shard_local(s.detach() if isinstance(s, torch.Tensor) else s, ph)
-                       for s, ph in zip(flat_states, io.state_ph)]
+                       for s, ph in zip(flat_states, state_ph)]
         named_states = pytree.tree_unflatten(flat_states, spec)
-    input_phs = io.input_ph
 
     def input_transform(a, kw):
         flat, spec_in = pytree.tree_flatten((a, kw))
@@ -185,6 +179,53 @@ def _compile_auto(func, tracing_mode, args, kwargs, *, plan=None, ops=_default_o
     info.update(mode="auto", mesh=mesh.shape)
     return EDCompiledFunc(gm, params, buffers, named_states, input_transform=input_transform,
                           info=info)
+
+
+def _compile_auto(func, tracing_mode, args, kwargs, *, plan=None, ops=_default_ops, native=True,
+                  planner="GREEDY", bundle=None):
+    """Auto-SPMD with a given plan: {node_name: {'strategy': NodeSPMDStrategy}} in the vocabulary
+    of easydist_b200.metair (or the reference's own objects), keyed by the node names of the
+    traced graph.  The plan is what the reference's AutoFlow solver emits
+    (compile_auto.py:93-186); producing it stays the reference's job.  `bundle` = JSON text from
+    graph_io.dump_bundle (graph + plan recorded where the reference runs)."""
+    mesh = get_device_mesh("spmd")
+    if bundle is not None:
+        return compile_from_bundle(bundle, args, kwargs, ops=ops, native=native, planner=planner)
+    if plan is None:
+        raise NotImplementedError(
+            "parallel_mode='auto' needs a sharding plan: use easydist_b200.api.register() to run "
+            "behind the reference's solver, or pass plan=<plan> / bundle=<recorded graph+plan>")
+    params, buffers, named_states, gm, module, opt = trace_train_step(func, args, kwargs,
+                                                                      tracing_mode)
+    io = GraphIO(gm, params, buffers, named_states)
+    return _lower_auto(gm, plan, io.state_io_map(), params, buffers, named_states, args, kwargs,
+                       ops=ops, native=native, planner=planner, mesh=mesh)
+
+
+def compile_from_bundle(bundle_text, args, kwargs, *, ops=_default_ops, native=True,
+                        planner="GREEDY"):
+    """Lower and run a graph + plan recorded by graph_io.dump_bundle (e.g. solved by the
+    reference on another machine).  `args` must contain the nn.Module and Optimizer the graph was
+    traced with (their parameters/optimizer state provide the initial values)."""
+    from . import graph_io
+    from .compile import find_module_and_optimizer, warm_up_optimizer
+    mesh = get_device_mesh("spmd")
+    module, opt = find_module_and_optimizer(args, kwargs)
+    device = next(module.parameters()).device
+    gm, plan, state_io, _ = graph_io.load_bundle(bundle_text, device=device.type)
+    params = dict(module.named_parameters())
+    buffers = dict(module.named_buffers())
+    named_states = warm_up_optimizer(module, opt)
+    flat = [x.detach() if isinstance(x, torch.Tensor) else None
+            for x in _flat_inputs(params, buffers, named_states, args, kwargs)]
+    lowering.propagate_local_meta(gm, flat)  # global metas (nothing is sharded yet)
+    class _Named:  # hashable stand-in for the MetaNode/MetaVar keys of the reference's map
+        def __init__(self, name):
+            self.name = name
+
+    io_map = {_Named(a): _Named(b) for a, b in state_io}
+    return _lower_auto(gm, plan, io_map, params, buffers, named_states, args, kwargs, ops=ops,
+                       native=native, planner=planner, mesh=mesh)
 
 
 class CompiledFuncWrapper:

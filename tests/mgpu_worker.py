@@ -264,6 +264,22 @@ def bench_fused(rank, world, group):
                   flush=True)
 
 
+def run_auto_bundle(rank, world):
+    """Auto-SPMD on real GPUs: graph + plan solved by the unmodified reference (recorded in
+    tests/golden/auto_foo_mesh*.json), lowered by easydist_b200.lowering.sharding_transform and
+    executed with the libedb kernels; outputs vs vanilla PyTorch on the same GPU, rtol 1e-4 (the
+    reference's comparator, tests/test_torch/test_spmd.py:67)."""
+    from tests.test_auto_bundle_cpu import run_bundle
+    mesh_shape = {2: (2,), 4: (2, 2)}.get(world)
+    if mesh_shape is None:
+        return 0
+    ok, msg, hist = run_bundle(rank, world, mesh_shape, reshard, True, "cuda")
+    assert ok, f"auto bundle mesh {mesh_shape}: {msg}"
+    if rank == 0:
+        print(f"AUTO_BUNDLE_OK mesh={mesh_shape} comm={hist}", flush=True)
+    return 1
+
+
 def _graph_timer(world):
     """Time `f` as the average of 10 captured calls per CUDA-graph replay (no Python / launch
     overhead in the measurement), max over ranks."""
@@ -369,6 +385,7 @@ def main():
     n += run_graph(rank, world, group)
     n += run_graph(rank, world, group, rows=4)
     n += run_fused(rank, world, group)
+    n += run_auto_bundle(rank, world)
     if world >= 4 and world % 2 == 0:
         # 2-D mesh: groups along each mesh dim (ranks in mesh-coordinate order)
         mesh = np.arange(world).reshape(2, world // 2)

@@ -81,7 +81,12 @@ def main():
 
             def mine(fx_module, opt_strategy, state_io_map):
                 if record and rank == 0:
-                    saved["plan"] = metair.plan_to_json(metair.plan_from_reference(opt_strategy))
+                    from easydist_b200 import graph_io
+                    saved["plan"] = graph_io.dump_bundle(
+                        fx_module, opt_strategy,
+                        [(a.name, b.name) for a, b in state_io_map.items()],
+                        extra={"mesh": list(mesh_shape), "model": "Foo(64)", "seed": 42,
+                               "batch_seed": 7, "batch": [16, 64], "planner": planner})
                 return lowering.sharding_transform(fx_module, opt_strategy, state_io_map,
                                                    ops=gloo_ops, mesh=my_mesh, planner=planner)
             ref_auto.sharding_transform = mine
