@@ -62,7 +62,7 @@ def run_cases(rank, world, group, tag=""):
             check_equal(got, want, key)
             n_ok += 1
     a2a = [((2, 4 * world), 0, 1), ((2 * world, 3), 1, 0), ((2, 3, 2 * world), 0, 2),
-           ((2, world, 5), 2, 1), ((2, 128, 16 * world), 0, 2), ((4, 128, 8 * world), 2, 0),
+           ((2, world, 5), 2, 1), ((2, 128, 16 * world), 0, 2), ((2 * world, 16, 8 * world), 2, 0),
            ((2, 32 * world, 128, 32), 0, 1), ((64 * world, 64), 1, 0)]
     for dtype in ("float32", "bfloat16", "int64"):
         for shape, g, s in a2a:
