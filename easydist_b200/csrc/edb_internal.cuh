@@ -21,14 +21,14 @@ constexpr int kMaxGroups = EDB_MAX_GROUPS;
 // CUDA-graph replays.
 constexpr size_t kFlagBlockBytes = 1024;
 constexpr size_t kFlagAreaBytes = 64 * 1024;           // kMaxGroups blocks + spare
-constexpr size_t kScratchBytes = 8u << 20;             // per-rank scratch: low-latency packet buffers
+constexpr size_t kScratchBytes = 40u << 20;             // per-rank scratch: low-latency packet buffers
 // Low-latency ("LL") small-message protocol: 8-byte packets {4 B payload, 4 B epoch} pushed into
 // the receivers' scratch with single 8-byte stores, so data and flag become visible together and
 // an op needs no fence, no flag round trip and no peer reads (NCCL's LL idea).  Per group slot
 // (first kLLGroups slots): 2 parities x kMaxGroup sources x kLLCapacity packets.
 constexpr int kLLGroups = 4;
-constexpr size_t kLLCapacity = 8192;                   // packets per (parity, source) = 32 KiB payload
-constexpr size_t kLLBytesPerGroup = 2 * 8 * kLLCapacity * 8;  // 1 MiB
+constexpr size_t kLLCapacity = 65536;                  // packets per (parity, source) = 256 KiB payload
+constexpr size_t kLLBytesPerGroup = 2 * 8 * kLLCapacity * 8;  // 8 MiB
 constexpr size_t kUserOffset = kFlagAreaBytes + kScratchBytes;
 
 enum FlagWord : int {
@@ -65,7 +65,7 @@ struct Runtime {
   int64_t copy_ctas_per_sm = 4;
   int64_t comm_ctas = 16;
   int64_t spin_timeout_ms = 10000;
-  int64_t ll_max_bytes = 0;  // payload per rank up to which the LL protocol is used (0 = off)
+  int64_t ll_max_bytes = 128 * 1024;  // payload per rank up to which the LL protocol is used (0 = off)
   int64_t gemm_force_bn = 0;  // tuning aid: 128 / 256 overrides the tile-width heuristic
   int64_t gemm_cluster = 2;  // 2: pair CTAs in clusters and multicast the B tile; 1: off
 };

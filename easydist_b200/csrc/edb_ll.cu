@@ -232,8 +232,8 @@ int ll_try(int gid, int mode, void* dst, const void* src, int64_t in_bytes, int6
   d.redop = (redop == EDB_AVG) ? EDB_SUM : redop;
   d.scale = scale;
   d.timeout_ns = (uint64_t)r.spin_timeout_ms * 1000000ull;
-  int grid = (int)((words + 255) / 256);
-  if (grid > 32) grid = 32;
+  int grid = (int)((words + 1023) / 1024);
+  if (grid > 64) grid = 64;
   if (grid < 1) grid = 1;
   switch (d.dtype) {
     case EDB_F32: launch_ll<EDB_F32>(d, grid, st); break;
