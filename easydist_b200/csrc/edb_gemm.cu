@@ -445,49 +445,70 @@ __device__ __forceinline__ void ag_comm_role(const FusedArgs& fa, uint8_t* smem,
 }
 
 template <typename Out>
+__device__ __forceinline__ void rs_store(Out* out, int64_t i, const float* acc) {
+  if (sizeof(Out) == 4) {
+    float4* o = reinterpret_cast<float4*>(out) + 2 * i;
+    o[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    o[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+  } else {
+    uint4 o;
+    __nv_bfloat162 h0 = __floats2bfloat162_rn(acc[0], acc[1]);
+    __nv_bfloat162 h1 = __floats2bfloat162_rn(acc[2], acc[3]);
+    __nv_bfloat162 h2 = __floats2bfloat162_rn(acc[4], acc[5]);
+    __nv_bfloat162 h3 = __floats2bfloat162_rn(acc[6], acc[7]);
+    o.x = *reinterpret_cast<uint32_t*>(&h0);
+    o.y = *reinterpret_cast<uint32_t*>(&h1);
+    o.z = *reinterpret_cast<uint32_t*>(&h2);
+    o.w = *reinterpret_cast<uint32_t*>(&h3);
+    reinterpret_cast<uint4*>(out)[i] = o;
+  }
+}
+
+// Sum the n receive slots in rank order (fp32), scale, cast.  All slots are local memory; every
+// load of an iteration is issued before the first add so that n x U 16-byte loads are in flight.
+template <typename Out>
 __device__ __forceinline__ void rs_tail_reduce(const FusedArgs& fa, uint64_t tid, uint64_t nthr) {
   const int64_t nvec = fa.chunk_bytes / 16;  // 8 bf16 per vector
   const int n = fa.f.n;
   Out* out = static_cast<Out*>(fa.rs_dst);
-  for (int64_t i = tid; i < nvec; i += nthr) {
-    float acc[8];
-    {
-      const uint4 r = *reinterpret_cast<const uint4*>(fa.recv_base + i * 16);
-      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r);
+  constexpr int U = 2;
+  for (int64_t i0 = tid; i0 < nvec; i0 += U * nthr) {
+    uint4 raw[U][kMaxGroup];
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const float2 v = __bfloat1622float2(h[e]);
-        acc[2 * e] = v.x;
-        acc[2 * e + 1] = v.y;
-      }
-    }
-    for (int s = 1; s < n; ++s) {
-      const uint4 r = *reinterpret_cast<const uint4*>(fa.recv_base + (int64_t)s * fa.chunk_bytes + i * 16);
-      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r);
+    for (int u = 0; u < U; ++u) {
+      const int64_t i = i0 + u * (int64_t)nthr;
+      if (i < nvec) {
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const float2 v = __bfloat1622float2(h[e]);
-        acc[2 * e] += v.x;
-        acc[2 * e + 1] += v.y;
+        for (int s = 0; s < kMaxGroup; ++s)
+          if (s < n)
+            raw[u][s] = *reinterpret_cast<const uint4*>(fa.recv_base + (int64_t)s * fa.chunk_bytes + i * 16);
       }
     }
 #pragma unroll
-    for (int e = 0; e < 8; ++e) acc[e] *= fa.rs_scale;
-    if (sizeof(Out) == 4) {
-      float4* o = reinterpret_cast<float4*>(out) + 2 * i;
-      o[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
-      o[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
-    } else {
-      uint4 o;
-      __nv_bfloat162 h0 = __floats2bfloat162_rn(acc[0], acc[1]);
-      __nv_bfloat162 h1 = __floats2bfloat162_rn(acc[2], acc[3]);
-      __nv_bfloat162 h2 = __floats2bfloat162_rn(acc[4], acc[5]);
-      __nv_bfloat162 h3 = __floats2bfloat162_rn(acc[6], acc[7]);
-      o.x = *reinterpret_cast<uint32_t*>(&h0);
-      o.y = *reinterpret_cast<uint32_t*>(&h1);
-      o.z = *reinterpret_cast<uint32_t*>(&h2);
-      o.w = *reinterpret_cast<uint32_t*>(&h3);
-      reinterpret_cast<uint4*>(out)[i] = o;
+    for (int u = 0; u < U; ++u) {
+      const int64_t i = i0 + u * (int64_t)nthr;
+      if (i >= nvec) break;
+      float acc[8];
+#pragma unroll
+      for (int s = 0; s < kMaxGroup; ++s) {
+        if (s < n) {
+          const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw[u][s]);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 v = __bfloat1622float2(h[e]);
+            if (s == 0) {
+              acc[2 * e] = v.x;
+              acc[2 * e + 1] = v.y;
+            } else {
+              acc[2 * e] += v.x;
+              acc[2 * e + 1] += v.y;
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[e] *= fa.rs_scale;
+      rs_store<Out>(out, i, acc);
     }
   }
 }
@@ -1142,8 +1163,9 @@ int edb_gemm_rs_bf16(int gid, void* dst, uint64_t recv_off, const void* A, const
   fa.rs_scale = post_scale;
   fa.rs_out_dtype = out_dtype;
   fa.tiles_per_chunk = (p.m_tiles / n) * p.n_tiles;
-  const int tiles = p.m_tiles * p.n_tiles;
-  const int grid = tiles < sms ? tiles : sms;
+  // always a full grid: CTAs without a tile still take part in the tail reduction, which is
+  // latency-bound when only a few CTAs read the receive slots (small weight gradients)
+  const int grid = sms;
   return dispatch_gemm<MODE_RS>(bn, a_kmajor != 0, b_kmajor != 0, ta, tb, tc, p, fa, cm, grid,
                                 (cudaStream_t)stream);
 }

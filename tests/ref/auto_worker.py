@@ -68,9 +68,15 @@ def main():
     gloo_ops.init_groups(my_mesh.mesh)
 
     torch.manual_seed(42)
-    model0 = Foo()
     g = torch.Generator().manual_seed(7)
-    batches = [torch.randn(16, 64, generator=g) for _ in range(3)]
+    if os.environ.get("EDB_MODEL", "foo") == "gpt":
+        # the reference's own test model: TEST_GPT of tests/test_torch/test_utils.py:55-68
+        from benchmark.torch.model.gpt import GPT
+        model0 = GPT(depth=2, dim=64, num_heads=4)
+        batches = [torch.randn(4, 32, 64, generator=g) for _ in range(2)]
+    else:
+        model0 = Foo()
+        batches = [torch.randn(16, 64, generator=g) for _ in range(3)]
 
     def run(variant):
         model = copy.deepcopy(model0)

@@ -12,14 +12,16 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 pytestmark = pytest.mark.refonly
 
 
-@pytest.mark.parametrize("mesh,nproc,port,planner", [("2", 2, 29791, "GREEDY"),
-                                                     ("2x2", 4, 29792, "GREEDY"),
-                                                     ("2x2", 4, 29793, "REPLICATE"),
-                                                     ("2x2", 4, 29794, "P2P")])
-def test_dropin_lowering_equals_reference_lowering(mesh, nproc, port, planner):
+@pytest.mark.parametrize("mesh,nproc,port,planner,model", [
+    ("2", 2, 29791, "GREEDY", "foo"), ("2x2", 4, 29792, "GREEDY", "foo"),
+    ("2x2", 4, 29793, "REPLICATE", "foo"), ("2x2", 4, 29794, "P2P", "foo"),
+    ("2", 2, 29795, "GREEDY", "gpt"),   # the reference's GPT test model: views, expand, bmm
+])
+def test_dropin_lowering_equals_reference_lowering(mesh, nproc, port, planner, model):
     if not os.path.isdir("/root/reference/easydist"):
         pytest.skip("reference not present (GPU box)")
-    env = dict(os.environ, EDB_TEST_MESH=mesh, OMP_NUM_THREADS="1", EDB_PLANNER=planner)
+    env = dict(os.environ, EDB_TEST_MESH=mesh, OMP_NUM_THREADS="1", EDB_PLANNER=planner,
+               EDB_MODEL=model)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
            f"--nproc-per-node={nproc}", "--master-addr", "127.0.0.1", "--master-port", str(port),
            os.path.join(ROOT, "tests", "ref", "auto_worker.py")]
