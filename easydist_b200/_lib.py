@@ -71,6 +71,11 @@ SIGNATURES = {
     "edb_gemm_rs_bf16": (c_int, [c_int, c_void_p, c_uint64, c_void_p, c_void_p, c_int64, c_int64,
                                  c_int64, c_int64, c_int64, c_int, c_int, c_float, c_int,
                                  c_void_p]),
+    "edb_layer_norm_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                   c_int64, c_int64, c_float, c_int, c_void_p]),
+    "edb_layer_norm_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                   c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_void_p]),
+    "edb_layer_norm_bwd_workspace": (c_int, [c_int64, POINTER(c_size_t)]),
     "edb_set_option": (c_int, [c_char_p, c_int64]),
     "edb_get_option": (c_int, [c_char_p, POINTER(c_int64)]),
     "edb_launch_count": (c_uint64, []),

@@ -485,10 +485,18 @@ def assign_static_buffers(gm, rt, ops=_default_ops):
 
 def dispatch_compute(gm):
     """Route bf16 `aten.mm` / `aten.addmm` nodes to the tcgen05 GEMM (sharded-op kernel dispatch)."""
-    from . import gemm
+    from . import gemm, norm
     n = 0
     for node in gm.graph.nodes:
         if node.op != "call_function":
+            continue
+        if node.target == aten.native_layer_norm.default:
+            node.target = norm.native_layer_norm
+            n += 1
+            continue
+        if node.target == aten.native_layer_norm_backward.default:
+            node.target = norm.native_layer_norm_backward
+            n += 1
             continue
         val = node.meta.get("val")
         if not isinstance(val, torch.Tensor) or val.dtype != torch.bfloat16:

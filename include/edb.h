@@ -185,6 +185,20 @@ int edb_gemm_rs_bf16(int gid, void* dst, uint64_t c_stage_off, const void* A, co
                      int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb, int a_kmajor,
                      int b_kmajor, float post_scale, int out_dtype, void* stream);
 
+/* LayerNorm over the last dimension — aten.native_layer_norm / native_layer_norm_backward nodes of
+ * the sharded graph (SURVEY.md App. B lists 8+8 per step in config 1).  x, y, dy, dx: [rows, H]
+ * contiguous, dtype bf16 or f32 (w, b, dw, db: [H], same dtype; b/dw/db may be NULL);
+ * mean, rstd: [rows] f32.  HBM-streaming kernels: one warp per row, 16-byte vector accesses, shuffle
+ * reductions; backward keeps the column partials of dw/db in registers and finishes them in a
+ * fixed order (deterministic).  `workspace`: edb_layer_norm_bwd_workspace(H) bytes of scratch.
+ * Supported H: multiples of 256 (bf16) / 128 (f32) up to 2048 / 1024; else EDB_E_UNSUPPORTED. */
+int edb_layer_norm_fwd(void* y, void* mean, void* rstd, const void* x, const void* w, const void* b,
+                       int64_t rows, int64_t H, float eps, int dtype, void* stream);
+int edb_layer_norm_bwd(void* dx, void* dw, void* db, const void* dy, const void* x, const void* mean,
+                       const void* rstd, const void* w, void* workspace, int64_t rows, int64_t H,
+                       int dtype, void* stream);
+int edb_layer_norm_bwd_workspace(int64_t H, size_t* bytes_out);
+
 /* ---- options / introspection --------------------------------------------------------------- */
 
 /* integer options: "allreduce_oneshot_bytes", "copy_ctas_per_sm", "comm_ctas", "spin_timeout_ms" */

@@ -183,3 +183,44 @@ def test_non_bf16_goes_to_aten(rt):
     c = gemm.mm(A, B)
     assert gemm.stats()["aten_mm"] == 1 and gemm.stats()["edb_gemm"] == 0
     assert torch.allclose(c, A @ B, atol=1e-4, rtol=1e-4)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_layer_norm_kernels_match_aten(rt, dtype):
+    """edb_layer_norm_fwd/bwd vs aten.native_layer_norm(_backward) in fp32 on the same inputs.
+    fp32: rtol 1e-5 (the north star's fp tolerance); bf16 I/O: one bf16 ulp on the outputs."""
+    from easydist_b200 import norm
+    aten = torch.ops.aten
+    torch.manual_seed(4)
+    for rows, H in [(4096, 1024), (37, 256), (1000, 768), (5, 2048 if dtype == torch.bfloat16 else 1024)]:
+        x = torch.randn(rows, H, device="cuda", dtype=dtype)
+        w = (torch.randn(H, device="cuda") * 0.5 + 1).to(dtype)
+        b = torch.randn(H, device="cuda").to(dtype)
+        dy = torch.randn(rows, H, device="cuda", dtype=dtype)
+        norm.reset_stats()
+        y, mean, rstd = norm.native_layer_norm(x.view(1, rows, H), [H], w, b, 1e-5)
+        dx, dw, db = norm.native_layer_norm_backward(dy.view(1, rows, H), x.view(1, rows, H), [H],
+                                                     mean, rstd, w, b, [True, True, True])
+        assert norm.stats()["edb_ln_fwd"] == 1 and norm.stats()["edb_ln_bwd"] == 1, norm.stats()
+        xf, wf, bf, dyf = x.float(), w.float(), b.float(), dy.float()
+        ry, rmean, rrstd = aten.native_layer_norm.default(xf.view(1, rows, H), [H], wf, bf, 1e-5)
+        rdx, rdw, rdb = aten.native_layer_norm_backward.default(
+            dyf.view(1, rows, H), xf.view(1, rows, H), [H], rmean, rrstd, wf, bf, [True, True, True])
+        assert mean.shape == rmean.shape and rstd.shape == rrstd.shape
+        assert torch.allclose(mean, rmean, rtol=1e-5, atol=1e-6)
+        assert torch.allclose(rstd, rrstd, rtol=1e-5, atol=1e-6)
+        if dtype == torch.float32:
+            tol = dict(rtol=1e-5, atol=1e-5)
+            red_tol = dict(rtol=1e-4, atol=1e-4 * rows ** 0.5)
+        else:
+            tol = dict(rtol=2 ** -7, atol=2e-2)
+            red_tol = dict(rtol=2 ** -6, atol=0.05 * rows ** 0.5)
+        assert torch.allclose(y.float(), ry, **tol), (rows, H, float((y.float() - ry).abs().max()))
+        assert torch.allclose(dx.float(), rdx, **tol), (rows, H, float((dx.float() - rdx).abs().max()))
+        assert torch.allclose(dw.float(), rdw, **red_tol), (rows, H, float((dw.float() - rdw).abs().max()))
+        assert torch.allclose(db.float(), rdb, **red_tol), (rows, H, float((db.float() - rdb).abs().max()))
+    # unsupported width goes to ATen
+    x = torch.randn(8, 100, device="cuda", dtype=dtype)
+    norm.reset_stats()
+    norm.native_layer_norm(x, [100], torch.ones(100, device="cuda", dtype=dtype), None, 1e-5)
+    assert norm.stats()["aten_ln"] == 1
