@@ -485,16 +485,20 @@ def assign_static_buffers(gm, rt, ops=_default_ops):
 
 def dispatch_compute(gm):
     """Route bf16 `aten.mm` / `aten.addmm` nodes to the tcgen05 GEMM (sharded-op kernel dispatch)."""
+    import os
     from . import gemm, norm
+    native_ln = os.environ.get("EDB_NATIVE_LN", "0") == "1"
     n = 0
     for node in gm.graph.nodes:
         if node.op != "call_function":
             continue
-        if node.target == aten.native_layer_norm.default:
+        if not native_ln:
+            pass
+        elif node.target == aten.native_layer_norm.default:
             node.target = norm.native_layer_norm
             n += 1
             continue
-        if node.target == aten.native_layer_norm_backward.default:
+        elif node.target == aten.native_layer_norm_backward.default:
             node.target = norm.native_layer_norm_backward
             n += 1
             continue
