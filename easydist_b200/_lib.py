@@ -76,6 +76,8 @@ SIGNATURES = {
     "edb_layer_norm_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                    c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_void_p]),
     "edb_layer_norm_bwd_workspace": (c_int, [c_int64, POINTER(c_size_t)]),
+    "edb_colsum": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int, c_void_p]),
+    "edb_colsum_workspace": (c_int, [c_int64, POINTER(c_size_t)]),
     "edb_set_option": (c_int, [c_char_p, c_int64]),
     "edb_get_option": (c_int, [c_char_p, POINTER(c_int64)]),
     "edb_launch_count": (c_uint64, []),

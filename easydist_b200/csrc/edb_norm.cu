@@ -218,6 +218,68 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// Column sums out[c] = sum_r x[r, c] (bias gradients: aten.sum.dim_IntList(dy, [0], True), 97 per
+// GPT-2-medium step).  Grid = column stripes of 32 lanes x EPV x row splits; every lane owns EPV
+// consecutive columns (16-byte loads, coalesced along the row), 4 independent loads in flight.
+template <typename T>
+__global__ void __launch_bounds__(kLnWarps * 32)
+    k_colsum(float* __restrict__ part, const T* __restrict__ x, int64_t rows, int64_t cols,
+             int64_t ld, int rows_per_split) {
+  constexpr int EPV = LnT<T>::EPV;
+  __shared__ float red[kLnWarps][32 * EPV];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t col = ((int64_t)blockIdx.x * 32 + lane) * EPV;
+  const int64_t r0 = (int64_t)blockIdx.y * rows_per_split;
+  const int64_t r1 = r0 + rows_per_split < rows ? r0 + rows_per_split : rows;
+  float acc[EPV];
+#pragma unroll
+  for (int e = 0; e < EPV; ++e) acc[e] = 0.f;
+  if (col < cols) {
+    int64_t r = r0 + warp;
+    for (; r + 3 * kLnWarps < r1; r += 4 * kLnWarps) {
+      uint4 raw[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        raw[u] = *reinterpret_cast<const uint4*>(x + (r + u * kLnWarps) * ld + col);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        float f[EPV];
+        LnT<T>::unpack(raw[u], f);
+#pragma unroll
+        for (int e = 0; e < EPV; ++e) acc[e] += f[e];
+      }
+    }
+    for (; r < r1; r += kLnWarps) {
+      float f[EPV];
+      LnT<T>::unpack(*reinterpret_cast<const uint4*>(x + r * ld + col), f);
+#pragma unroll
+      for (int e = 0; e < EPV; ++e) acc[e] += f[e];
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < EPV; ++e) red[warp][lane * EPV + e] = acc[e];
+  __syncthreads();
+  for (int i = threadIdx.x; i < 32 * EPV; i += blockDim.x) {
+    const int64_t c = (int64_t)blockIdx.x * 32 * EPV + i;
+    if (c < cols) {
+      float s = 0.f;
+#pragma unroll
+      for (int k = 0; k < kLnWarps; ++k) s += red[k][i];
+      part[(int64_t)blockIdx.y * cols + c] = s;
+    }
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+    k_colsum_finish(T* __restrict__ out, const float* __restrict__ part, int n_part, int64_t cols) {
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= cols) return;
+  float s = 0.f;
+  for (int k = 0; k < n_part; ++k) s += part[(int64_t)k * cols + c];
+  out[c] = (T)s;
+}
+
 template <typename T> static bool ln_shape_ok(int64_t H) {
   const int per = 32 * LnT<T>::EPV;
   return H > 0 && H % per == 0 && H / per <= kLnMaxVec && H <= 2048;
@@ -269,6 +331,44 @@ int edb_layer_norm_bwd_workspace(int64_t H, size_t* bytes_out) {
   int sms = rt().sm_count;
   *bytes_out = (size_t)sms * 2 * (size_t)H * sizeof(float);
   return EDB_OK;
+}
+
+int edb_colsum_workspace(int64_t cols, size_t* bytes_out) {
+  *bytes_out = (size_t)64 * (size_t)cols * sizeof(float);
+  return EDB_OK;
+}
+
+int edb_colsum(void* out, const void* x, void* workspace, int64_t rows, int64_t cols, int64_t ld,
+               int dtype, void* stream) {
+  if (rows <= 0 || cols <= 0) return set_error(EDB_E_UNSUPPORTED, "edb_colsum: empty input");
+  if (dtype != EDB_BF16 && dtype != EDB_F32)
+    return set_error(EDB_E_UNSUPPORTED, "edb_colsum: dtype %d", dtype);
+  const int epv = dtype == EDB_BF16 ? 8 : 4;
+  if ((cols % epv) || (ld % epv) || (((uintptr_t)x | (uintptr_t)workspace) & 15))
+    return set_error(EDB_E_UNSUPPORTED, "edb_colsum: cols/ld must be multiples of %d, 16-byte aligned",
+                     epv);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int stripes = (int)((cols + 32 * epv - 1) / (32 * epv));
+  int splits = (2 * rt().sm_count + stripes - 1) / stripes;
+  if (splits > 64) splits = 64;
+  if (splits > rows / 16) splits = (int)(rows / 16 > 0 ? rows / 16 : 1);
+  if (splits < 1) splits = 1;
+  const int rps = (int)((rows + splits - 1) / splits);
+  splits = (int)((rows + rps - 1) / rps);
+  float* part = static_cast<float*>(workspace);
+  dim3 grid(stripes, splits);
+  if (dtype == EDB_BF16) {
+    k_colsum<__nv_bfloat16><<<grid, kLnWarps * 32, 0, st>>>(part, (const __nv_bfloat16*)x, rows, cols,
+                                                           ld, rps);
+    k_colsum_finish<__nv_bfloat16><<<(int)((cols + 255) / 256), 256, 0, st>>>((__nv_bfloat16*)out, part,
+                                                                             splits, cols);
+  } else {
+    k_colsum<float><<<grid, kLnWarps * 32, 0, st>>>(part, (const float*)x, rows, cols, ld, rps);
+    k_colsum_finish<float><<<(int)((cols + 255) / 256), 256, 0, st>>>((float*)out, part, splits, cols);
+  }
+  count_launch();
+  count_launch();
+  return cuda_check(cudaGetLastError(), "k_colsum launch");
 }
 
 int edb_layer_norm_fwd(void* y, void* mean, void* rstd, const void* x, const void* w, const void* b,

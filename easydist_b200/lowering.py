@@ -487,7 +487,7 @@ def dispatch_compute(gm):
     """Route bf16 `aten.mm` / `aten.addmm` nodes to the tcgen05 GEMM (sharded-op kernel dispatch)."""
     import os
     from . import gemm, norm
-    native_ln = os.environ.get("EDB_NATIVE_LN", "0") == "1"
+    native_ln = os.environ.get("EDB_NATIVE_LN", "1") == "1"
     n = 0
     for node in gm.graph.nodes:
         if node.op != "call_function":
@@ -500,6 +500,10 @@ def dispatch_compute(gm):
             continue
         elif node.target == aten.native_layer_norm_backward.default:
             node.target = norm.native_layer_norm_backward
+            n += 1
+            continue
+        if native_ln and node.target == aten.sum.dim_IntList:
+            node.target = norm.sum_dim_intlist
             n += 1
             continue
         val = node.meta.get("val")

@@ -9,7 +9,7 @@ from torch._subclasses.fake_tensor import FakeTensor
 from . import _lib
 from ._lib import check
 
-_stats = {"edb_ln_fwd": 0, "edb_ln_bwd": 0, "aten_ln": 0}
+_stats = {"edb_ln_fwd": 0, "edb_ln_bwd": 0, "aten_ln": 0, "edb_colsum": 0, "aten_sum": 0}
 _DT = {torch.bfloat16: _lib.DTYPE_CODES["bfloat16"], torch.float32: _lib.DTYPE_CODES["float32"]}
 _workspaces = {}
 aten = torch.ops.aten
@@ -94,3 +94,35 @@ def native_layer_norm_backward(grad_out, input, normalized_shape, mean, rstd, we
                                  H, _DT[x.dtype], _stream(x)))
     _stats["edb_ln_bwd"] += 1
     return dx, dw, db
+
+
+_cs_workspaces = {}
+
+
+def sum_dim_intlist(x, dim, keepdim=False, *, dtype=None):
+    """aten.sum.dim_IntList; the column-sum case (2-D, dim == [0]) — every bias gradient of the
+    train step — runs on edb_colsum, everything else on ATen."""
+    ok = (not isinstance(x, FakeTensor) and x.is_cuda and x.dim() == 2 and list(dim) == [0]
+          and dtype is None and x.dtype in _DT and x.stride(1) == 1 and x.numel() > 0)
+    if ok:
+        epv = 8 if x.dtype == torch.bfloat16 else 4
+        ok = x.shape[1] % epv == 0 and x.stride(0) % epv == 0 and x.data_ptr() % 16 == 0 \
+            and x.shape[0] >= 64
+    if not ok:
+        if not isinstance(x, FakeTensor):
+            _stats["aten_sum"] += 1
+        return aten.sum.dim_IntList(x, dim, keepdim, dtype=dtype)
+    rows, cols = x.shape
+    key = (cols, x.device)
+    ws = _cs_workspaces.get(key)
+    lib = _lib.load()
+    if ws is None:
+        nbytes = c_size_t()
+        check(lib.edb_colsum_workspace(cols, byref(nbytes)))
+        ws = torch.empty(nbytes.value, dtype=torch.uint8, device=x.device)
+        _cs_workspaces[key] = ws
+    out = torch.empty((1, cols) if keepdim else (cols,), dtype=x.dtype, device=x.device)
+    check(lib.edb_colsum(out.data_ptr(), x.data_ptr(), ws.data_ptr(), rows, cols, x.stride(0),
+                         _DT[x.dtype], _stream(x)))
+    _stats["edb_colsum"] += 1
+    return out

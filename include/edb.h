@@ -199,6 +199,13 @@ int edb_layer_norm_bwd(void* dx, void* dw, void* db, const void* dy, const void*
                        int dtype, void* stream);
 int edb_layer_norm_bwd_workspace(int64_t H, size_t* bytes_out);
 
+/* Column sums out[c] = sum_r x[r, c] of a [rows, cols] matrix with row stride `ld` (elements):
+ * the bias gradients `aten.sum.dim_IntList(dy, [0], True)` of the sharded graph.  bf16 or f32, fp32
+ * accumulation in a fixed order (deterministic).  `workspace`: edb_colsum_workspace(cols) bytes. */
+int edb_colsum(void* out, const void* x, void* workspace, int64_t rows, int64_t cols, int64_t ld,
+               int dtype, void* stream);
+int edb_colsum_workspace(int64_t cols, size_t* bytes_out);
+
 /* ---- options / introspection --------------------------------------------------------------- */
 
 /* integer options: "allreduce_oneshot_bytes", "copy_ctas_per_sm", "comm_ctas", "spin_timeout_ms" */

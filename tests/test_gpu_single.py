@@ -224,3 +224,25 @@ def test_layer_norm_kernels_match_aten(rt, dtype):
     norm.reset_stats()
     norm.native_layer_norm(x, [100], torch.ones(100, device="cuda", dtype=dtype), None, 1e-5)
     assert norm.stats()["aten_ln"] == 1
+
+
+def test_colsum_matches_fp32_reference(rt):
+    """edb_colsum (bias gradients) vs an fp32 column sum; fp32 accumulation in both, so only the
+    final rounding to the I/O dtype differs: 1 ulp of bf16 / 1e-5 relative for fp32."""
+    from easydist_b200 import norm
+    torch.manual_seed(5)
+    for dtype in (torch.bfloat16, torch.float32):
+        for rows, cols in [(4096, 1024), (4096, 3072), (4096, 4096), (100, 256), (777, 1032)]:
+            x = torch.randn(rows, cols, device="cuda", dtype=dtype)
+            norm.reset_stats()
+            got = norm.sum_dim_intlist(x, [0], True)
+            assert norm.stats()["edb_colsum"] == 1 and got.shape == (1, cols)
+            want = x.double().sum(0, keepdim=True)
+            if dtype == torch.float32:
+                assert torch.allclose(got.double(), want, rtol=1e-5, atol=1e-4)
+            else:
+                assert torch.allclose(got.double(), want, rtol=2 ** -7, atol=0.05 * rows ** 0.5)
+    x = torch.randn(8, 5, 16, device="cuda")
+    norm.reset_stats()
+    norm.sum_dim_intlist(x, [0, 1], False)
+    assert norm.stats()["aten_sum"] == 1
