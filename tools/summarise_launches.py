@@ -1,0 +1,38 @@
+"""Per-kernel totals of an `ncu --metrics gpu__time_duration.sum --csv` launch list.
+
+usage: python tools/summarise_launches.py gpurun_out/final_launches.csv [last_n_launches] > profiles/...csv
+With last_n_launches the summary covers only the tail of the list (= the final, timed step).
+"""
+import csv
+import sys
+from collections import defaultdict
+
+
+def main():
+    path = sys.argv[1]
+    last = int(sys.argv[2]) if len(sys.argv) > 2 else 0
+    rows = []
+    with open(path, newline="") as f:
+        lines = [l for l in f if l.startswith('"')]
+    for r in csv.DictReader(lines):
+        if r.get("Metric Name") == "gpu__time_duration.sum":
+            rows.append((r["Kernel Name"], float(r["Metric Value"].replace(",", "")) / 1e3))
+    if last:
+        rows = rows[-last:]
+    tot = defaultdict(float)
+    cnt = defaultdict(int)
+    for k, us in rows:
+        k = k[:110]
+        tot[k] += us
+        cnt[k] += 1
+    total = sum(tot.values())
+    edb = sum(v for k, v in tot.items() if "edb::" in k)
+    print(f"# {path}: {len(rows)} launches, {total / 1e3:.2f} ms of kernel time (cold-cache, serialised under ncu); "
+          f"edb:: kernels {edb / total:.3f} of it")
+    print("kernel,launches,total_us,avg_us,share")
+    for k, v in sorted(tot.items(), key=lambda kv: -kv[1]):
+        print(f'"{k}",{cnt[k]},{v:.1f},{v / cnt[k]:.2f},{v / total:.4f}')
+
+
+if __name__ == "__main__":
+    main()
