@@ -153,46 +153,55 @@ def workload_config(args, world):
 
 
 def gemm_roofline(torch, gemm, calls, peaks, sustained):
-    """Dominant kernel = the tcgen05 GEMM.  Replays the step's GEMM launches (exact shapes and
-    operand layouts recorded from the compiled graph) back to back on the current stream with
-    CUDA events around the whole list; operands of consecutive launches differ and sum to far more
-    than L2.  achieved = algorithmic FLOPs (2*M*N*K per launch) / measured time."""
+    """Dominant kernel = the tcgen05 GEMM.  Replays the step's GEMM launches (exact shapes, operand
+    layouts and strides recorded from the compiled graph) back to back from a CUDA graph with CUDA
+    events around the whole list on the launching stream; operands of consecutive launches differ
+    and sum to far more than L2.  achieved = algorithmic FLOPs (2*M*N*K per launch) / measured time."""
     if not calls:
         return None
     ops = []
     flops = 0
-    for (M, N, K, a_k, b_k) in calls:
-        A = torch.randn(M, K, device="cuda", dtype=torch.bfloat16)
-        B = torch.randn(K, N, device="cuda", dtype=torch.bfloat16)
-        a = A if a_k else A.t().contiguous().t()
-        b = B.t().contiguous().t() if b_k else B
+    for (M, N, K, a_k, b_k, a_stride, b_stride) in calls:
+        # same extents AND strides as in the step (e.g. the LM-head gradient arrives with a padded,
+        # TMA-legal row stride from the cross-entropy kernel; an unaligned one is staged by gemm.mm)
+        a = torch.empty_strided((M, K), a_stride, device="cuda", dtype=torch.bfloat16).normal_()
+        b = torch.empty_strided((K, N), b_stride, device="cuda", dtype=torch.bfloat16).normal_()
         ops.append((a, b))
         flops += 2 * M * N * K
-    for a, b in ops[:8]:
+    for a, b in ops:
         gemm.mm(a, b)
     torch.cuda.synchronize()
-    reps = 3
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(reps):
-        for a, b in ops:
-            gemm.mm(a, b)
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / reps
+    # replayed from a CUDA graph like the step itself: eager launches of 30-us kernels would measure
+    # the host (ctypes + tensor-map encode per call), not the kernel
+    def graph_ms(mm, reps=3):
+        graph = torch.cuda.CUDAGraph()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            with torch.cuda.graph(graph, stream=side):
+                for a, b in ops:
+                    mm(a, b)
+            graph.replay()
+            side.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(side)
+            for _ in range(reps):
+                graph.replay()
+            e1.record(side)
+            side.synchronize()
+        torch.cuda.current_stream().wait_stream(side)
+        del graph
+        return e0.elapsed_time(e1) / reps
+
+    ms = graph_ms(gemm.mm)
     achieved = flops / ms / 1e9  # TFLOP/s
     # context only: what cuBLAS reaches on the very same list of GEMMs (same operands, same
-    # back-to-back replay); shapes cuBLAS cannot align (LM head, vocab 50257) hit its sm_75-class
+    # graph replay); shapes cuBLAS cannot align (LM head, vocab 50257) hit its sm_75-class
     # `align1` kernels
-    for a, b in ops[:8]:
-        torch.mm(a, b)
-    torch.cuda.synchronize()
-    e0.record()
     for a, b in ops:
         torch.mm(a, b)
-    e1.record()
     torch.cuda.synchronize()
-    cublas_tf = flops / e0.elapsed_time(e1) / 1e9
+    cublas_tf = flops / graph_ms(torch.mm) / 1e9
     peak = peaks["bf16_tflops_sustained"] if sustained else peaks["bf16_tflops"]
     return {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
             "frac": achieved / peak, "traffic": None, "kernel": "edb::k_gemm_bf16",

@@ -78,6 +78,13 @@ SIGNATURES = {
     "edb_layer_norm_bwd_workspace": (c_int, [c_int64, POINTER(c_size_t)]),
     "edb_colsum": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int, c_void_p]),
     "edb_colsum_workspace": (c_int, [c_int64, POINTER(c_size_t)]),
+    "edb_cross_entropy_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
+                                      c_void_p, c_int64, c_int64, c_int64, c_int, c_int, c_void_p]),
+    "edb_cross_entropy_bwd": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p,
+                                      c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int, c_int,
+                                      c_void_p]),
+    "edb_sgd_momentum": (c_int, [c_int, c_void_p, c_void_p, c_void_p, _I64P, c_float, c_float, c_float,
+                                 c_int, c_void_p]),
     "edb_set_option": (c_int, [c_char_p, c_int64]),
     "edb_get_option": (c_int, [c_char_p, POINTER(c_int64)]),
     "edb_launch_count": (c_uint64, []),

@@ -17,7 +17,7 @@ INCLUDE = os.path.join(ROOT, "include")
 LIB_PATH = os.path.join(HERE, "libedb.so")
 BUILD_DIR = os.path.join(HERE, "csrc", "_build")
 
-SOURCES = ["edb_runtime.cu", "edb_reshard.cu", "edb_ll.cu", "edb_norm.cu", "edb_gemm.cu"]
+SOURCES = ["edb_runtime.cu", "edb_reshard.cu", "edb_ll.cu", "edb_norm.cu", "edb_loss.cu", "edb_optim.cu", "edb_gemm.cu"]
 
 NVCC_FLAGS = [
     "-std=c++17", "-O3", "-lineinfo",

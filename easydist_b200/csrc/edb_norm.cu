@@ -119,7 +119,7 @@ __global__ void __launch_bounds__(kLnWarps * 32)
 }
 
 template <typename T, int NV>
-__global__ void __launch_bounds__(kLnWarps * 32)
+__global__ void __launch_bounds__(kLnWarps * 32, (NV <= 4 ? 2 : 1))
     k_ln_bwd(T* __restrict__ dx, float* __restrict__ part, const T* __restrict__ dy,
              const T* __restrict__ x, const float* __restrict__ mean,
              const float* __restrict__ rstd, const T* __restrict__ w, int64_t rows, int H) {
@@ -134,18 +134,60 @@ __global__ void __launch_bounds__(kLnWarps * 32)
     for (int e = 0; e < EPV; ++e) dwa[i][e] = dba[i][e] = 0.f;
   }
   const float inv_h = 1.0f / (float)H;
-  for (int64_t row = (int64_t)blockIdx.x * kLnWarps + warp; row < rows;
-       row += (int64_t)gridDim.x * kLnWarps) {
-    const uint4* xr = reinterpret_cast<const uint4*>(x + row * H);
-    const uint4* gr = reinterpret_cast<const uint4*>(dy + row * H);
-    const float mu = mean[row], rs = rstd[row];
+  const int64_t stride = (int64_t)gridDim.x * kLnWarps;
+  int64_t row = (int64_t)blockIdx.x * kLnWarps + warp;
+  // NV <= 4 (H <= 1024 bf16): the next row's x / dy vectors are requested before the current row
+  // is reduced, so every warp keeps two rows (4 * NV 16-byte loads per lane) in flight; wider rows
+  // already carry that many loads per row and would spill with the extra buffers
+  constexpr bool PF = (NV <= 4);
+  uint4 xq[PF ? NV : 1], gq[PF ? NV : 1];
+  float mu_n = 0.f, rs_n = 0.f;
+  if (PF && row < rows) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      xq[PF ? i : 0] = __ldg(reinterpret_cast<const uint4*>(x + row * H) + i * 32 + lane);
+      gq[PF ? i : 0] = __ldg(reinterpret_cast<const uint4*>(dy + row * H) + i * 32 + lane);
+    }
+    mu_n = mean[row];
+    rs_n = rstd[row];
+  }
+  for (; row < rows; row += stride) {
+    uint4 xc[NV], gc[NV];
+    float mu, rs;
+    if (PF) {
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        xc[i] = xq[PF ? i : 0];
+        gc[i] = gq[PF ? i : 0];
+      }
+      mu = mu_n;
+      rs = rs_n;
+      const int64_t nxt = row + stride;
+      if (nxt < rows) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+          xq[PF ? i : 0] = __ldg(reinterpret_cast<const uint4*>(x + nxt * H) + i * 32 + lane);
+          gq[PF ? i : 0] = __ldg(reinterpret_cast<const uint4*>(dy + nxt * H) + i * 32 + lane);
+        }
+        mu_n = mean[nxt];
+        rs_n = rstd[nxt];
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        xc[i] = __ldg(reinterpret_cast<const uint4*>(x + row * H) + i * 32 + lane);
+        gc[i] = __ldg(reinterpret_cast<const uint4*>(dy + row * H) + i * 32 + lane);
+      }
+      mu = mean[row];
+      rs = rstd[row];
+    }
     float xh[NV][EPV], g[NV][EPV];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       float xv[EPV], gv[EPV];
-      LnT<T>::unpack(xr[i * 32 + lane], xv);
-      LnT<T>::unpack(gr[i * 32 + lane], gv);
+      LnT<T>::unpack(xc[i], xv);
+      LnT<T>::unpack(gc[i], gv);
 #pragma unroll
       for (int e = 0; e < EPV; ++e) {
         xh[i][e] = (xv[e] - mu) * rs;
@@ -218,15 +260,21 @@ __global__ void __launch_bounds__(256)
   }
 }
 
-// Column sums out[c] = sum_r x[r, c] (bias gradients: aten.sum.dim_IntList(dy, [0], True), 97 per
-// GPT-2-medium step).  Grid = column stripes of 32 lanes x EPV x row splits; every lane owns EPV
-// consecutive columns (16-byte loads, coalesced along the row), 4 independent loads in flight.
+// Column sums out[c] = sum_r x[r, c] (bias gradients: aten.sum.dim_IntList(dy, [0], True), 96 per
+// GPT-2-medium step).  Grid = column stripes (32 lanes x EPV columns) x row splits; every lane owns
+// EPV consecutive columns (16-byte loads, coalesced along the row); 8 warps interleave the rows of a
+// split and each keeps 8 independent row loads in flight (32 KB per CTA), so that a [4096,1024]
+// bf16 operand (8 MB) is entirely in flight at once.  Partials are combined in a fixed order.
+constexpr int kCsWarps = 8;
+constexpr int kCsUnroll = 8;
+constexpr int kCsMaxSplits = 128;
+
 template <typename T>
-__global__ void __launch_bounds__(kLnWarps * 32)
+__global__ void __launch_bounds__(kCsWarps * 32)
     k_colsum(float* __restrict__ part, const T* __restrict__ x, int64_t rows, int64_t cols,
              int64_t ld, int rows_per_split) {
   constexpr int EPV = LnT<T>::EPV;
-  __shared__ float red[kLnWarps][32 * EPV];
+  __shared__ float red[kCsWarps][32 * EPV];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t col = ((int64_t)blockIdx.x * 32 + lane) * EPV;
   const int64_t r0 = (int64_t)blockIdx.y * rows_per_split;
@@ -236,22 +284,22 @@ __global__ void __launch_bounds__(kLnWarps * 32)
   for (int e = 0; e < EPV; ++e) acc[e] = 0.f;
   if (col < cols) {
     int64_t r = r0 + warp;
-    for (; r + 3 * kLnWarps < r1; r += 4 * kLnWarps) {
-      uint4 raw[4];
+    for (; r + (kCsUnroll - 1) * kCsWarps < r1; r += kCsUnroll * kCsWarps) {
+      uint4 raw[kCsUnroll];
 #pragma unroll
-      for (int u = 0; u < 4; ++u)
-        raw[u] = *reinterpret_cast<const uint4*>(x + (r + u * kLnWarps) * ld + col);
+      for (int u = 0; u < kCsUnroll; ++u)
+        raw[u] = __ldg(reinterpret_cast<const uint4*>(x + (r + u * kCsWarps) * ld + col));
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < kCsUnroll; ++u) {
         float f[EPV];
         LnT<T>::unpack(raw[u], f);
 #pragma unroll
         for (int e = 0; e < EPV; ++e) acc[e] += f[e];
       }
     }
-    for (; r < r1; r += kLnWarps) {
+    for (; r < r1; r += kCsWarps) {
       float f[EPV];
-      LnT<T>::unpack(*reinterpret_cast<const uint4*>(x + r * ld + col), f);
+      LnT<T>::unpack(__ldg(reinterpret_cast<const uint4*>(x + r * ld + col)), f);
 #pragma unroll
       for (int e = 0; e < EPV; ++e) acc[e] += f[e];
     }
@@ -264,20 +312,33 @@ __global__ void __launch_bounds__(kLnWarps * 32)
     if (c < cols) {
       float s = 0.f;
 #pragma unroll
-      for (int k = 0; k < kLnWarps; ++k) s += red[k][i];
+      for (int k = 0; k < kCsWarps; ++k) s += red[k][i];
       part[(int64_t)blockIdx.y * cols + c] = s;
     }
   }
 }
 
+// out[c] = sum over splits of part[k][c]: 32 columns x 8 slices of k per CTA (independent loads),
+// slices combined in a fixed order.
 template <typename T>
 __global__ void __launch_bounds__(256)
     k_colsum_finish(T* __restrict__ out, const float* __restrict__ part, int n_part, int64_t cols) {
-  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= cols) return;
+  __shared__ float red[8][33];
+  const int cx = threadIdx.x & 31, ky = threadIdx.x >> 5;
+  const int64_t c = (int64_t)blockIdx.x * 32 + cx;
   float s = 0.f;
-  for (int k = 0; k < n_part; ++k) s += part[(int64_t)k * cols + c];
-  out[c] = (T)s;
+  if (c < cols) {
+#pragma unroll 4
+    for (int k = ky; k < n_part; k += 8) s += part[(int64_t)k * cols + c];
+  }
+  red[ky][cx] = s;
+  __syncthreads();
+  if (ky == 0 && c < cols) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += red[k][cx];
+    out[c] = (T)t;
+  }
 }
 
 template <typename T> static bool ln_shape_ok(int64_t H) {
@@ -329,12 +390,12 @@ extern "C" {
 
 int edb_layer_norm_bwd_workspace(int64_t H, size_t* bytes_out) {
   int sms = rt().sm_count;
-  *bytes_out = (size_t)sms * 2 * (size_t)H * sizeof(float);
+  *bytes_out = (size_t)(2 * sms) * 2 * (size_t)H * sizeof(float);  // one partial pair per CTA, 2 CTAs/SM
   return EDB_OK;
 }
 
 int edb_colsum_workspace(int64_t cols, size_t* bytes_out) {
-  *bytes_out = (size_t)64 * (size_t)cols * sizeof(float);
+  *bytes_out = (size_t)kCsMaxSplits * (size_t)cols * sizeof(float);
   return EDB_OK;
 }
 
@@ -349,22 +410,24 @@ int edb_colsum(void* out, const void* x, void* workspace, int64_t rows, int64_t 
                      epv);
   cudaStream_t st = (cudaStream_t)stream;
   const int stripes = (int)((cols + 32 * epv - 1) / (32 * epv));
-  int splits = (2 * rt().sm_count + stripes - 1) / stripes;
-  if (splits > 64) splits = 64;
-  if (splits > rows / 16) splits = (int)(rows / 16 > 0 ? rows / 16 : 1);
+  // about 4 CTAs per SM in total, but at least one full unrolled pass (64 rows) per split
+  int splits = (4 * rt().sm_count + stripes - 1) / stripes;
+  if (splits > kCsMaxSplits) splits = kCsMaxSplits;
+  const int64_t min_rows = kCsWarps * kCsUnroll;
+  if (splits > rows / min_rows) splits = (int)(rows / min_rows > 0 ? rows / min_rows : 1);
   if (splits < 1) splits = 1;
   const int rps = (int)((rows + splits - 1) / splits);
   splits = (int)((rows + rps - 1) / rps);
   float* part = static_cast<float*>(workspace);
   dim3 grid(stripes, splits);
+  const int fin = (int)((cols + 31) / 32);
   if (dtype == EDB_BF16) {
-    k_colsum<__nv_bfloat16><<<grid, kLnWarps * 32, 0, st>>>(part, (const __nv_bfloat16*)x, rows, cols,
+    k_colsum<__nv_bfloat16><<<grid, kCsWarps * 32, 0, st>>>(part, (const __nv_bfloat16*)x, rows, cols,
                                                            ld, rps);
-    k_colsum_finish<__nv_bfloat16><<<(int)((cols + 255) / 256), 256, 0, st>>>((__nv_bfloat16*)out, part,
-                                                                             splits, cols);
+    k_colsum_finish<__nv_bfloat16><<<fin, 256, 0, st>>>((__nv_bfloat16*)out, part, splits, cols);
   } else {
-    k_colsum<float><<<grid, kLnWarps * 32, 0, st>>>(part, (const float*)x, rows, cols, ld, rps);
-    k_colsum_finish<float><<<(int)((cols + 255) / 256), 256, 0, st>>>((float*)out, part, splits, cols);
+    k_colsum<float><<<grid, kCsWarps * 32, 0, st>>>(part, (const float*)x, rows, cols, ld, rps);
+    k_colsum_finish<float><<<fin, 256, 0, st>>>((float*)out, part, splits, cols);
   }
   count_launch();
   count_launch();
@@ -401,7 +464,7 @@ int edb_layer_norm_bwd(void* dx, void* dw, void* db, const void* dy, const void*
   if (((uintptr_t)dx | (uintptr_t)dy | (uintptr_t)x | (uintptr_t)w | (uintptr_t)workspace) & 15)
     return set_error(EDB_E_UNSUPPORTED, "layer_norm_bwd: pointers must be 16-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
-  int grid = rt().sm_count;
+  int grid = 2 * rt().sm_count;
   const int64_t row_ctas = (rows + kLnWarps - 1) / kLnWarps;
   if (grid > row_ctas) grid = (int)row_ctas;
   float* part = static_cast<float*>(workspace);

@@ -23,7 +23,7 @@ from . import _lib
 from ._lib import check, i64_array
 
 _stats = {"edb_gemm": 0, "aten_mm": 0, "padded_operands": 0, "unsupported": {}}
-_calls = []  # (M, N, K, a_kmajor, b_kmajor) of the native launches since reset_stats()
+_calls = []  # (M, N, K, a_kmajor, b_kmajor, a.stride(), b.stride()) of the native launches since reset_stats()
 
 
 def stats():
@@ -101,7 +101,7 @@ def _launch(a, b, bias):
                             1 if a_k else 0, 1 if b_k else 0, 0, _stream(a)))
     _stats["edb_gemm"] += 1
     if len(_calls) < 8192:
-        _calls.append((M, N, K, bool(a_k), bool(b_k)))
+        _calls.append((M, N, K, bool(a_k), bool(b_k), tuple(a.stride()), tuple(b.stride())))
     return out if ldc == N else out[:, :N]
 
 

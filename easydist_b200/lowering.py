@@ -483,12 +483,136 @@ def assign_static_buffers(gm, rt, ops=_default_ops):
     return total
 
 
+def fuse_cross_entropy(gm):
+    """Rewrite the cross-entropy tail of a traced train step onto edb_loss.cu:
+
+        [_to_copy(fp32)] -> _log_softmax(dim=-1) -> nll_loss_forward          ==> loss.cross_entropy_fwd
+        nll_loss_backward -> _log_softmax_backward_data -> [_to_copy(lp)]     ==> loss.cross_entropy_bwd
+
+    Only the exact chain F.cross_entropy(logits.float(), target) traces to is matched (2-D logits,
+    weight=None, reduction mean/sum, log-softmax saved for nothing but its own backward).
+    Returns the number of chains rewritten."""
+    import operator
+    from . import loss
+    graph = gm.graph
+    n = 0
+    for ls in [x for x in graph.nodes if x.op == "call_function" and x.target == aten._log_softmax.default]:
+        x32, dim, half_to_float = ls.args
+        if half_to_float or not isinstance(x32, Node):
+            continue
+        users = list(ls.users)
+        fwd = [u for u in users if u.target == aten.nll_loss_forward.default and u.args[0] is ls]
+        bwd = [u for u in users if u.target == aten.nll_loss_backward.default and u.args[1] is ls]
+        lsb = [u for u in users if u.target == aten._log_softmax_backward_data.default and u.args[1] is ls]
+        if len(users) != 3 or len(fwd) != 1 or len(bwd) != 1 or len(lsb) != 1:
+            continue
+        fwd, bwd, lsb = fwd[0], bwd[0], lsb[0]
+        if len(fwd.args) != 5 or len(bwd.args) != 7 or fwd.kwargs or bwd.kwargs:
+            continue
+        _, tgt, weight, red, ign = fwd.args
+        gout, _, tgt_b, weight_b, red_b, ign_b, tw = bwd.args
+        if weight is not None or weight_b is not None or red not in (1, 2) or red_b != red \
+                or ign_b != ign or tgt_b is not tgt:
+            continue
+        if lsb.args[0] is not bwd or list(bwd.users) != [lsb] or lsb.args[2] != dim:
+            continue
+        if not (isinstance(tw, Node) and tw.target is operator.getitem and tw.args[0] is fwd
+                and tw.args[1] == 1):
+            continue
+        if any(u.target is not operator.getitem for u in fwd.users):
+            continue
+        val = ls.meta.get("val")
+        if isinstance(val, torch.Tensor) and (val.dim() != 2 or dim not in (1, -1)):
+            continue
+        if val is None and dim != 1:
+            continue
+        # optional precision round trip around the fp32 log-softmax
+        x, last = x32, lsb
+        if x32.op == "call_function" and x32.target == aten._to_copy.default and len(x32.users) == 1 \
+                and x32.kwargs.get("dtype") == torch.float32 and len(lsb.users) == 1:
+            cast_back = next(iter(lsb.users))
+            src_val = x32.args[0].meta.get("val") if isinstance(x32.args[0], Node) else None
+            if cast_back.target == aten._to_copy.default and isinstance(src_val, torch.Tensor) \
+                    and cast_back.kwargs.get("dtype") == src_val.dtype \
+                    and set(cast_back.kwargs) <= {"dtype", "layout", "device"} \
+                    and cast_back.kwargs.get("layout", torch.strided) == torch.strided \
+                    and set(x32.kwargs) <= {"dtype"}:
+                x, last = x32.args[0], cast_back
+        with graph.inserting_before(fwd):
+            ce = graph.call_function(loss.cross_entropy_fwd, (x, tgt, ign, red))
+            outs = [graph.call_function(operator.getitem, (ce, i)) for i in range(3)]
+        for u in list(fwd.users):
+            outs[u.args[1]].meta = dict(u.meta)
+            u.replace_all_uses_with(outs[u.args[1]])
+        with graph.inserting_before(last):
+            dx = graph.call_function(loss.cross_entropy_bwd,
+                                     (gout, x, tgt, outs[2], outs[1], ign, red))
+        dx.meta = dict(last.meta)
+        last.replace_all_uses_with(dx)
+        # erase exactly the replaced chain (no graph-wide DCE: userless comm/in-place nodes must stay)
+        dead = [last] if last is not lsb else []
+        dead += [lsb, bwd] + list(fwd.users) + [fwd, ls]
+        if x32 is not x:
+            dead.append(x32)
+        for d in dead:
+            assert not d.users, (d, list(d.users))
+            graph.erase_node(d)
+        n += 1
+    if n:
+        gm.recompile()
+    return n
+
+
+def fuse_optimizer_updates(gm):
+    """The re-inplaced update of torch.optim.SGD(momentum, foreach=True),
+        _foreach_mul_(bufs, mu); _foreach_add_(bufs, grads[, alpha=a]); _foreach_add_(params, bufs, alpha=-lr)
+    (three adjacent nodes), becomes one `optim.sgd_momentum_` node = one multi-tensor kernel pass.
+    Returns the number of triples fused."""
+    from . import optim
+    graph = gm.graph
+    n = 0
+    for mul in [x for x in graph.nodes if x.op == "call_function" and x.target == aten._foreach_mul_.Scalar]:
+        add1, add2 = mul.next, mul.next.next
+        if not (add1.op == "call_function" and add1.target == aten._foreach_add_.List
+                and add2.op == "call_function" and add2.target == aten._foreach_add_.List):
+            continue
+        if mul.kwargs or set(add1.kwargs) - {"alpha"} or set(add2.kwargs) - {"alpha"}:
+            continue
+        if mul.users or add1.users or add2.users or len(mul.args) != 2:
+            continue
+        bufs, mu = mul.args
+        if not isinstance(mu, (int, float)) or len(add1.args) != 2 or len(add2.args) != 2:
+            continue
+        if list(add1.args[0]) != list(bufs) or list(add2.args[1]) != list(bufs):
+            continue
+        grads, params = add1.args[1], add2.args[0]
+        if not (len(grads) == len(bufs) == len(params)):
+            continue
+        if set(params) & set(bufs) or set(grads) & set(bufs) or set(grads) & set(params):
+            continue
+        ga, nlr = add1.kwargs.get("alpha", 1), add2.kwargs.get("alpha", 1)
+        if not isinstance(ga, (int, float)) or not isinstance(nlr, (int, float)):
+            continue
+        with graph.inserting_before(mul):
+            graph.call_function(optim.sgd_momentum_, (list(params), list(grads), list(bufs), mu, ga, nlr))
+        for d in (add2, add1, mul):
+            graph.erase_node(d)
+        n += 1
+    if n:
+        gm.recompile()
+    return n
+
+
 def dispatch_compute(gm):
     """Route bf16 `aten.mm` / `aten.addmm` nodes to the tcgen05 GEMM (sharded-op kernel dispatch)."""
     import os
     from . import gemm, norm
     native_ln = os.environ.get("EDB_NATIVE_LN", "1") == "1"
     n = 0
+    if os.environ.get("EDB_NATIVE_CE", "1") == "1":
+        n += fuse_cross_entropy(gm)
+    if os.environ.get("EDB_NATIVE_OPT", "1") == "1":
+        n += fuse_optimizer_updates(gm)
     for node in gm.graph.nodes:
         if node.op != "call_function":
             continue

@@ -206,6 +206,34 @@ int edb_colsum(void* out, const void* x, void* workspace, int64_t rows, int64_t 
                int dtype, void* stream);
 int edb_colsum_workspace(int64_t cols, size_t* bytes_out);
 
+/* Cross-entropy over the last dimension of logits [rows, vocab] (row stride `ld` elements, bf16 or
+ * f32) — the `_log_softmax -> nll_loss_forward` / `nll_loss_backward -> _log_softmax_backward_data`
+ * chains that end the traced train step (weight=None; reduction 1 = mean, 2 = sum; ignore_index as
+ * in aten.nll_loss_forward).  Forward: one pass, online max / sum-exp in fp32; writes the fp32 scalars
+ * `loss`, `total_weight` (= number of non-ignored rows) and per-row logsumexp `lse` [rows]
+ * (`row_loss` [rows]: scratch).  Backward: dlogits[r, j] = c * (softmax(x_r)[j] - [j == target_r]),
+ * c = *grad_out / *total_weight (mean) or *grad_out (sum), 0 for ignored rows, written in the logits
+ * dtype with row stride `ld_out` (padding columns [vocab, ld_out) zeroed) so the LM-head GEMMs can
+ * consume it without staging.  Rows reduced in a fixed order (deterministic). */
+int edb_cross_entropy_fwd(float* loss, float* total_weight, float* lse, float* row_loss,
+                          const void* logits, int64_t ld, const int64_t* target, int64_t rows,
+                          int64_t vocab, int64_t ignore_index, int reduction, int dtype, void* stream);
+int edb_cross_entropy_bwd(void* dlogits, int64_t ld_out, const void* logits, int64_t ld,
+                          const int64_t* target, const float* lse, const float* grad_out,
+                          const float* total_weight, int64_t rows, int64_t vocab,
+                          int64_t ignore_index, int reduction, int dtype, void* stream);
+
+/* Fused multi-tensor SGD-momentum step — the optimizer region of the compiled train step
+ * (torch.optim.SGD(momentum, foreach=True) traces to `_foreach_mul_(bufs, mu)`,
+ * `_foreach_add_(bufs, grads, alpha=grad_alpha)`, `_foreach_add_(params, bufs, alpha=neg_lr)`; the
+ * reference keeps the optimizer inside the compiled graph: easydist/torch/compile_dp.py:201-260).
+ * For each of the n tensors (host arrays of device pointers and element counts, all of `dtype` bf16
+ * or f32, 16-byte aligned, contiguous):  m = mu*m + grad_alpha*g;  p = p + neg_lr*m, in one pass, with
+ * the rounding of the three ATen ops reproduced (bit-identical result). */
+int edb_sgd_momentum(int n, void* const* params, const void* const* grads, void* const* bufs,
+                     const int64_t* numels, float mu, float grad_alpha, float neg_lr, int dtype,
+                     void* stream);
+
 /* ---- options / introspection --------------------------------------------------------------- */
 
 /* integer options: "allreduce_oneshot_bytes", "copy_ctas_per_sm", "comm_ctas", "spin_timeout_ms" */

@@ -246,3 +246,95 @@ def test_colsum_matches_fp32_reference(rt):
     norm.reset_stats()
     norm.sum_dim_intlist(x, [0, 1], False)
     assert norm.stats()["aten_sum"] == 1
+
+
+def _ce_reference(logits, target, ignore_index, reduction):
+    x = logits.detach().float().requires_grad_(True)
+    red = "mean" if reduction == 1 else "sum"
+    l = torch.nn.functional.cross_entropy(x, target, ignore_index=ignore_index, reduction=red)
+    l.backward()
+    return l.detach(), x.grad
+
+
+def test_cross_entropy_matches_fp32_reference(rt):
+    """edb_cross_entropy_fwd/bwd vs F.cross_entropy on the fp32 copy of the same logits (the chain
+    the traced step contains).  Loss: fp32 online logsumexp, rtol 1e-5.  Gradient: computed in fp32
+    and rounded once to the logits dtype like ATen's chain, but with ex2.approx and x - lse instead of
+    the stored log-softmax: within 1 ulp of the I/O dtype (bf16: 2^-7 relative) plus 1e-7 absolute."""
+    from easydist_b200 import loss
+    torch.manual_seed(11)
+    cases = [(64, 512, torch.bfloat16, "contig"), (37, 50257, torch.bfloat16, "padded"),
+             (37, 50257, torch.bfloat16, "contig"), (129, 1000, torch.float32, "contig"),
+             (16, 1003, torch.float32, "padded"), (4096, 50257, torch.bfloat16, "padded")]
+    for rows, vocab, dtype, layout in cases:
+        for reduction in (1, 2):
+            if layout == "padded":
+                ld = (vocab + 7) // 8 * 8
+                buf = torch.full((rows, ld), 1e4, device="cuda", dtype=dtype)  # poison the padding
+                logits = buf[:, :vocab]
+                logits.copy_(torch.randn(rows, vocab, device="cuda") * 3)
+            else:
+                logits = (torch.randn(rows, vocab, device="cuda") * 3).to(dtype)
+            target = torch.randint(0, vocab, (rows,), device="cuda")
+            target[::7] = -100
+            target[1] = vocab - 1
+            target[2] = 0
+            loss.reset_stats()
+            l, tw, lse = loss.cross_entropy_fwd(logits, target, -100, reduction)
+            g = torch.full((), 0.5, device="cuda")
+            dx = loss.cross_entropy_bwd(g, logits, target, lse, tw, -100, reduction)
+            st = loss.stats()
+            assert st["edb_ce_fwd"] == 1 and st["edb_ce_bwd"] == 1 and st["aten_ce"] == 0
+            want_l, want_dx = _ce_reference(logits, target, -100, reduction)
+            assert torch.allclose(l, want_l, rtol=1e-5, atol=1e-5), (rows, vocab, dtype, l, want_l)
+            assert float(tw) == float((target != -100).sum())
+            assert torch.allclose(lse, torch.logsumexp(logits.float(), 1), rtol=1e-6, atol=1e-5)
+            assert dx.dtype == dtype and dx.shape == (rows, vocab) and dx.stride(0) % 8 == 0
+            ulp = 2.0 ** -7 if dtype == torch.bfloat16 else 1e-5
+            err = (dx.float() - 0.5 * want_dx).abs()
+            bound = ulp * (0.5 * want_dx).abs() + 1e-7
+            assert bool((err <= bound).all()), (rows, vocab, dtype, float((err - bound).max()))
+            assert bool((dx[target == -100] == 0).all())  # ignored rows carry no gradient
+            # padding columns of the output buffer are zero (TMA reads them as part of a box)
+            if dx.stride(0) != vocab:
+                pad = dx.as_strided((rows, dx.stride(0) - vocab), (dx.stride(0), 1), vocab)
+                assert bool((pad == 0).all())
+    # determinism: same bits on a second run
+    l2, _, _ = loss.cross_entropy_fwd(logits, target, -100, 1)
+    l3, _, _ = loss.cross_entropy_fwd(logits, target, -100, 1)
+    assert l2.item() == l3.item()
+    # 3-D logits are not this kernel's case
+    loss.reset_stats()
+    loss.cross_entropy_fwd(torch.randn(4, 10, device="cuda", dtype=torch.float64),
+                           torch.randint(0, 10, (4,), device="cuda"), -100, 1)
+    assert loss.stats()["aten_ce"] == 1
+
+
+def test_sgd_momentum_is_bit_identical_to_the_foreach_ops(rt):
+    """edb_sgd_momentum vs the three ATen foreach ops it replaces (integer-exactness is not enough
+    here: the claim is identical rounding, so torch.equal on random data, bf16 and fp32)."""
+    from easydist_b200 import optim
+    torch.manual_seed(13)
+    shapes = [(50257, 64), (1024,), (3, 5), (7,), (1,), (4096, 1024), (8,), (1000, 33)] + \
+        [(16 + i,) for i in range(330)]  # > 320 tensors: more than one launch
+    for dtype in (torch.bfloat16, torch.float32):
+        for mu, ga, nlr in [(0.9, 1, -1e-3), (0.8, 0.9, -0.05)]:
+            p = [torch.randn(s, device="cuda").to(dtype) for s in shapes]
+            g = [(torch.randn(s, device="cuda") * 0.1).to(dtype) for s in shapes]
+            m = [(torch.randn(s, device="cuda") * 0.1).to(dtype) for s in shapes]
+            p2, m2 = [t.clone() for t in p], [t.clone() for t in m]
+            torch.ops.aten._foreach_mul_.Scalar(m2, mu)
+            torch.ops.aten._foreach_add_.List(m2, g, alpha=ga)
+            torch.ops.aten._foreach_add_.List(p2, m2, alpha=nlr)
+            optim.reset_stats()
+            optim.sgd_momentum_(p, g, m, mu, ga, nlr)
+            assert optim.stats() == {"edb_sgd": 1, "aten_sgd": 0}
+            for i, s in enumerate(shapes):
+                assert torch.equal(m[i], m2[i]), (dtype, s, "momentum buffer")
+                assert torch.equal(p[i], p2[i]), (dtype, s, "parameter")
+    # views that are not 16-byte aligned take the ATen ops
+    base = torch.randn(64, device="cuda")
+    optim.reset_stats()
+    optim.sgd_momentum_([base[1:9]], [torch.randn(8, device="cuda")], [torch.zeros(8, device="cuda")],
+                        0.9, 1, -0.1)
+    assert optim.stats()["aten_sgd"] == 1

@@ -24,7 +24,7 @@ def rt():
                                                     (torch.bfloat16, False, 3e-2),
                                                     (torch.bfloat16, True, 3e-2)])
 def test_gpt2_tiny_train_steps_match_oracle(rt, dtype, cuda_graph, rtol):
-    from easydist_b200 import gemm
+    from easydist_b200 import gemm, loss as loss_mod, optim as optim_mod
     from easydist_b200.api import easydist_compile
     from easydist_b200.workloads import GPT2, GPT2_CONFIGS, gpt2_train_step, synthetic_tokens
     from oracle import train_oracle
@@ -37,6 +37,8 @@ def test_gpt2_tiny_train_steps_match_oracle(rt, dtype, cuda_graph, rtol):
                             cuda_graph=cuda_graph)
     steps = 4
     gemm.reset_stats()
+    loss_mod.reset_stats()
+    optim_mod.reset_stats()
     losses = []
     if cuda_graph:
         # the reference documents the same effect (gpt_train.py:34-36): warm-up + capture consume
@@ -58,3 +60,7 @@ def test_gpt2_tiny_train_steps_match_oracle(rt, dtype, cuda_graph, rtol):
             assert abs(got - w) <= rtol * abs(w), (losses, want)
     if dtype == torch.bfloat16:
         assert gemm.stats()["edb_gemm"] > 0, "bf16 Linear layers must run on the native GEMM"
+    st = loss_mod.stats()
+    assert st["edb_ce_fwd"] > 0 and st["edb_ce_bwd"] > 0 and st["aten_ce"] == 0, st
+    ost = optim_mod.stats()
+    assert ost["edb_sgd"] > 0 and ost["aten_sgd"] == 0, ost
