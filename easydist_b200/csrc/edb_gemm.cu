@@ -278,6 +278,11 @@ struct GemmParams {
   int64_t ldc;
   int M, N, K;
   int m_tiles, n_tiles;
+  // split-K (MODE_PLAIN only): work unit = (tile, k-slice); every slice writes its fp32 partial
+  // tile to `partial` [splits][M][ldp] and k_splitk_reduce sums the slices in a fixed order
+  int splits, kb_per_split;
+  float* partial;
+  int64_t ldp;
 };
 
 // Fusion modes of the GEMM kernel
@@ -568,6 +573,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
   const int crank = (CL == 2) ? (int)cluster_ctarank() : 0;
   const int pm_tiles = (CL == 2) ? (p.m_tiles + 1) / 2 : p.m_tiles;
   const int num_tiles = pm_tiles * p.n_tiles;
+  const int num_units = (MODE == MODE_PLAIN) ? num_tiles * p.splits : num_tiles;
   const int unit0 = (CL == 2) ? (int)blockIdx.x / 2 : (int)blockIdx.x;
   const int unit_stride = (CL == 2) ? n_gemm_ctas / 2 : n_gemm_ctas;
 
@@ -604,7 +610,13 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
       int stage = 0;
       uint32_t phase = 0;
       int ready_chunk = -1;
-      for (int t = unit0; t < num_tiles; t += unit_stride) {
+      for (int u = unit0; u < num_units; u += unit_stride) {
+        const int t = (MODE == MODE_PLAIN) ? u % num_tiles : u;
+        int kb0 = 0, kb1 = k_blocks;
+        if (MODE == MODE_PLAIN && p.splits > 1) {
+          kb0 = (u / num_tiles) * p.kb_per_split;
+          kb1 = kb0 + p.kb_per_split < k_blocks ? kb0 + p.kb_per_split : k_blocks;
+        }
         int m_blk, n_blk, chunk;
         if (CL == 2) {
           chunk = 0;
@@ -626,7 +638,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
             ready_chunk = n_blk;
           }
         }
-        for (int kb = 0; kb < k_blocks; ++kb) {
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem_a + stage * kSmemABytes;
           uint8_t* sb = smem_b + stage * Cfg::kSmemBBytes;
@@ -687,11 +699,16 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
     uint32_t phase = 0;
     int as = 0;
     uint32_t aphase = 0;
-    for (int t = unit0; t < num_tiles; t += unit_stride) {
+    for (int u = unit0; u < num_units; u += unit_stride) {
+      int kb0 = 0, kb1 = k_blocks;
+      if (MODE == MODE_PLAIN && p.splits > 1) {
+        kb0 = (u / num_tiles) * p.kb_per_split;
+        kb1 = kb0 + p.kb_per_split < k_blocks ? kb0 + p.kb_per_split : k_blocks;
+      }
       mbar_wait(&tmem_empty[as], aphase ^ 1);
       tcgen05_fence_after();
       const uint32_t tmem_d = tmem_base + as * BN;
-      for (int kb = 0; kb < k_blocks; ++kb) {
+      for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(&full_bar[stage], phase);
         tcgen05_fence_after();
         if (lane == 0) {
@@ -704,16 +721,16 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
             else da = make_smem_desc(a_addr + k * UMMA_K * 128, 64 * BK * 2, 1024);
             if (B_KMAJOR) db = make_smem_desc(b_addr + k * UMMA_K * 2, 0, 1024);
             else db = make_smem_desc(b_addr + k * UMMA_K * 128, 64 * BK * 2, 1024);
-            if (CL == 2) umma_f16_2cta(tmem_d, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
-            else umma_f16(tmem_d, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            if (CL == 2) umma_f16_2cta(tmem_d, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            else umma_f16(tmem_d, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
           // free the smem stage when these MMAs retire (in both CTAs of a pair)
           if (CL == 2) {
             umma_commit_2cta(&empty_bar[stage], (uint16_t)3);
-            if (kb == k_blocks - 1) umma_commit_2cta(&tmem_full[as], (uint16_t)3);
+            if (kb == kb1 - 1) umma_commit_2cta(&tmem_full[as], (uint16_t)3);
           } else {
             umma_commit(&empty_bar[stage]);
-            if (kb == k_blocks - 1) umma_commit(&tmem_full[as]);
+            if (kb == kb1 - 1) umma_commit(&tmem_full[as]);
           }
         }
         __syncwarp();
@@ -735,7 +752,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
     int as = 0;
     uint32_t aphase = 0;
     int ebuf = 0;
-    for (int t = unit0; t < num_tiles; t += unit_stride) {
+    for (int u = unit0; u < num_units; u += unit_stride) {
+      const int t = (MODE == MODE_PLAIN) ? u % num_tiles : u;
       int m_blk, n_blk, chunk;
       if (CL == 2) {
         chunk = 0;
@@ -743,6 +761,45 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
         n_blk = t / pm_tiles;
       } else {
         tile_coords<MODE>(t, p, fa, m_blk, n_blk, chunk);
+      }
+      if (MODE == MODE_PLAIN && p.splits > 1) {
+        // split-K: this unit's fp32 partial goes straight from registers to the workspace (one
+        // 256-byte run per thread and chunk); k_splitk_reduce adds the slices, bias and rounds
+        mbar_wait(&tmem_full[as], aphase);
+        tcgen05_fence_after();
+        const int64_t r = (int64_t)m_blk * BM + row_in_tile;
+        float* prow = p.partial + ((int64_t)(u / num_tiles) * p.M + r) * p.ldp;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 64) {
+          uint32_t v[64];
+          const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BN + c0);
+          tmem_ld_32x32b_x32(taddr, v);
+          tmem_ld_32x32b_x32(taddr + 32, v + 32);
+          tmem_ld_wait();
+          if (c0 + 64 >= BN) {
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+              if (CL == 2) mbar_arrive_on_leader(&tmem_empty[as]);
+              else mbar_arrive(&tmem_empty[as]);
+            }
+          }
+          const int col0 = n_blk * BN + c0;
+          if (r < p.M) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const int col = col0 + 4 * j;
+              if (col < p.ldp)  // ldp = N rounded up to 4: whole float4 groups only
+                *reinterpret_cast<uint4*>(prow + col) =
+                    make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            }
+          }
+        }
+        if (++as == 2) {
+          as = 0;
+          aphase ^= 1;
+        }
+        continue;
       }
       const CUtensorMap* cmap = &tmap_c;
       int c_row = m_blk * BM;
@@ -852,6 +909,38 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
     if (fa.rs_out_dtype == EDB_F32) rs_tail_reduce<float>(fa, tid, nthr);
     else rs_tail_reduce<__nv_bfloat16>(fa, tid, nthr);
     finish_op(fa.f, q, &s_last, gridDim.x);
+  }
+}
+
+// out[r, c] = bf16( sum_s partial[s][r][c] (s ascending) + bias[c] ): the second half of a split-K GEMM
+__global__ void __launch_bounds__(256)
+    k_splitk_reduce(__nv_bfloat16* __restrict__ C, int64_t ldc, const float* __restrict__ partial,
+                    int64_t ldp, int splits, int M, int N, const __nv_bfloat16* __restrict__ bias) {
+  const int64_t groups_per_row = ldp / 4;
+  const int64_t total = (int64_t)M * groups_per_row;
+  const int64_t slice = (int64_t)M * ldp;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / groups_per_row;
+    const int c = (int)(i - r * groups_per_row) * 4;
+    const float* src = partial + r * ldp + c;
+    float4 acc = *reinterpret_cast<const float4*>(src);
+    for (int s = 1; s < splits; ++s) {
+      const float4 v = *reinterpret_cast<const float4*>(src + s * slice);
+      acc.x += v.x;
+      acc.y += v.y;
+      acc.z += v.z;
+      acc.w += v.w;
+    }
+    float o[4] = {acc.x, acc.y, acc.z, acc.w};
+    __nv_bfloat16* dst = C + r * ldc + c;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      if (c + e < N) {
+        if (bias) o[e] += __bfloat162float(bias[c + e]);
+        dst[e] = __float2bfloat16_rn(o[e]);
+      }
+    }
   }
 }
 
@@ -977,6 +1066,37 @@ static int check_operands(const void* A, const void* B, const void* C, const voi
   return EDB_OK;
 }
 
+// fp32 workspace of split-K GEMMs: one slab per (device, stream) pair, allocated on first use
+// (outside any stream capture: the compiled step always runs eagerly once before it is captured).
+constexpr size_t kSplitKBytes = (size_t)64 << 20;
+struct SplitKSlab {
+  int device;
+  cudaStream_t stream;
+  float* ptr;
+};
+static SplitKSlab g_splitk[16];
+static int g_splitk_n = 0;
+
+static float* splitk_workspace(cudaStream_t st) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+  for (int i = 0; i < g_splitk_n; ++i)
+    if (g_splitk[i].device == dev && g_splitk[i].stream == st) return g_splitk[i].ptr;
+  if (g_splitk_n == 16) return nullptr;
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) {
+    cudaGetLastError();
+    return nullptr;  // cannot allocate while capturing: this launch runs unsplit
+  }
+  float* ptr = nullptr;
+  if (cudaMalloc(&ptr, kSplitKBytes) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  g_splitk[g_splitk_n++] = {dev, st, ptr};
+  return ptr;
+}
+
 static int sm_count_now() {
   Runtime& r = rt();
   if (!r.inited) {
@@ -1027,17 +1147,49 @@ int edb_gemm_bf16(void* C, const void* A, const void* B, const void* bias, int64
   memset(&fa, 0, sizeof(fa));
   CMaps cm;
   memset(&cm, 0, sizeof(cm));
+  p.splits = 1;
+  p.kb_per_split = 0;
+  p.partial = nullptr;
+  p.ldp = (N + 3) / 4 * 4;
+  cudaStream_t st = (cudaStream_t)stream;
+  // split-K: when the tiles occupy at most half of the SMs and K is long (weight gradients:
+  // M, N = layer widths, K = tokens), slices of K go to the idle SMs.  Each slice keeps >= 8
+  // k-blocks so that the pipeline fill and the fp32 partial traffic stay small against the MMAs.
+  const int units = (cl == 2 ? ((p.m_tiles + 1) / 2) : p.m_tiles) * p.n_tiles;
+  const int ctas = units * cl;
+  const int k_blocks = (int)((K + BK - 1) / BK);
+  if (rt().gemm_splitk && 2 * ctas <= sms && k_blocks >= 16) {
+    int splits = sms / ctas;
+    if (splits > k_blocks / 8) splits = k_blocks / 8;
+    if (splits > 8) splits = 8;
+    while (splits > 1 && (size_t)splits * (size_t)M * (size_t)p.ldp * sizeof(float) > kSplitKBytes)
+      --splits;
+    if (splits > 1) {
+      float* ws = splitk_workspace(st);
+      if (ws != nullptr) {
+        p.kb_per_split = (k_blocks + splits - 1) / splits;
+        p.splits = (k_blocks + p.kb_per_split - 1) / p.kb_per_split;  // no empty slice
+        p.partial = ws;
+      }
+    }
+  }
   int grid;
   if (cl == 2) {
-    const int pairs = ((p.m_tiles + 1) / 2) * p.n_tiles;
+    const int pairs = units * p.splits;
     const int clusters = pairs < sms / 2 ? pairs : sms / 2;
     grid = 2 * clusters;
   } else {
-    const int tiles = p.m_tiles * p.n_tiles;
+    const int tiles = units * p.splits;
     grid = tiles < sms ? tiles : sms;
   }
-  return dispatch_gemm<MODE_PLAIN>(bn, a_kmajor != 0, b_kmajor != 0, ta, tb, tc, p, fa, cm, grid,
-                                   (cudaStream_t)stream, cl);
+  rc = dispatch_gemm<MODE_PLAIN>(bn, a_kmajor != 0, b_kmajor != 0, ta, tb, tc, p, fa, cm, grid, st, cl);
+  if (rc || p.splits == 1) return rc;
+  const int64_t groups = (int64_t)M * (p.ldp / 4);
+  int rgrid = (int)((groups + 255) / 256);
+  if (rgrid > 4 * sms) rgrid = 4 * sms;
+  k_splitk_reduce<<<rgrid, 256, 0, st>>>(p.C, ldc, p.partial, p.ldp, p.splits, (int)M, (int)N, p.bias);
+  count_launch();
+  return cuda_check(cudaGetLastError(), "k_splitk_reduce launch");
 }
 
 int edb_ag_gemm_bf16(int gid, void* C, const void* A, const void* bias, uint64_t b_shard_off,
@@ -1089,6 +1241,10 @@ int edb_ag_gemm_bf16(int gid, void* C, const void* A, const void* bias, uint64_t
   p.K = (int)K;
   p.m_tiles = (int)((M + BM - 1) / BM);
   p.n_tiles = (int)(N / bn);
+  p.splits = 1;
+  p.kb_per_split = 0;
+  p.partial = nullptr;
+  p.ldp = 0;
   const int sms = r.sm_count;
   int n_comm = (int)r.comm_ctas;
   if (n_comm < 1) n_comm = 1;
@@ -1157,6 +1313,10 @@ int edb_gemm_rs_bf16(int gid, void* dst, uint64_t recv_off, const void* A, const
   p.K = (int)K;
   p.m_tiles = (int)(M / BM);
   p.n_tiles = (int)((N + bn - 1) / bn);
+  p.splits = 1;
+  p.kb_per_split = 0;
+  p.partial = nullptr;
+  p.ldp = 0;
   fa.recv_base = recv;
   fa.chunk_bytes = (int64_t)chunk_bytes;
   fa.rs_dst = dst;

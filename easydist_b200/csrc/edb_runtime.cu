@@ -208,6 +208,7 @@ int edb_set_option(const char* name, int64_t value) {
   else if (!strcmp(name, "comm_ctas")) r.comm_ctas = value;
   else if (!strcmp(name, "spin_timeout_ms")) r.spin_timeout_ms = value;
   else if (!strcmp(name, "gemm_cluster")) r.gemm_cluster = value;
+  else if (!strcmp(name, "gemm_splitk")) r.gemm_splitk = value;
   else if (!strcmp(name, "gemm_force_bn")) r.gemm_force_bn = value;
   else if (!strcmp(name, "ll_max_bytes")) r.ll_max_bytes = value;
   else return set_error(EDB_E_INVALID, "edb_set_option: unknown option '%s'", name);
@@ -221,6 +222,7 @@ int edb_get_option(const char* name, int64_t* out) {
   else if (!strcmp(name, "comm_ctas")) *out = r.comm_ctas;
   else if (!strcmp(name, "spin_timeout_ms")) *out = r.spin_timeout_ms;
   else if (!strcmp(name, "gemm_cluster")) *out = r.gemm_cluster;
+  else if (!strcmp(name, "gemm_splitk")) *out = r.gemm_splitk;
   else if (!strcmp(name, "gemm_force_bn")) *out = r.gemm_force_bn;
   else if (!strcmp(name, "ll_max_bytes")) *out = r.ll_max_bytes;
   else if (!strcmp(name, "sm_count")) *out = r.sm_count;

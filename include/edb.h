@@ -236,7 +236,8 @@ int edb_sgd_momentum(int n, void* const* params, const void* const* grads, void*
 
 /* ---- options / introspection --------------------------------------------------------------- */
 
-/* integer options: "allreduce_oneshot_bytes", "copy_ctas_per_sm", "comm_ctas", "spin_timeout_ms" */
+/* integer options: "allreduce_oneshot_bytes", "copy_ctas_per_sm", "comm_ctas", "spin_timeout_ms",
+ * "ll_max_bytes", "gemm_cluster", "gemm_force_bn", "gemm_splitk" */
 int edb_set_option(const char* name, int64_t value);
 int edb_get_option(const char* name, int64_t* value_out);
 /* number of kernels this library has launched since load (all entry points) */

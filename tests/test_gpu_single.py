@@ -90,7 +90,9 @@ def test_box_copy_general_strides(rt):
 
 
 GEMM_SHAPES = [(128, 128, 64), (128, 256, 128), (256, 512, 256), (384, 200, 136), (100, 72, 40),
-               (4096, 1024, 1024), (1024, 4096, 1024), (512, 1024, 4096), (640, 3072, 1024)]
+               (4096, 1024, 1024), (1024, 4096, 1024), (512, 1024, 4096), (640, 3072, 1024),
+               # few tiles, long K: these run split-K (fp32 partials + k_splitk_reduce)
+               (1024, 1024, 4096), (304, 200, 2056), (128, 256, 2048), (1000, 72, 1544)]
 
 
 @pytest.mark.parametrize("a_k", [True, False])
@@ -121,7 +123,7 @@ def test_gemm_exact_on_integer_inputs(rt):
     exactly representable, so the result must equal the fp32 reference bit for bit."""
     from easydist_b200 import gemm
     torch.manual_seed(1)
-    for (M, N, K) in [(4096, 1024, 1024), (256, 4096, 512)]:
+    for (M, N, K) in [(4096, 1024, 1024), (256, 4096, 512), (1024, 1024, 2048)]:  # last: split-K
         A = torch.randint(-1, 2, (M, K), device="cuda").bfloat16()
         B = torch.randint(-1, 2, (K, N), device="cuda").bfloat16()
         c = gemm.mm(A, B.t().contiguous().t())
@@ -163,7 +165,7 @@ def test_gemm_unaligned_extents_run_natively(rt):
 def test_addmm_bias_fused_in_epilogue(rt):
     from easydist_b200 import gemm
     torch.manual_seed(3)
-    for (M, N, K) in [(256, 512, 128), (4096, 3072, 1024), (100, 72, 40)]:
+    for (M, N, K) in [(256, 512, 128), (4096, 3072, 1024), (100, 72, 40), (512, 1024, 4096)]:
         a = torch.randn(M, K, device="cuda", dtype=torch.bfloat16)
         w = torch.randn(N, K, device="cuda", dtype=torch.bfloat16)
         bias = torch.randn(N, device="cuda", dtype=torch.bfloat16)
@@ -338,3 +340,29 @@ def test_sgd_momentum_is_bit_identical_to_the_foreach_ops(rt):
     optim.sgd_momentum_([base[1:9]], [torch.randn(8, device="cuda")], [torch.zeros(8, device="cuda")],
                         0.9, 1, -0.1)
     assert optim.stats()["aten_sgd"] == 1
+
+
+def test_gemm_split_k_agrees_with_unsplit(rt):
+    """Split-K only reorders the fp32 accumulation: on small-integer operands the split and the
+    unsplit kernel must agree bit for bit, on random data within one bf16 ulp; the option turns it
+    off; and the workspace is reused across calls (results of consecutive GEMMs do not mix)."""
+    from easydist_b200 import gemm
+    torch.manual_seed(17)
+    M, N, K = 1024, 1024, 4096
+    Ai = torch.randint(-1, 2, (M, K), device="cuda").bfloat16()
+    Bi = torch.randint(-1, 2, (K, N), device="cuda").bfloat16()
+    Ar = torch.randn(M, K, device="cuda", dtype=torch.bfloat16)
+    Br = torch.randn(K, N, device="cuda", dtype=torch.bfloat16)
+    launches0 = rt.lib.edb_launch_count()
+    ci, cr = gemm.mm(Ai.t().contiguous().t(), Bi), gemm.mm(Ar.t().contiguous().t(), Br)  # wgrad layout
+    assert rt.lib.edb_launch_count() - launches0 == 4  # GEMM + reduce, twice
+    rt.set_option("gemm_splitk", 0)
+    try:
+        launches0 = rt.lib.edb_launch_count()
+        ci0, cr0 = gemm.mm(Ai.t().contiguous().t(), Bi), gemm.mm(Ar.t().contiguous().t(), Br)
+        assert rt.lib.edb_launch_count() - launches0 == 2
+    finally:
+        rt.set_option("gemm_splitk", 1)
+    assert torch.equal(ci, ci0)
+    err = (cr.float() - cr0.float()).abs()
+    assert bool((err <= cr0.float().abs() * 2 ** -7 + 1e-2).all())
