@@ -71,6 +71,10 @@ SIGNATURES = {
     "edb_gemm_rs_bf16": (c_int, [c_int, c_void_p, c_uint64, c_void_p, c_void_p, c_int64, c_int64,
                                  c_int64, c_int64, c_int64, c_int, c_int, c_float, c_int,
                                  c_void_p]),
+    "edb_gemm_rs_push_bf16": (c_int, [c_int, c_uint64, c_uint64, c_void_p, c_void_p, c_int64, c_int64,
+                                      c_int64, c_int64, c_int64, c_int, c_int, c_void_p]),
+    "edb_rs_finish": (c_int, [c_int, c_int, c_void_p, c_void_p, c_void_p, _I64P, c_float, c_int,
+                              c_void_p]),
     "edb_layer_norm_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                    c_int64, c_int64, c_float, c_int, c_void_p]),
     "edb_layer_norm_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,

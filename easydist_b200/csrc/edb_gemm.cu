@@ -315,7 +315,13 @@ struct FusedArgs {
   float rs_scale;
   int rs_out_dtype;
   int tiles_per_chunk;
+  // deferred reduce-scatter: the kernel only pushes its tiles (flag words F_CHUNK + 8 + src) and
+  // records its op number in rs_state[0]; k_rs_finish reduces the slots later (rs_state[1] = the op
+  // number of that reduction, which guards the slots against the next step's pushes)
+  int rs_defer;
+  uint64_t* rs_state;
 };
+constexpr int F_PUSHED = F_CHUNK + 8;  // [40..47] PUSHED[p]: peer p's deferred-RS tiles of op q landed
 
 struct CMaps {
   CUtensorMap m[kMaxGroup];  // MODE_RS: store map of member p's receive slot [me]; MODE_AG: m[0] = local shard
@@ -542,7 +548,19 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
   const int n_gemm_ctas = (MODE == MODE_AG) ? (int)gridDim.x - fa.n_comm : (int)gridDim.x;
 
   if (MODE == MODE_RS) {
-    q = begin_op(fa.f, &s_q);  // WAR guard: peers are done with my buffers of earlier ops
+    if (fa.rs_defer) {
+      // no lockstep with the peers: the receive slots belong to this weight alone, and the owners
+      // finished reducing their previous content in op rs_state[1] (same op number on every rank)
+      if (threadIdx.x == 0) s_q = ld_relaxed_gpu(fa.f.local + F_SEQ) + 1;
+      if ((int)threadIdx.x < fa.f.n && (int)threadIdx.x != fa.f.me) {
+        const uint64_t prev = ld_relaxed_gpu(fa.rs_state + 1);
+        if (prev) spin_wait_sys(fa.f.local + F_DONE + threadIdx.x, prev, fa.f.timeout_ns, fa.f.local + F_ERR);
+      }
+      __syncthreads();
+      q = s_q;
+    } else {
+      q = begin_op(fa.f, &s_q);  // WAR guard: peers are done with my buffers of earlier ops
+    }
   } else if (MODE == MODE_AG) {
     if (threadIdx.x == 0) {
       s_q = ld_relaxed_gpu(fa.f.local + F_SEQ) + 1;
@@ -879,7 +897,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
         if (prev == (unsigned long long)fa.tiles_per_chunk - 1) {
           fa.f.local[F_TILECNT + chunk] = 0;
           __threadfence_system();
-          st_release_sys(fa.f.peer[chunk] + F_CHUNK + fa.f.me, q);
+          st_release_sys(fa.f.peer[chunk] + (fa.rs_defer ? F_PUSHED : F_CHUNK) + fa.f.me, q);
         }
       }
       if (++as == 2) {
@@ -900,16 +918,124 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
   }
 
   if (MODE == MODE_RS) {
-    // ===== tail: reduce my rows from the n receive slots (all local), rank order =====
-    if (threadIdx.x < fa.f.n)
-      spin_wait_sys(fa.f.local + F_CHUNK + threadIdx.x, q, fa.f.timeout_ns, fa.f.local + F_ERR);
-    __syncthreads();
-    const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const uint64_t nthr = (uint64_t)gridDim.x * blockDim.x;
-    if (fa.rs_out_dtype == EDB_F32) rs_tail_reduce<float>(fa, tid, nthr);
-    else rs_tail_reduce<__nv_bfloat16>(fa, tid, nthr);
+    if (fa.rs_defer) {
+      if (blockIdx.x == 0 && threadIdx.x == 0) fa.rs_state[0] = q;  // read by k_rs_finish (later kernel)
+    } else {
+      // ===== tail: reduce my rows from the n receive slots (all local), rank order =====
+      if (threadIdx.x < fa.f.n)
+        spin_wait_sys(fa.f.local + F_CHUNK + threadIdx.x, q, fa.f.timeout_ns, fa.f.local + F_ERR);
+      __syncthreads();
+      const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+      const uint64_t nthr = (uint64_t)gridDim.x * blockDim.x;
+      if (fa.rs_out_dtype == EDB_F32) rs_tail_reduce<float>(fa, tid, nthr);
+      else rs_tail_reduce<__nv_bfloat16>(fa, tid, nthr);
+    }
     finish_op(fa.f, q, &s_last, gridDim.x);
   }
+}
+
+// ---- deferred reduce-scatter: reduce the receive slots of many pushed GEMMs in one launch -----------
+constexpr int kRsMaxItems = 160;
+constexpr int kRsFinishThreads = 256;
+constexpr int64_t kRsFinishChunkVecs = 4096;  // 64 KiB of bf16 per slot and work unit
+
+struct RsFinishItem {
+  const char* recv;     // n slots of chunk_bytes (local)
+  void* dst;            // [chunk_bytes / 2] elements of out_dtype
+  int64_t chunk_bytes;
+  uint64_t* state;      // [0] op number of the push, [1] op number of this reduction
+};
+struct RsFinishDesc {
+  FlagCtx f;
+  int n_items;
+  float scale;
+  int out_dtype;
+  int first_unit[kRsMaxItems + 1];
+  RsFinishItem it[kRsMaxItems];
+};
+
+__global__ void __launch_bounds__(kRsFinishThreads)
+    k_rs_finish(const __grid_constant__ RsFinishDesc d) {
+  __shared__ uint64_t s_q;
+  __shared__ unsigned long long s_need;
+  __shared__ int s_last;
+  if (threadIdx.x == 0) {
+    s_q = ld_relaxed_gpu(d.f.local + F_SEQ) + 1;
+    s_need = 0;
+  }
+  __syncthreads();
+  // every source must have landed its tiles of the latest push among the items (flags are
+  // monotonic and a source's pushes complete in stream order, so the latest covers the earlier)
+  unsigned long long need = 0;
+  for (int i = threadIdx.x; i < d.n_items; i += blockDim.x) {
+    const unsigned long long e = ld_relaxed_gpu(d.it[i].state);
+    need = e > need ? e : need;
+  }
+  if (need) atomicMax(&s_need, need);
+  __syncthreads();
+  if ((int)threadIdx.x < d.f.n)
+    spin_wait_sys(d.f.local + F_PUSHED + threadIdx.x, s_need, d.f.timeout_ns, d.f.local + F_ERR);
+  __syncthreads();
+  const uint64_t q = s_q;
+  const int total_units = d.first_unit[d.n_items];
+  const int n = d.f.n;
+  for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
+    int lo = 0, hi = d.n_items;
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (d.first_unit[mid] <= u) lo = mid;
+      else hi = mid;
+    }
+    const RsFinishItem& it = d.it[lo];
+    const int64_t nvec = it.chunk_bytes / 16;
+    const int64_t v0 = (int64_t)(u - d.first_unit[lo]) * kRsFinishChunkVecs;
+    const int64_t v1 = v0 + kRsFinishChunkVecs < nvec ? v0 + kRsFinishChunkVecs : nvec;
+    constexpr int U = 2;
+    for (int64_t i0 = v0 + threadIdx.x; i0 < v1; i0 += U * kRsFinishThreads) {
+      uint4 raw[U][kMaxGroup];
+#pragma unroll
+      for (int uu = 0; uu < U; ++uu) {
+        const int64_t i = i0 + uu * kRsFinishThreads;
+        if (i < v1) {
+#pragma unroll
+          for (int sidx = 0; sidx < kMaxGroup; ++sidx)
+            if (sidx < n)
+              raw[uu][sidx] = *reinterpret_cast<const uint4*>(it.recv + (int64_t)sidx * it.chunk_bytes + i * 16);
+        }
+      }
+#pragma unroll
+      for (int uu = 0; uu < U; ++uu) {
+        const int64_t i = i0 + uu * kRsFinishThreads;
+        if (i >= v1) break;
+        float acc[8];
+#pragma unroll
+        for (int sidx = 0; sidx < kMaxGroup; ++sidx) {
+          if (sidx < n) {
+            const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw[uu][sidx]);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float2 v = __bfloat1622float2(h[e]);
+              if (sidx == 0) {
+                acc[2 * e] = v.x;
+                acc[2 * e + 1] = v.y;
+              } else {
+                acc[2 * e] += v.x;
+                acc[2 * e + 1] += v.y;
+              }
+            }
+          }
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] *= d.scale;
+        if (d.out_dtype == EDB_F32) rs_store<float>(static_cast<float*>(it.dst), i, acc);
+        else rs_store<__nv_bfloat16>(static_cast<__nv_bfloat16*>(it.dst), i, acc);
+      }
+    }
+  }
+  // remember which op reduced these slots (the next pushes check the owners' DONE against it)
+  if (blockIdx.x == 0)
+    for (int i = threadIdx.x; i < d.n_items; i += blockDim.x) d.it[i].state[1] = q;
+  finish_op(d.f, q, &s_last, gridDim.x);
 }
 
 // out[r, c] = bf16( sum_s partial[s][r][c] (s ascending) + bias[c] ): the second half of a split-K GEMM
@@ -1264,9 +1390,78 @@ int edb_ag_gemm_bf16(int gid, void* C, const void* A, const void* bias, uint64_t
                                 (cudaStream_t)stream);
 }
 
+static int gemm_rs_impl(int gid, void* dst, uint64_t recv_off, uint64_t state_off, bool defer,
+                        const void* A, const void* B, int64_t M, int64_t N, int64_t K, int64_t lda,
+                        int64_t ldb, int a_kmajor, int b_kmajor, float post_scale, int out_dtype,
+                        void* stream);
+
 int edb_gemm_rs_bf16(int gid, void* dst, uint64_t recv_off, const void* A, const void* B,
                      int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb, int a_kmajor,
                      int b_kmajor, float post_scale, int out_dtype, void* stream) {
+  return gemm_rs_impl(gid, dst, recv_off, 0, false, A, B, M, N, K, lda, ldb, a_kmajor, b_kmajor,
+                      post_scale, out_dtype, stream);
+}
+
+int edb_gemm_rs_push_bf16(int gid, uint64_t recv_off, uint64_t state_off, const void* A,
+                          const void* B, int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb,
+                          int a_kmajor, int b_kmajor, void* stream) {
+  Runtime& r = rt();
+  if (!r.inited) return set_error(EDB_E_STATE, "runtime not initialised (call edb_init)");
+  if (state_off < kUserOffset || state_off + 16 > r.heap_bytes || (state_off & 15))
+    return set_error(EDB_E_INVALID, "edb_gemm_rs_push_bf16: bad state offset");
+  return gemm_rs_impl(gid, nullptr, recv_off, state_off, true, A, B, M, N, K, lda, ldb, a_kmajor,
+                      b_kmajor, 1.0f, EDB_BF16, stream);
+}
+
+int edb_rs_finish(int gid, int n_items, void* const* dsts, const uint64_t* recv_offs,
+                  const uint64_t* state_offs, const int64_t* chunk_bytes, float post_scale,
+                  int out_dtype, void* stream) {
+  if (n_items <= 0) return EDB_OK;
+  if (out_dtype != EDB_BF16 && out_dtype != EDB_F32)
+    return set_error(EDB_E_UNSUPPORTED, "edb_rs_finish: out dtype must be bf16 or f32");
+  Runtime& r = rt();
+  cudaStream_t st = (cudaStream_t)stream;
+  int done = 0;
+  while (done < n_items) {
+    RsFinishDesc d;
+    int rc = fill_flagctx(&d.f, gid);
+    if (rc) return rc;
+    const int n = d.f.n;
+    d.scale = post_scale;
+    d.out_dtype = out_dtype;
+    d.first_unit[0] = 0;
+    int k = 0;
+    int64_t units = 0;
+    for (; done < n_items && k < kRsMaxItems; ++done, ++k) {
+      const int64_t cb = chunk_bytes[done];
+      if (cb <= 0 || (cb & 15) || ((uintptr_t)dsts[done] & 15))
+        return set_error(EDB_E_INVALID, "edb_rs_finish: item %d: chunk bytes / dst alignment", done);
+      if (recv_offs[done] < kUserOffset || recv_offs[done] + (uint64_t)cb * n > r.heap_bytes ||
+          (recv_offs[done] & 15) || state_offs[done] < kUserOffset ||
+          state_offs[done] + 16 > r.heap_bytes || (state_offs[done] & 15))
+        return set_error(EDB_E_INVALID, "edb_rs_finish: item %d: bad symmetric offset", done);
+      d.it[k].recv = r.heap + recv_offs[done];
+      d.it[k].dst = dsts[done];
+      d.it[k].chunk_bytes = cb;
+      d.it[k].state = reinterpret_cast<uint64_t*>(r.heap + state_offs[done]);
+      units += (cb / 16 + kRsFinishChunkVecs - 1) / kRsFinishChunkVecs;
+      if (units > 0x7fffffffLL) return set_error(EDB_E_UNSUPPORTED, "edb_rs_finish: too much work");
+      d.first_unit[k + 1] = (int)units;
+    }
+    d.n_items = k;
+    int grid = (int)(units < 4LL * r.sm_count ? units : 4LL * r.sm_count);
+    k_rs_finish<<<grid, kRsFinishThreads, 0, st>>>(d);
+    count_launch();
+    rc = cuda_check(cudaGetLastError(), "k_rs_finish launch");
+    if (rc) return rc;
+  }
+  return EDB_OK;
+}
+
+static int gemm_rs_impl(int gid, void* dst, uint64_t recv_off, uint64_t state_off, bool defer,
+                        const void* A, const void* B, int64_t M, int64_t N, int64_t K, int64_t lda,
+                        int64_t ldb, int a_kmajor, int b_kmajor, float post_scale, int out_dtype,
+                        void* stream) {
   FusedArgs fa;
   memset(&fa, 0, sizeof(fa));
   int rc = fill_flagctx(&fa.f, gid);
@@ -1323,9 +1518,13 @@ int edb_gemm_rs_bf16(int gid, void* dst, uint64_t recv_off, const void* A, const
   fa.rs_scale = post_scale;
   fa.rs_out_dtype = out_dtype;
   fa.tiles_per_chunk = (p.m_tiles / n) * p.n_tiles;
-  // always a full grid: CTAs without a tile still take part in the tail reduction, which is
-  // latency-bound when only a few CTAs read the receive slots (small weight gradients)
-  const int grid = sms;
+  fa.rs_defer = defer ? 1 : 0;
+  fa.rs_state = defer ? reinterpret_cast<uint64_t*>(r.heap + state_off) : nullptr;
+  // fused tail: always a full grid — CTAs without a tile still take part in the tail reduction,
+  // which is latency-bound when only a few CTAs read the receive slots (small weight gradients);
+  // push-only: one CTA per tile
+  const int tiles = p.m_tiles * p.n_tiles;
+  const int grid = defer ? (tiles < sms ? tiles : sms) : sms;
   return dispatch_gemm<MODE_RS>(bn, a_kmajor != 0, b_kmajor != 0, ta, tb, tc, p, fa, cm, grid,
                                 (cudaStream_t)stream);
 }

@@ -235,14 +235,20 @@ __device__ __forceinline__ uint64_t begin_op(const FlagCtx& f, uint64_t* s_q) {
 // `flag_base + me` of every member's flag block (its own included).
 __device__ __forceinline__ void grid_signal(const FlagCtx& f, int cnt_word, int flag_base,
                                             uint64_t q, int* s_last, unsigned n_ctas) {
-  __threadfence_system();
+  // One fence per CTA, not per thread: bar.sync orders every thread's writes before thread 0's
+  // system-scope fence (PTX causality order is cumulative through barriers; this is the pattern of
+  // a cooperative-groups grid sync).  A membar.sys in all 256 threads of every CTA cost several
+  // microseconds per op.
   __syncthreads();
   if (threadIdx.x == 0) {
+    __threadfence_system();
     const unsigned long long prev =
         atomicAdd(reinterpret_cast<unsigned long long*>(f.local + cnt_word), 1ULL);
     const int last = (prev == (unsigned long long)n_ctas - 1);
-    if (last) f.local[cnt_word] = 0;
-    __threadfence_system();
+    if (last) {
+      f.local[cnt_word] = 0;
+      __threadfence_system();  // acquire side: the other CTAs' fenced writes precede the flag
+    }
     *s_last = last;
   }
   __syncthreads();
@@ -256,14 +262,16 @@ __device__ __forceinline__ void wait_flag(const FlagCtx& f, int flag_base, int p
 
 __device__ __forceinline__ void finish_op(const FlagCtx& f, uint64_t q, int* s_last,
                                           unsigned n_ctas) {
-  __threadfence_system();
   __syncthreads();
   if (threadIdx.x == 0) {
+    __threadfence_system();  // covers the whole CTA's writes (see grid_signal)
     const unsigned long long prev =
         atomicAdd(reinterpret_cast<unsigned long long*>(f.local + F_CNT_B), 1ULL);
     const int last = (prev == (unsigned long long)n_ctas - 1);
-    if (last) f.local[F_CNT_B] = 0;
-    __threadfence_system();
+    if (last) {
+      f.local[F_CNT_B] = 0;
+      __threadfence_system();
+    }
     *s_last = last;
   }
   __syncthreads();

@@ -566,15 +566,31 @@ def fuse_cross_entropy(gm):
 def fuse_optimizer_updates(gm):
     """The re-inplaced update of torch.optim.SGD(momentum, foreach=True),
         _foreach_mul_(bufs, mu); _foreach_add_(bufs, grads[, alpha=a]); _foreach_add_(params, bufs, alpha=-lr)
-    (three adjacent nodes), becomes one `optim.sgd_momentum_` node = one multi-tensor kernel pass.
+    (three consecutive foreach nodes), becomes one `optim.sgd_momentum_` node = one multi-tensor kernel pass.
     Returns the number of triples fused."""
     from . import optim
     graph = gm.graph
     n = 0
     for mul in [x for x in graph.nodes if x.op == "call_function" and x.target == aten._foreach_mul_.Scalar]:
-        add1, add2 = mul.next, mul.next.next
-        if not (add1.op == "call_function" and add1.target == aten._foreach_add_.List
-                and add2.op == "call_function" and add2.target == aten._foreach_add_.List):
+        # the next two in-place foreach nodes; nodes in between are allowed as long as they do not
+        # touch the tensors being updated (zero2/zero3 graphs flatten gradients there)
+        def next_foreach(start):
+            skipped = []
+            nd = start.next
+            while nd.op == "call_function" and nd.target != aten._foreach_add_.List:
+                if "_foreach_" in str(nd.target):
+                    return None, skipped
+                skipped.append(nd)
+                nd = nd.next
+            return (nd if nd.op == "call_function" else None), skipped
+
+        add1, skip1 = next_foreach(mul)
+        add2, skip2 = next_foreach(add1) if add1 is not None else (None, [])
+        if add1 is None or add2 is None:
+            continue
+        touched = {a for a in pytree.tree_flatten((mul.args[0], add2.args[0]))[0] if isinstance(a, Node)}
+        if any(isinstance(a, Node) and a in touched
+               for nd in skip1 + skip2 for a in pytree.tree_flatten((nd.args, nd.kwargs))[0]):
             continue
         if mul.kwargs or set(add1.kwargs) - {"alpha"} or set(add2.kwargs) - {"alpha"}:
             continue
@@ -593,7 +609,7 @@ def fuse_optimizer_updates(gm):
         ga, nlr = add1.kwargs.get("alpha", 1), add2.kwargs.get("alpha", 1)
         if not isinstance(ga, (int, float)) or not isinstance(nlr, (int, float)):
             continue
-        with graph.inserting_before(mul):
+        with graph.inserting_before(add2):
             graph.call_function(optim.sgd_momentum_, (list(params), list(grads), list(bufs), mu, ga, nlr))
         for d in (add2, add1, mul):
             graph.erase_node(d)
@@ -711,6 +727,11 @@ def fuse_collective_gemms(gm, io, rt, ranks, ops=_default_ops):
         n_ag += 1
 
     # ---- GEMM + reduce-scatter -------------------------------------------------------------
+    # deferred form (EDB_DEFER_RS=1): the GEMM only pushes its tiles to the owners; one rs_finish
+    # node in front of the first consumer reduces every weight gradient's slots in a single kernel
+    import os
+    defer = os.environ.get("EDB_DEFER_RS", "0") == "1" and hasattr(ops, "mm_rs_push")
+    pushed = []  # (token node, recv buffer, state buffer, shard numel, rs_end node)
     for rs_s in [x for x in graph.nodes if x.op == "call_function" and x.target is ops.reduce_scatter_start]:
         f = rs_s.args[0]
         if rs_s.args[1] != "avg" or rs_s.args[2] != 0 or rs_s.kwargs:
@@ -750,12 +771,52 @@ def fuse_collective_gemms(gm, io, rt, ranks, ops=_default_ops):
                     nd.meta["val"] = src.t()
             else:
                 a, b = a0, b0
-            fused = graph.call_function(ops.mm_rs, args=(a, b, list(ranks)),
-                                        kwargs={"_buf": (recv.offset,), "_scale": 1.0 / n})
-        rs_e.replace_all_uses_with(fused)
-        for dead in [rs_e, rs_s, f] + t_chain + [mm_node]:
-            graph.erase_node(dead)
+            if defer:
+                state = rt.alloc(16, align=16)
+                state.tensor(torch.int64, (2,)).zero_()
+                tok = graph.call_function(ops.mm_rs_push, args=(a, b, list(ranks)),
+                                          kwargs={"_buf": (recv.offset, state.offset)})
+                pushed.append((tok, recv, state, M // n * N, rs_e))
+                fused = None
+            else:
+                fused = graph.call_function(ops.mm_rs, args=(a, b, list(ranks)),
+                                            kwargs={"_buf": (recv.offset,), "_scale": 1.0 / n})
+        if fused is not None:
+            rs_e.replace_all_uses_with(fused)
+            for dead in [rs_e, rs_s, f] + t_chain + [mm_node]:
+                graph.erase_node(dead)
+        else:
+            # rs_e stays until rs_finish replaces it below; its producers go now
+            rs_e.args = (pushed[-1][0],) + tuple(rs_e.args[1:])
+            for dead in [rs_s, f] + t_chain + [mm_node]:
+                graph.erase_node(dead)
         n_rs += 1
+    if pushed:
+        order = {nd: i for i, nd in enumerate(graph.nodes)}
+
+        def first_use_of(items):
+            return min((u for *_, rs_e in items for u in rs_e.users), key=lambda u: order[u])
+
+        # one rs_finish per run of pushes that all precede the run's first consumer (a single one
+        # for a train step whose gradients are only read by the optimizer)
+        groups, cur = [], []
+        for it in pushed:
+            if cur and order[it[0]] > order[first_use_of(cur)]:
+                groups.append(cur)
+                cur = []
+            cur.append(it)
+        groups.append(cur)
+        for items in groups:
+            with graph.inserting_before(first_use_of(items)):
+                fin = graph.call_function(
+                    ops.rs_finish, args=([it[0] for it in items], list(ranks)),
+                    kwargs={"_bufs": [(it[1].offset, it[2].offset) for it in items],
+                            "_numels": [it[3] for it in items], "_scale": 1.0 / n})
+                for i, (tok, recv, state, numel, rs_e) in enumerate(items):
+                    gi = graph.call_function(operator.getitem, args=(fin, i))
+                    gi.meta = dict(rs_e.meta)
+                    rs_e.replace_all_uses_with(gi)
+                    graph.erase_node(rs_e)
 
     # peers read parameter shards in place: keep the optimizer from overwriting them too early
     if rehomed:

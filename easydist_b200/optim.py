@@ -32,38 +32,48 @@ def _ptr_array(tensors):
     return (ctypes.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
 
 
-def _native_ok(params, grads, bufs):
-    if not params or len(params) != len(grads) or len(params) != len(bufs):
+def _tensor_ok(p, g, m, dt):
+    if isinstance(p, FakeTensor) or not p.is_cuda:
         return False
-    dt = params[0].dtype
-    if dt not in _DT:
+    if not (p.dtype == g.dtype == m.dtype == dt and p.shape == g.shape == m.shape):
         return False
-    for p, g, m in zip(params, grads, bufs):
-        if isinstance(p, FakeTensor) or not p.is_cuda:
-            return False
-        if not (p.dtype == g.dtype == m.dtype == dt and p.shape == g.shape == m.shape):
-            return False
-        if not (p.is_contiguous() and g.is_contiguous() and m.is_contiguous()):
-            return False
-        if (p.data_ptr() | g.data_ptr() | m.data_ptr()) & 15:
-            return False
-    return True
+    if not (p.is_contiguous() and g.is_contiguous() and m.is_contiguous()):
+        return False
+    return not ((p.data_ptr() | g.data_ptr() | m.data_ptr()) & 15)
+
+
+def _aten(params, grads, bufs, mu, grad_alpha, neg_lr):
+    aten._foreach_mul_.Scalar(bufs, mu)
+    aten._foreach_add_.List(bufs, grads, alpha=grad_alpha)
+    aten._foreach_add_.List(params, bufs, alpha=neg_lr)
 
 
 @has_side_effect
 def sgd_momentum_(params, grads, bufs, mu, grad_alpha, neg_lr):
-    """In place: bufs = mu*bufs + grad_alpha*grads; params += neg_lr*bufs (per tensor)."""
-    if not _native_ok(params, grads, bufs):
-        if params and not isinstance(params[0], FakeTensor):
-            _stats["aten_sgd"] += 1
-        aten._foreach_mul_.Scalar(bufs, mu)
-        aten._foreach_add_.List(bufs, grads, alpha=grad_alpha)
-        aten._foreach_add_.List(params, bufs, alpha=neg_lr)
-        return None
-    lib = _lib.load()
-    stream = torch.cuda.current_stream(params[0].device).cuda_stream
-    check(lib.edb_sgd_momentum(len(params), _ptr_array(params), _ptr_array(grads), _ptr_array(bufs),
-                               i64_array([p.numel() for p in params]), float(mu), float(grad_alpha),
-                               float(neg_lr), _DT[params[0].dtype], stream))
-    _stats["edb_sgd"] += 1
+    """In place: bufs = mu*bufs + grad_alpha*grads; params += neg_lr*bufs (per tensor).  Tensors the
+    kernel's contract does not cover (other dtypes, views that are not 16-byte aligned, e.g. slices
+    of a gradient bucket) take the three ATen ops; both groups are counted."""
+    if not params or len(params) != len(grads) or len(params) != len(bufs):
+        raise ValueError("sgd_momentum_: params, grads and bufs must be lists of equal length")
+    if isinstance(params[0], FakeTensor):
+        return _aten(params, grads, bufs, mu, grad_alpha, neg_lr)
+    native = {}
+    rest = []
+    for i, (p, g, m) in enumerate(zip(params, grads, bufs)):
+        if p.dtype in _DT and _tensor_ok(p, g, m, p.dtype):
+            native.setdefault(p.dtype, []).append(i)
+        else:
+            rest.append(i)
+    if rest:
+        _stats["aten_sgd"] += 1
+        _aten([params[i] for i in rest], [grads[i] for i in rest], [bufs[i] for i in rest], mu,
+              grad_alpha, neg_lr)
+    for dt, idx in native.items():
+        lib = _lib.load()
+        ps, gs, ms = [params[i] for i in idx], [grads[i] for i in idx], [bufs[i] for i in idx]
+        stream = torch.cuda.current_stream(ps[0].device).cuda_stream
+        check(lib.edb_sgd_momentum(len(ps), _ptr_array(ps), _ptr_array(gs), _ptr_array(ms),
+                                   i64_array([p.numel() for p in ps]), float(mu), float(grad_alpha),
+                                   float(neg_lr), _DT[dt], stream))
+        _stats["edb_sgd"] += 1
     return None

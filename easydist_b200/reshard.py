@@ -19,6 +19,8 @@ that FX meta propagation works, mirroring how the reference's passes call these 
 from ctypes import byref, c_int64
 from typing import List
 
+import ctypes
+
 import torch
 from torch._subclasses.fake_tensor import FakeTensor
 
@@ -393,7 +395,49 @@ def mm_rs(a, b, group, *, _buf, _scale=1.0, _out_dtype=None):
     return out
 
 
+def mm_rs_push(a, b, group, *, _buf):
+    """Deferred half of mm_rs: computes a @ b and pushes every tile into its owner's receive slot
+    (no waiting, no reduction).  _buf = (symmetric offset of the n receive slots, symmetric offset
+    of 16 zeroed state bytes), both private to this GEMM.  Returns an empty token that `rs_finish`
+    takes so that the graph keeps the order."""
+    if _is_fake(a):
+        return a.new_empty((0,))
+    _require_cuda(a, "mm_rs_push")
+    from . import gemm as _gemm
+    rt, gid, n, me = _group(group)
+    M, K = a.shape
+    N = b.shape[1]
+    pa, pb = _gemm._prepare(a, 1), _gemm._prepare(b, 0)
+    if pa is None or pb is None:
+        raise _lib.EdbUnsupported(_lib.EDB_E_UNSUPPORTED, "mm_rs_push: operand layout")
+    (ta, a_k, lda), (tb, b_k, ldb) = pa, pb
+    check(rt.lib.edb_gemm_rs_push_bf16(gid, int(_buf[0]), int(_buf[1]), ta.data_ptr(), tb.data_ptr(),
+                                       M, N, K, lda, ldb, 1 if a_k else 0, 1 if b_k else 0,
+                                       rt.stream()))
+    return torch.empty((0,), dtype=a.dtype, device=a.device)
+
+
+def rs_finish(tokens, group, *, _bufs, _numels, _scale=1.0, _out_dtype=None):
+    """Reduce the receive slots of the pushed GEMMs `tokens` came from, all in one kernel:
+    item i -> flat shard of _numels[i] elements = sum over ranks (rank order, fp32) * _scale.
+    _bufs[i] = the (_buf) pair given to mm_rs_push i."""
+    out_dtype = _out_dtype or torch.bfloat16
+    if tokens and _is_fake(tokens[0]):
+        return [tokens[0].new_empty((int(k),), dtype=out_dtype) for k in _numels]
+    rt, gid, n, me = _group(group)
+    dev = tokens[0].device
+    outs = [torch.empty((int(k),), dtype=out_dtype, device=dev) for k in _numels]
+    cnt = len(outs)
+    dsts = (ctypes.c_void_p * cnt)(*[o.data_ptr() for o in outs])
+    recv = (ctypes.c_uint64 * cnt)(*[int(b[0]) for b in _bufs])
+    state = (ctypes.c_uint64 * cnt)(*[int(b[1]) for b in _bufs])
+    chunk = (ctypes.c_int64 * cnt)(*[int(k) * 2 for k in _numels])  # slots hold bf16
+    check(rt.lib.edb_rs_finish(gid, cnt, dsts, recv, state, chunk, float(_scale),
+                               _TORCH_DTYPE_CODE[out_dtype], rt.stream()))
+    return outs
+
+
 COMM_FUNCS = [all_reduce_start, all_gather_start, reduce_scatter_start, all_to_all_start]
 COMM_SYNC_FUNCS = [all_reduce_end, all_gather_end, reduce_scatter_end, all_to_all_end]
 CUSTOM_FUNCS = COMM_FUNCS + COMM_SYNC_FUNCS + [scatter_wrapper, copy_wrapper]
-FUSED_FUNCS = [ag_mm, mm_rs, symm_guard]
+FUSED_FUNCS = [ag_mm, mm_rs, mm_rs_push, rs_finish, symm_guard]

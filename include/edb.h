@@ -185,6 +185,23 @@ int edb_gemm_rs_bf16(int gid, void* dst, uint64_t c_stage_off, const void* A, co
                      int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb, int a_kmajor,
                      int b_kmajor, float post_scale, int out_dtype, void* stream);
 
+/* Deferred form of the fused GEMM + reduce-scatter (weight gradients of zero2/zero3: the reduced
+ * shard is only needed by the optimizer at the end of the step).  `edb_gemm_rs_push_bf16` computes
+ * C = A.B and TMA-stores every tile into the owner's receive slot [me] (symmetric `recv_off`, n
+ * slots of (M/n)*N*2 bytes, dedicated to this GEMM) without waiting for anybody: no lockstep with
+ * the peers and no tail.  `state_off`: 16 zero-initialised symmetric bytes private to this GEMM
+ * (word 0: op number of the push, word 1: op number of the last reduction — the push checks the
+ * owners' DONE flags against it, which guards the slots across steps).  `edb_rs_finish` reduces the
+ * slots of n_items such GEMMs in ONE launch (rank order, fp32, scale, cast; host arrays of
+ * per-item destinations, offsets and slot sizes), waiting once for every source's latest push.
+ * Result identical to edb_gemm_rs_bf16. */
+int edb_gemm_rs_push_bf16(int gid, uint64_t recv_off, uint64_t state_off, const void* A,
+                          const void* B, int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb,
+                          int a_kmajor, int b_kmajor, void* stream);
+int edb_rs_finish(int gid, int n_items, void* const* dsts, const uint64_t* recv_offs,
+                  const uint64_t* state_offs, const int64_t* chunk_bytes, float post_scale,
+                  int out_dtype, void* stream);
+
 /* LayerNorm over the last dimension — aten.native_layer_norm / native_layer_norm_backward nodes of
  * the sharded graph (SURVEY.md App. B lists 8+8 per step in config 1).  x, y, dy, dx: [rows, H]
  * contiguous, dtype bf16 or f32 (w, b, dw, db: [H], same dtype; b/dw/db may be NULL);

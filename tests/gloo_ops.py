@@ -142,6 +142,25 @@ def mm_rs(a, b, group, *, _buf=None, _scale=1.0, _out_dtype=None):
     return out.to(_out_dtype or a.dtype)
 
 
+def mm_rs_push(a, b, group, *, _buf=None):
+    """CPU stand-in of reshard.mm_rs_push: the 'token' carries the partial product itself."""
+    if _fake(a):
+        return a.new_empty((a.shape[0], b.shape[1]))
+    return a @ b
+
+
+def rs_finish(tokens, group, *, _bufs=None, _numels=None, _scale=1.0, _out_dtype=None):
+    n = len(group)
+    if tokens and _fake(tokens[0]):
+        return [t.new_empty((int(k),), dtype=_out_dtype or t.dtype) for t, k in zip(tokens, _numels)]
+    me = list(group).index(dist.get_rank())
+    outs = []
+    for t in tokens:
+        red = all_reduce_start(t.flatten(), "sum", group)
+        outs.append((torch.chunk(red, n, 0)[me].contiguous() * _scale).to(_out_dtype or t.dtype))
+    return outs
+
+
 def box_exchange(tensor, dst_shape, boxes, peer_src_shapes, group, *, _buf=None):
     """Partition P2P redistribution over gloo: every member publishes its source partition, each
     rank copies the boxes it needs (semantics of reshard.box_exchange / sharding.py:427-474)."""
@@ -183,7 +202,7 @@ class FakeSymmRuntime:
         return FakeSymmRuntime._Buf(off, nbytes)
 
 
-FUSED_FUNCS = [ag_mm, mm_rs, symm_guard]
+FUSED_FUNCS = [ag_mm, mm_rs, mm_rs_push, rs_finish, symm_guard]
 COMM_FUNCS = [all_reduce_start, all_gather_start, reduce_scatter_start, all_to_all_start]
 COMM_SYNC_FUNCS = [all_reduce_end, all_gather_end, reduce_scatter_end, all_to_all_end]
 CUSTOM_FUNCS = COMM_FUNCS + COMM_SYNC_FUNCS + [scatter_wrapper, copy_wrapper]

@@ -182,6 +182,19 @@ def run_fused(rank, world, group):
     from easydist_b200 import gemm
     rt = runtime.get_runtime()
     n_ok = 0
+    # the unfused references below must accumulate in the same order as the fused kernels, which
+    # never split K
+    rt.set_option("gemm_splitk", 0)
+    try:
+        n_ok += _run_fused_cases(rank, world, group, rt, gemm)
+    finally:
+        rt.set_option("gemm_splitk", 1)
+    n_ok += run_deferred_rs(rank, world, group)
+    return n_ok
+
+
+def _run_fused_cases(rank, world, group, rt, gemm):
+    n_ok = 0
     torch.manual_seed(1234)  # same on every rank: every rank knows every shard
     for (M, N, K, with_bias) in [(512, 256 * world, 256, False), (4096, 1024, 1024, True),
                                  (384, 128 * world, 1000 // 8 * 8, False), (4096, 4096, 1024, True)]:
@@ -227,6 +240,58 @@ def run_fused(rank, world, group):
     return n_ok
 
 
+def run_deferred_rs(rank, world, group):
+    """Deferred GEMM+RS (mm_rs_push x k, other ops in between, then ONE rs_finish) vs mm_rs: bit
+    exact, over several steps (the cross-step slot guard) and from a replayed CUDA graph."""
+    from easydist_b200 import gemm
+    rt = runtime.get_runtime()
+    shapes = [(M, N, K) for (M, N, K) in [(128 * world, 256, 512), (1024, 1024, 4096),
+                                          (1024, 4096, 4096), (256 * world, 3072, 1024)]
+              if (M // world) % 128 == 0]
+    g = torch.Generator(device="cuda").manual_seed(99)
+    data = []
+    for (M, N, K) in shapes:
+        a_all = [torch.randn(K, M, device="cuda", generator=g).bfloat16() for _ in range(world)]
+        b_all = [torch.randn(K, N, device="cuda", generator=g).bfloat16() for _ in range(world)]
+        recv, recv2 = rt.alloc(M * N * 2, align=1024), rt.alloc(M * N * 2, align=1024)
+        state = rt.alloc(16, align=16)
+        state.tensor(torch.int64, (2,)).zero_()
+        data.append((a_all[rank], b_all[rank].clone(), recv, recv2, state))
+    scale_in = torch.ones((), device="cuda", dtype=torch.bfloat16)
+
+    def step():
+        toks, wants = [], []
+        for (M, N, K), (a_t, b, recv, recv2, state) in zip(shapes, data):
+            bb = b * scale_in  # new values every step, same addresses under graph replay
+            toks.append(reshard.mm_rs_push(a_t.t(), bb, group, _buf=(recv.offset, state.offset)))
+            wants.append(reshard.mm_rs(a_t.t(), bb, group, _buf=(recv2.offset,), _scale=1.0 / world))
+        outs = reshard.rs_finish(toks, group, _bufs=[(d[2].offset, d[4].offset) for d in data],
+                                 _numels=[M // world * N for (M, N, K) in shapes], _scale=1.0 / world)
+        return outs, wants
+
+    n_ok = 0
+    for it in range(3):
+        scale_in.fill_(float(it + 1))
+        outs, wants = step()
+        torch.cuda.synchronize()
+        for o, w, shp in zip(outs, wants, shapes):
+            assert torch.equal(o, w), f"deferred rs mismatch {shp} it {it}: " \
+                f"{(o.float() - w.float()).abs().max()}"
+            n_ok += 1
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        outs, wants = step()
+    for it in range(4):
+        scale_in.fill_(float(2 * it + 1))
+        graph.replay()
+        torch.cuda.synchronize()
+        for o, w, shp in zip(outs, wants, shapes):
+            assert torch.equal(o, w), f"deferred rs (graph) mismatch {shp} replay {it}"
+            n_ok += 1
+    assert not any(rt.error_flags()), rt.error_flags()
+    return n_ok
+
+
 def bench_fused(rank, world, group):
     from easydist_b200 import gemm
     rt = runtime.get_runtime()
@@ -252,6 +317,15 @@ def bench_fused(rank, world, group):
         dy = torch.randn(M, N, device="cuda").bfloat16()
         recv, stage = rt.alloc(N * K * 2, align=1024), rt.alloc(N * K * 2, align=1024)
         t_rs_f = timeit(lambda: reshard.mm_rs(dy.t(), x, group, _buf=(recv.offset,), _scale=1.0 / world))
+        st8 = rt.alloc(16, align=16)
+        st8.tensor(torch.int64, (2,)).zero_()
+
+        def deferred():
+            tok = reshard.mm_rs_push(dy.t(), x, group, _buf=(recv.offset, st8.offset))
+            return reshard.rs_finish([tok], group, _bufs=[(recv.offset, st8.offset)],
+                                     _numels=[N // world * K], _scale=1.0 / world)
+        t_rs_d = timeit(deferred)
+        t_wg = timeit(lambda: gemm.mm(dy.t(), x))
 
         def unfused_rs():
             part = gemm.mm(dy.t(), x)
@@ -260,8 +334,8 @@ def bench_fused(rank, world, group):
         t_rs_u = timeit(unfused_rs)
         if rank == 0:
             print(f"FUSED M{M} N{N} K{K}: ag+gemm fused {t_fused:.1f}us unfused {t_unf:.1f}us "
-                  f"(gemm alone {t_gemm:.1f}us) | gemm+rs fused {t_rs_f:.1f}us unfused {t_rs_u:.1f}us",
-                  flush=True)
+                  f"(gemm alone {t_gemm:.1f}us) | gemm+rs fused {t_rs_f:.1f}us unfused {t_rs_u:.1f}us "
+                  f"push+finish {t_rs_d:.1f}us (wgrad gemm alone {t_wg:.1f}us)", flush=True)
 
 
 def run_auto_bundle(rank, world):
@@ -365,6 +439,7 @@ def bench(rank, world, group):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--bench", action="store_true")
+    ap.add_argument("--bench-fused", action="store_true", help="only the fused-kernel microbench")
     ap.add_argument("--heap-gb", type=float, default=8.0)
     ap.add_argument("--ll-bytes", type=int, default=-1,
                     help="override the low-latency protocol threshold (0 = off)")
@@ -406,8 +481,9 @@ def main():
     dist.barrier()
     if rank == 0:
         print(f"MGPU_OK world={world} checks={n} launches={rt.launch_count()}", flush=True)
-    if args.bench:
+    if args.bench or args.bench_fused:
         bench_fused(rank, world, group)
+    if args.bench:
         bench(rank, world, group)
     dist.barrier()
     dist.destroy_process_group()

@@ -57,8 +57,9 @@ class Wide(torch.nn.Module):
         return self.fc2(torch.nn.functional.gelu(self.fc1(self.norm(x))))
 
 
-def _fusion_worker(rank, world, port, q):
+def _fusion_worker(rank, world, port, q, defer="0"):
     os.environ["OMP_NUM_THREADS"] = "1"
+    os.environ["EDB_DEFER_RS"] = defer
     torch.set_num_threads(1)
     dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank,
                             world_size=world)
@@ -93,13 +94,16 @@ def _fusion_worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
-def test_fusion_rewrite_on_cpu():
+@pytest.mark.parametrize("defer", ["0", "1"])
+def test_fusion_rewrite_on_cpu(defer):
     """The AG+GEMM / GEMM+RS peephole (lowering.fuse_collective_gemms) rewrites the zero3 graph of
     a 2-layer MLP: both weights' all-gathers fuse into their forward GEMMs and both weight
-    gradients' reduce-scatters fuse into the wgrad GEMMs; training still matches vanilla."""
+    gradients' reduce-scatters fuse into the wgrad GEMMs (defer=1: push-only GEMMs + one rs_finish
+    in front of the optimizer); training still matches vanilla."""
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_fusion_worker, args=(r, 2, 29871, q)) for r in range(2)]
+    procs = [ctx.Process(target=_fusion_worker, args=(r, 2, 29871 + int(defer), q, defer))
+             for r in range(2)]
     for p in procs:
         p.start()
     for p in procs:
@@ -109,6 +113,11 @@ def test_fusion_rewrite_on_cpu():
     assert ok, msg
     assert info["fused"] == {"ag_mm": 2, "mm_rs": 2}, info
     assert info["comm_nodes"].get("reduce_scatter_start", 0) == 0, info
+    if defer == "1":
+        assert info["comm_nodes"].get("mm_rs_push") == 2 and info["comm_nodes"].get("rs_finish") == 1, info
+        assert "mm_rs" not in info["comm_nodes"], info
+    else:
+        assert info["comm_nodes"].get("mm_rs") == 2, info
 
 
 def _worker(rank, world, port, mode, opt_kind, q, bucket=0):
@@ -131,6 +140,12 @@ def _worker(rank, world, port, mode, opt_kind, q, bucket=0):
     compiled = api._compile_dp(train_step, mode, "fake", (batches[0][rank * 4:(rank + 1) * 4], model,
                                                          opt), {}, ops=gloo_ops, native=False,
                                bucket_numel=bucket)
+    # the optimizer rewrite of the native path (on CPU the fused node takes its ATen branch): the
+    # sharded update of every mode must still match vanilla
+    from easydist_b200 import lowering
+    n_opt = lowering.fuse_optimizer_updates(compiled.graph)
+    # zero2 updates parameter shards out of place (the new shards are all-gathered): no triple
+    assert n_opt == (1 if opt_kind == "sgd" and mode != "zero2" else 0), (mode, opt_kind, n_opt)
     ok = True
     msg = ""
     for b in batches:
