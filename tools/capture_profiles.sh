@@ -18,4 +18,7 @@ timeout 300 ncu --set full --clock-control none --import-source on -k regex:k_ge
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:k_ln_ -s 60 -c 4 \
     -o $O/final_prof_ln python bench.py --steps 1 --warmup 3 --no-cuda-graph --no-cpu-baseline \
     > $O/final_bench_under_ncu3.log 2>&1; echo "ncu_ln=$?"
-ls -la $O | tail -12
+timeout 300 ncu --set full --clock-control none --import-source on -k "regex:k_ce_|k_sgd_momentum|k_splitk_reduce" -s 2 -c 5 \
+    -o $O/final_prof_loss_optim python bench.py --steps 1 --warmup 3 --no-cuda-graph --no-cpu-baseline \
+    > $O/final_bench_under_ncu4.log 2>&1; echo "ncu_loss_optim=$?"
+ls -la $O | tail -14
