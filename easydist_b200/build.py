@@ -17,6 +17,7 @@ INCLUDE = os.path.join(ROOT, "include")
 LIB_PATH = os.path.join(HERE, "libedb.so")
 BUILD_DIR = os.path.join(HERE, "csrc", "_build")
 
+HEADERS = ["edb_internal.cuh", "edb_vec.cuh"]
 SOURCES = ["edb_runtime.cu", "edb_reshard.cu", "edb_ll.cu", "edb_norm.cu", "edb_loss.cu", "edb_optim.cu", "edb_gemm.cu"]
 
 NVCC_FLAGS = [
@@ -50,7 +51,7 @@ def needs_build():
     stamp = os.path.join(BUILD_DIR, "stamp")
     if not os.path.exists(LIB_PATH) or not os.path.exists(stamp):
         return True
-    deps = sources() + [os.path.join(CSRC, "edb_internal.cuh"), os.path.join(INCLUDE, "edb.h")]
+    deps = sources() + [os.path.join(CSRC, h) for h in HEADERS] + [os.path.join(INCLUDE, "edb.h")]
     with open(stamp) as f:
         return f.read().strip() != _digest(deps)
 
@@ -84,7 +85,7 @@ def build(force=False, verbose=False):
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
-    deps = srcs + [os.path.join(CSRC, "edb_internal.cuh"), os.path.join(INCLUDE, "edb.h")]
+    deps = srcs + [os.path.join(CSRC, h) for h in HEADERS] + [os.path.join(INCLUDE, "edb.h")]
     with open(os.path.join(BUILD_DIR, "stamp"), "w") as f:
         f.write(_digest(deps))
     return LIB_PATH

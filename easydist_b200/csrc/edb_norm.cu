@@ -17,50 +17,14 @@
 #include <cuda_bf16.h>
 
 #include "edb_internal.cuh"
+#include "edb_vec.cuh"
 
 namespace edb {
 
 constexpr int kLnWarps = 4;
 constexpr int kLnMaxVec = 16;  // 16-byte vectors per lane: H <= 32*16*EPV
 
-template <typename T> struct LnT;
-template <> struct LnT<float> {
-  static constexpr int EPV = 4;
-  static __device__ __forceinline__ void unpack(const uint4& r, float* f) {
-    f[0] = __uint_as_float(r.x);
-    f[1] = __uint_as_float(r.y);
-    f[2] = __uint_as_float(r.z);
-    f[3] = __uint_as_float(r.w);
-  }
-  static __device__ __forceinline__ uint4 pack(const float* f) {
-    return make_uint4(__float_as_uint(f[0]), __float_as_uint(f[1]), __float_as_uint(f[2]),
-                      __float_as_uint(f[3]));
-  }
-};
-template <> struct LnT<__nv_bfloat16> {
-  static constexpr int EPV = 8;
-  static __device__ __forceinline__ void unpack(const uint4& r, float* f) {
-    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r);
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const float2 v = __bfloat1622float2(h[e]);
-      f[2 * e] = v.x;
-      f[2 * e + 1] = v.y;
-    }
-  }
-  static __device__ __forceinline__ uint4 pack(const float* f) {
-    uint4 o;
-    __nv_bfloat162 h0 = __floats2bfloat162_rn(f[0], f[1]);
-    __nv_bfloat162 h1 = __floats2bfloat162_rn(f[2], f[3]);
-    __nv_bfloat162 h2 = __floats2bfloat162_rn(f[4], f[5]);
-    __nv_bfloat162 h3 = __floats2bfloat162_rn(f[6], f[7]);
-    o.x = *reinterpret_cast<uint32_t*>(&h0);
-    o.y = *reinterpret_cast<uint32_t*>(&h1);
-    o.z = *reinterpret_cast<uint32_t*>(&h2);
-    o.w = *reinterpret_cast<uint32_t*>(&h3);
-    return o;
-  }
-};
+template <typename T> using LnT = VecT<T>;
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
