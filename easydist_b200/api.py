@@ -20,6 +20,8 @@ import logging
 from functools import update_wrapper
 from typing import Any
 
+import os
+
 import torch
 import torch.utils._pytree as pytree
 
@@ -65,6 +67,10 @@ def _finish(gm, params, buffers, named_states, args, kwargs, ops, native, io=Non
     flat = _flat_inputs(params, buffers, named_states, args, kwargs)
     lowering.propagate_local_meta(gm, flat)
     info = {}
+    if os.environ.get("EDB_BUCKET_COMM", "0") == "1":
+        # opt-in: changes the communication structure the reference's lowering would produce
+        info["bucketed"] = lowering.bucket_small_comm(gm, ops)
+        lowering.propagate_local_meta(gm, flat)
     if (native or fuse_rt is not None) and fuse and io is not None and ranks is not None \
             and len(ranks) > 1:
         if fuse_rt is None:

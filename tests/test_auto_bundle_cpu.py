@@ -63,8 +63,9 @@ def run_bundle(rank, world, mesh_shape, ops, native, device):
     return ok, msg, compiled.info["comm_nodes"]
 
 
-def _worker(rank, world, mesh_shape, port, q):
+def _worker(rank, world, mesh_shape, port, q, bucket="0"):
     os.environ["OMP_NUM_THREADS"] = "1"
+    os.environ["EDB_BUCKET_COMM"] = bucket
     torch.set_num_threads(1)
     dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank,
                             world_size=world)
@@ -100,3 +101,26 @@ def test_recorded_reference_plan_lowers_and_matches_vanilla(mesh_shape, port):
                      "all_reduce_start": 5, "all_to_all_start": 2}}[mesh_shape]
     for k, v in want.items():
         assert hist.get(k, 0) == v, (k, hist)
+
+
+@pytest.mark.parametrize("mesh_shape,port", [((2,), 29863), ((2, 2), 29864)])
+def test_bucketed_small_collectives_match_vanilla(mesh_shape, port):
+    """EDB_BUCKET_COMM=1 (lowering.bucket_small_comm, the analogue of the reference's comm_group
+    pass): the same recorded plans with their small all-reduces / dim-0 all-gathers bucketed still
+    reproduce vanilla PyTorch, with fewer collectives."""
+    world = 1
+    for v in mesh_shape:
+        world *= v
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, mesh_shape, port, q, "1")) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(240)
+    assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
+    ok, msg, hist = q.get(timeout=5)
+    assert ok, msg
+    plain = {(2,): (26, 3), (2, 2): (37, 5)}[mesh_shape]
+    assert hist.get("all_gather_start", 0) < plain[0], hist
+    assert hist.get("all_reduce_start", 0) <= plain[1], hist

@@ -120,8 +120,9 @@ def test_fusion_rewrite_on_cpu(defer):
         assert info["comm_nodes"].get("mm_rs") == 2, info
 
 
-def _worker(rank, world, port, mode, opt_kind, q, bucket=0):
+def _worker(rank, world, port, mode, opt_kind, q, bucket=0, generic_bucket="0"):
     os.environ["OMP_NUM_THREADS"] = "1"
+    os.environ["EDB_BUCKET_COMM"] = generic_bucket
     torch.set_num_threads(1)
     dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank,
                             world_size=world)
@@ -201,3 +202,24 @@ def test_dp_modes_match_vanilla(mode, opt_kind, bucket):
     if bucket and mode != "ddp":
         # only the 32x32 weight is sharded; the three small tensors share one all-reduce
         assert hist.get("reduce_scatter_start", 0) == 1 and hist.get("all_reduce_start", 0) == 1
+
+
+@pytest.mark.parametrize("mode", ["ddp", "zero3"])
+def test_generic_comm_bucketing_in_dp_graphs(mode):
+    """EDB_BUCKET_COMM=1 (lowering.bucket_small_comm) on the tensor-by-tensor DP graphs: the four
+    per-parameter collectives of each kind collapse into buckets and training still matches vanilla."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29890 + (mode == "zero3")
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, mode, "sgd", q, 0, "1")) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(180)
+    assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
+    ok, msg, hist = q.get(timeout=5)
+    assert ok, msg
+    if mode == "ddp":
+        assert hist.get("all_reduce_start", 0) == 1, hist   # 4 gradients, one bucket
+    else:
+        assert hist.get("all_gather_start", 0) < 4, hist     # parameter shards gathered together
