@@ -106,6 +106,96 @@ class GPT2(nn.Module):
         return sum(p.numel() for n, p in self.named_parameters() if p.dim() == 2 and "wpe" not in n)
 
 
+@dataclass
+class LlamaConfig:
+    n_layer: int = 32
+    n_head: int = 32
+    n_embd: int = 4096
+    ffn: int = 11008
+    vocab_size: int = 32000
+    block_size: int = 2048
+    eps: float = 1e-5
+
+
+LLAMA_CONFIGS = {
+    "llama2-7b": LlamaConfig(),
+    "llama-tiny": LlamaConfig(2, 4, 64, 176, vocab_size=256, block_size=64),
+}
+
+
+class RMSNorm(nn.Module):
+    def __init__(self, d, eps):
+        super().__init__()
+        self.weight = nn.Parameter(torch.ones(d))
+        self.eps = eps
+
+    def forward(self, x):
+        v = x.float().pow(2).mean(-1, keepdim=True)
+        return (x.float() * torch.rsqrt(v + self.eps)).to(x.dtype) * self.weight
+
+
+def _rope(x, cos, sin):
+    # x: [B, H, T, hd]; rotate pairs (first half, second half), the published Llama-2 layout
+    h = x.shape[-1] // 2
+    x1, x2 = x[..., :h], x[..., h:]
+    return torch.cat((x1 * cos - x2 * sin, x2 * cos + x1 * sin), dim=-1)
+
+
+class LlamaBlock(nn.Module):
+    def __init__(self, cfg):
+        super().__init__()
+        d = cfg.n_embd
+        self.n_head = cfg.n_head
+        self.ln1 = RMSNorm(d, cfg.eps)
+        self.wq = nn.Linear(d, d, bias=False)
+        self.wk = nn.Linear(d, d, bias=False)
+        self.wv = nn.Linear(d, d, bias=False)
+        self.wo = nn.Linear(d, d, bias=False)
+        self.ln2 = RMSNorm(d, cfg.eps)
+        self.w_gate = nn.Linear(d, cfg.ffn, bias=False)
+        self.w_up = nn.Linear(d, cfg.ffn, bias=False)
+        self.w_down = nn.Linear(cfg.ffn, d, bias=False)
+
+    def forward(self, x, cos, sin):
+        B, T, C = x.shape
+        h = self.ln1(x)
+        q, k, v = (w(h).view(B, T, self.n_head, C // self.n_head).transpose(1, 2)
+                   for w in (self.wq, self.wk, self.wv))
+        y = F.scaled_dot_product_attention(_rope(q, cos, sin), _rope(k, cos, sin), v, is_causal=True)
+        x = x + self.wo(y.transpose(1, 2).contiguous().view(B, T, C))
+        h = self.ln2(x)
+        return x + self.w_down(F.silu(self.w_gate(h)) * self.w_up(h))
+
+
+class Llama(nn.Module):
+    """Llama-2 architecture (BASELINE.json config 4) from the published description: RMSNorm,
+    rotary position embedding, SwiGLU MLP, no biases, untied LM head.  Random init; the reference
+    ships no Llama definition either (benchmark/torch/model/__init__.py advertises one)."""
+
+    def __init__(self, cfg: LlamaConfig):
+        super().__init__()
+        self.cfg = cfg
+        self.tok = nn.Embedding(cfg.vocab_size, cfg.n_embd)
+        self.h = nn.ModuleList(LlamaBlock(cfg) for _ in range(cfg.n_layer))
+        self.norm = RMSNorm(cfg.n_embd, cfg.eps)
+        self.lm_head = nn.Linear(cfg.n_embd, cfg.vocab_size, bias=False)
+        for m in self.modules():
+            if isinstance(m, (nn.Linear, nn.Embedding)):
+                nn.init.normal_(m.weight, mean=0.0, std=0.02)
+
+    def forward(self, idx, targets):
+        B, T = idx.shape
+        hd = self.cfg.n_embd // self.cfg.n_head
+        inv = 1.0 / (10000.0 ** (torch.arange(0, hd, 2, device=idx.device).float() / hd))
+        ang = torch.arange(T, device=idx.device).float()[:, None] * inv[None, :]
+        x = self.tok(idx)
+        cos, sin = ang.cos().to(x.dtype), ang.sin().to(x.dtype)
+        for blk in self.h:
+            x = blk(x, cos, sin)
+        logits = self.lm_head(self.norm(x))
+        return F.cross_entropy(logits.view(-1, logits.size(-1)).float(), targets.view(-1))
+
+
 def gpt2_train_step(tokens, targets, model, opt):
     """One optimisation step; same shape as the reference's examples (gpt_train.py:37-43)."""
     loss = model(tokens, targets)
