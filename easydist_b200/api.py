@@ -71,7 +71,13 @@ def _finish(gm, params, buffers, named_states, args, kwargs, ops, native, io=Non
         # opt-in: changes the communication structure the reference's lowering would produce
         info["bucketed"] = lowering.bucket_small_comm(gm, ops)
         lowering.propagate_local_meta(gm, flat)
-    if (native or fuse_rt is not None) and fuse and io is not None and ranks is not None \
+    overlap = os.environ.get("EDB_OVERLAP", "0") == "1" and io is not None and ranks is not None \
+        and len(ranks) > 1
+    if overlap:
+        # stream-level overlap instead of in-kernel fusion: plain GEMMs on the compute stream,
+        # collectives on the communication lane
+        info["overlap"] = lowering.overlap_schedule(gm, io, ops)
+    elif (native or fuse_rt is not None) and fuse and io is not None and ranks is not None \
             and len(ranks) > 1:
         if fuse_rt is None:
             from .runtime import get_runtime

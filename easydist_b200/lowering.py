@@ -534,6 +534,71 @@ def bucket_small_comm(gm, ops=_default_ops, max_bytes=1 << 20, max_bucket_bytes=
     return done
 
 
+def overlap_schedule(gm, io, ops=_default_ops, prefetch=2):
+    """Stream-level overlap of the DP collectives with compute (opt-in `EDB_OVERLAP=1`; the
+    reference's counterpart is the ordering half of passes/comm_optimize.py:50-141).
+
+      * all-gathers of parameter shards (inputs are placeholders, legal anywhere) are marked
+        `_lane=1` and their *_start hoisted `prefetch` gathers ahead: the weights of the next
+        layers travel while the current layer computes; the *_end stays in front of the first use;
+      * reduce-scatters / all-reduces of gradients are marked `_lane=1` and their *_end sunk to
+        the first reader of the result (the optimizer): gradient reduction overlaps the rest of
+        the backward pass.
+
+    Lane ops run on the communication stream with their own group / op sequence
+    (reshard._Lane); values are unchanged.  Returns {"prefetched": n, "deferred": n}."""
+    graph = gm.graph
+    param_ph = set(io.param_ph)
+    order = {nd: i for i, nd in enumerate(graph.nodes)}
+
+    def pair(st):
+        if len(st.users) != 1:
+            return None
+        end = next(iter(st.users))
+        return end if end.target in ops.COMM_SYNC_FUNCS else None
+
+    def lane(st):
+        kw = dict(st.kwargs)
+        kw["_lane"] = 1
+        st.kwargs = kw
+
+    gathers = []
+    for st in graph.nodes:
+        if st.op == "call_function" and st.target is ops.all_gather_start and st.args[0] in param_ph:
+            end = pair(st)
+            if end is not None and end.users:
+                gathers.append((st, end))
+    # hoist: gather i starts right after the end of gather i - prefetch (never later than it was)
+    for i, (st, end) in enumerate(gathers):
+        lane(st)
+        if i >= prefetch:
+            anchor = gathers[i - prefetch][1]
+            if order[anchor] < order[st]:
+                anchor.append(st)
+        elif i > 0:
+            gathers[i - 1][0].append(st)  # the first `prefetch` gathers all start at the top
+    region = optimizer_region(gm, io)
+    region_set = set(region)
+    deferred = 0
+    order = {nd: i for i, nd in enumerate(graph.nodes)}
+    for st in list(graph.nodes):
+        if st.op != "call_function" or st.target not in (ops.reduce_scatter_start,
+                                                         ops.all_reduce_start):
+            continue
+        end = pair(st)
+        if end is None or not end.users:
+            continue
+        if st not in region_set:  # only gradient collectives (downstream of the final grads)
+            continue
+        first = min(end.users, key=lambda u: order[u])
+        lane(st)
+        first.prepend(end)
+        deferred += 1
+    graph.lint()
+    gm.recompile()
+    return {"prefetched": len(gathers), "deferred": deferred}
+
+
 def propagate_local_meta(gm, flat_inputs):
     """Re-run shape propagation on the lowered graph with LOCAL placeholder values so that every
     node's meta['val'] is the per-rank tensor (the reference recomputes metas node by node with

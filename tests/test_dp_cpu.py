@@ -120,9 +120,10 @@ def test_fusion_rewrite_on_cpu(defer):
         assert info["comm_nodes"].get("mm_rs") == 2, info
 
 
-def _worker(rank, world, port, mode, opt_kind, q, bucket=0, generic_bucket="0"):
+def _worker(rank, world, port, mode, opt_kind, q, bucket=0, generic_bucket="0", overlap="0"):
     os.environ["OMP_NUM_THREADS"] = "1"
     os.environ["EDB_BUCKET_COMM"] = generic_bucket
+    os.environ["EDB_OVERLAP"] = overlap
     torch.set_num_threads(1)
     dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank,
                             world_size=world)
@@ -167,7 +168,25 @@ def _worker(rank, world, port, mode, opt_kind, q, bucket=0, generic_bucket="0"):
             p = torch.cat(parts).view(p_ref.shape)
         if not torch.allclose(p, p_ref.detach(), rtol=1e-4, atol=1e-5):
             ok, msg = False, f"param {name} differs: {(p - p_ref).abs().max()}"
-    hist = compiled.info["comm_nodes"]
+    hist = dict(compiled.info["comm_nodes"])
+    if overlap == "1":
+        # structure of the overlap schedule: every gradient collective runs on the lane and its end
+        # sits right in front of its first reader; parameter gathers start ahead of their use
+        from tests import gloo_ops as G
+        nodes = list(compiled.graph.graph.nodes)
+        pos = {n: i for i, n in enumerate(nodes)}
+        hist["overlap"] = compiled.info.get("overlap")
+        for n in nodes:
+            if n.op == "call_function" and n.target in (G.reduce_scatter_start, G.all_reduce_start) \
+                    and n.kwargs.get("_lane") == 1:
+                end = next(iter(n.users))
+                first = min(end.users, key=lambda u: pos[u])
+                between = nodes[pos[end] + 1:pos[first]]
+                if any(b.target not in G.COMM_SYNC_FUNCS for b in between):
+                    ok, msg = False, f"{end.name} is not sunk to its first reader"
+                hist["lane_grad"] = hist.get("lane_grad", 0) + 1
+            if n.op == "call_function" and n.target is G.all_gather_start and n.kwargs.get("_lane") == 1:
+                hist["lane_ag"] = hist.get("lane_ag", 0) + 1
     if rank == 0:
         q.put((ok, msg, hist))
     dist.barrier()
@@ -223,3 +242,24 @@ def test_generic_comm_bucketing_in_dp_graphs(mode):
         assert hist.get("all_reduce_start", 0) == 1, hist   # 4 gradients, one bucket
     else:
         assert hist.get("all_gather_start", 0) < 4, hist     # parameter shards gathered together
+
+
+@pytest.mark.parametrize("mode", ["ddp", "zero2", "zero3"])
+def test_overlap_schedule_keeps_results(mode):
+    """EDB_OVERLAP=1 (lowering.overlap_schedule): gradient collectives on the communication lane
+    with deferred *_end, parameter gathers prefetched; same training results as vanilla."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29895 + ["ddp", "zero2", "zero3"].index(mode)
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, mode, "sgd", q, 0, "0", "1"))
+             for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(180)
+    assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
+    ok, msg, hist = q.get(timeout=5)
+    assert ok, msg
+    assert hist.get("lane_grad", 0) == 4, hist           # one collective per parameter gradient
+    if mode == "zero3":
+        assert hist.get("lane_ag", 0) >= 4, hist         # parameter shards gathered on the lane
