@@ -111,21 +111,26 @@ def _compile_dp(func, parallel_mode, tracing_mode, args, kwargs, *, ops=_default
     """ddp / zero2 / zero3 (reference: _compile_dp, compile_dp.py:201-381)."""
     mode = parallel_mode.replace("b200_", "")
     assert mode in DP_MODES, parallel_mode
-    params, buffers, named_states, gm, module, opt = trace_train_step(func, args, kwargs,
-                                                                      tracing_mode)
-    io = GraphIO(gm, params, buffers, named_states)
     ranks, my_index = _dp_group(get_device_mesh())
     n = len(ranks)
-    shard_info = {}
-    if n > 1:
-        if bucket_numel is None:
-            bucket_numel = 65536 if native else 0
-        if mode == "ddp":
-            lowering.transform_ddp(gm, io, ranks, ops, bucket_numel=bucket_numel)
-        else:
-            _, shard_info = lowering.transform_fsdp(gm, io, ranks, my_index,
-                                                    shard_param=(mode == "zero3"), ops=ops,
-                                                    bucket_numel=bucket_numel)
+    if bucket_numel is None:
+        bucket_numel = 65536 if native else 0
+
+    def trace_and_rewrite(a, kw, warm_up=True):
+        params, buffers, named_states, gm, module, opt = trace_train_step(func, a, kw, tracing_mode,
+                                                                          warm_up=warm_up)
+        io = GraphIO(gm, params, buffers, named_states)
+        shard_info = {}
+        if n > 1:
+            if mode == "ddp":
+                lowering.transform_ddp(gm, io, ranks, ops, bucket_numel=bucket_numel)
+            else:
+                _, shard_info = lowering.transform_fsdp(gm, io, ranks, my_index,
+                                                        shard_param=(mode == "zero3"), ops=ops,
+                                                        bucket_numel=bucket_numel)
+        return params, buffers, named_states, gm, io, shard_info
+
+    params, buffers, named_states, gm, io, shard_info = trace_and_rewrite(args, kwargs)
     # pre-shard parameters (zero3) and optimizer states (zero2/zero3): flat 1/n shards
     # (compile_dp.py:330-343)
     with torch.no_grad():
@@ -145,7 +150,17 @@ def _compile_dp(func, parallel_mode, tracing_mode, args, kwargs, *, ops=_default
     info = _finish(gm, params, buffers, named_states, args, kwargs, ops, native, io=io,
                    ranks=ranks, fuse=fuse, fuse_rt=fuse_rt)
     info.update(mode=mode, dp_size=n)
-    return EDCompiledFunc(gm, params, buffers, named_states, info=info)
+
+    def mono_compiler(compiled, a, kw):
+        """Same rewrite for another input shape, lowered against the live (sharded) state.  The
+        collective/GEMM fusion is left out: it re-homes parameter shards, and the first graph's
+        kernels already address the current homes."""
+        _, _, _, gm2, io2, _ = trace_and_rewrite(a, kw, warm_up=False)
+        p, b, st = compiled.get_state()
+        _finish(gm2, p, b, st, a, kw, ops, native, io=io2, ranks=ranks, fuse=False)
+        return gm2
+
+    return EDCompiledFunc(gm, params, buffers, named_states, info=info, mono_compiler=mono_compiler)
 
 
 def _lower_auto(gm, plan, state_io_map, params, buffers, named_states, args, kwargs, *, ops, native,
@@ -240,8 +255,29 @@ def compile_from_bundle(bundle_text, args, kwargs, *, ops=_default_ops, native=T
                        native=native, planner=planner, mesh=mesh)
 
 
+def input_signature(args, kwargs):
+    """Key of a compiled graph: shapes and dtypes of the tensor inputs, repr of everything else
+    (scalars; modules and optimizers by identity) — the information the reference's
+    get_input_signature hashes (torch/utils.py:210-213: repr of the inputs moved to `meta`)."""
+    import hashlib
+    leaves, spec = pytree.tree_flatten((args, kwargs))
+    parts = [repr(spec)]
+    for x in leaves:
+        if isinstance(x, torch.Tensor):
+            parts.append(f"T{tuple(x.shape)}:{x.dtype}")
+        elif isinstance(x, (torch.nn.Module, torch.optim.Optimizer)):
+            # the object itself stands for its architecture / hyper-parameters: repr() of a large
+            # module costs milliseconds and this runs on every call
+            parts.append(f"{type(x).__qualname__}@{id(x):x}")
+        else:
+            parts.append(repr(x))
+    return hashlib.sha256("|".join(parts).encode("utf-8")).hexdigest()
+
+
 class CompiledFuncWrapper:
-    """Dispatch + CUDA-graph capture/replay (reference: api.py:53-224)."""
+    """Dispatch + CUDA-graph capture/replay (reference: api.py:53-224): one compilation, one
+    lowered graph per input signature (`enable_mono_graph`), one CUDA graph per signature sharing
+    a memory pool."""
 
     def __init__(self, func, parallel_mode="auto", tracing_mode="fake", cuda_graph=True,
                  enable_mono_graph=False, compile_only=False, compile_kwargs=None):
@@ -251,11 +287,13 @@ class CompiledFuncWrapper:
         self.parallel_mode = parallel_mode
         self.tracing_mode = tracing_mode
         self.enable_cuda_graph = cuda_graph
+        self.enable_mono_graph = enable_mono_graph
         self.compile_only = compile_only
         self.compile_kwargs = compile_kwargs or {}
-        self._graph = None
-        self._static_inputs = None
-        self._static_output = None
+        self.all_input_signature = []
+        self.graph_list = {}
+        self.cuda_graph_space = {}
+        self.graph_pool = None
 
     def _compile(self, args, kwargs):
         mode = self.parallel_mode
@@ -270,33 +308,58 @@ class CompiledFuncWrapper:
                                             kwargs)
         raise NotImplementedError()
 
+    def register_input_signature(self, *args, **kwargs):
+        sig = input_signature(args, kwargs)
+        if sig not in self.all_input_signature:
+            self.all_input_signature.append(sig)
+            if self.enable_cuda_graph:
+                self.cuda_graph_space[sig] = {"cuda_graph": None, "cuda_graph_input": None,
+                                              "cuda_graph_output": None}
+        return sig
+
+    def _run(self, sig, args, kwargs):
+        if sig not in self.graph_list:
+            if not self.enable_mono_graph:
+                # same message as the reference (api.py:157-159)
+                raise RuntimeError(
+                    "Input mismatch. If you are sure that different inputs do not change the graph, "
+                    "you can try turning on the enable_mono_graph option.")
+            self.graph_list[sig] = self.compiled_func.compile_mono_graph(*args, **kwargs)
+            logger.info(f"[Compile API] compile mono graph for {sig}")
+        return self.compiled_func.run_with_graph(self.graph_list[sig], *args, **kwargs)
+
     def __call__(self, *args: Any, **kwargs: Any) -> Any:
+        sig = self.register_input_signature(*args, **kwargs)
         if self.compiled_func is None:
             self.compiled_func = self._compile(args, kwargs)
+            self.graph_list[sig] = self.compiled_func.graph
         if self.compile_only:
             return self.compiled_func
         if not self.enable_cuda_graph:
-            return self.compiled_func(*args, **kwargs)
+            return self._run(sig, args, kwargs)
+        space = self.cuda_graph_space[sig]
         flat, spec = pytree.tree_flatten([args, kwargs])
-        if self._graph is None:
-            self._static_inputs = [torch.empty_like(x).copy_(x) if isinstance(x, torch.Tensor)
-                                   else x for x in flat]
-            sargs, skwargs = pytree.tree_unflatten(self._static_inputs, spec)
+        if space["cuda_graph"] is None:
+            space["cuda_graph_input"] = [torch.empty_like(x).copy_(x) if isinstance(x, torch.Tensor)
+                                         else x for x in flat]
+            sargs, skwargs = pytree.tree_unflatten(space["cuda_graph_input"], spec)
             s = torch.cuda.Stream()
             s.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(s):
-                self._static_output = self.compiled_func(*sargs, **skwargs)  # eager warm-up
+                space["cuda_graph_output"] = self._run(sig, sargs, skwargs)  # eager warm-up
             torch.cuda.current_stream().wait_stream(s)
             torch.cuda.synchronize()
-            self._graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self._graph):
-                self._static_output = self.compiled_func(*sargs, **skwargs)
+            space["cuda_graph"] = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(space["cuda_graph"], self.graph_pool):
+                space["cuda_graph_output"] = self._run(sig, sargs, skwargs)
+            if self.graph_pool is None:
+                self.graph_pool = space["cuda_graph"].pool()
         else:
-            for dst, src in zip(self._static_inputs, flat):
+            for dst, src in zip(space["cuda_graph_input"], flat):
                 if isinstance(dst, torch.Tensor):
                     dst.copy_(src, non_blocking=True)
-        self._graph.replay()
-        return self._static_output
+        space["cuda_graph"].replay()
+        return space["cuda_graph_output"]
 
 
 def easydist_compile(func=None, parallel_mode="auto", tracing_mode="fake", cuda_graph=True,

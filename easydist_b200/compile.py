@@ -180,22 +180,25 @@ def _stateless_call(func, module, opt, grad_nodes, params, buffers, named_states
     return params, buffers, named_states, grads, ret
 
 
-def warm_up_optimizer(module, opt):
+def warm_up_optimizer(module, opt, take_step=True):
     """One zero-gradient step so that the optimizer materialises its state tensors
-    (compile.py:52-66); `step` counters are rewound by one."""
+    (compile.py:52-66); `step` counters are rewound by one.  `take_step=False` only collects the
+    state that already exists (re-tracing for a mono graph must not touch a live optimizer: a
+    zero-gradient step still moves parameters along their momentum)."""
     named_states = {}
     params = dict(module.named_parameters())
     if opt is None:
         return named_states
-    with torch.no_grad():
-        for p in params.values():
-            p.grad = torch.zeros_like(p)
-    opt.step()
-    opt.zero_grad(True)
+    if take_step:
+        with torch.no_grad():
+            for p in params.values():
+                p.grad = torch.zeros_like(p)
+        opt.step()
+        opt.zero_grad(True)
     for n, p in params.items():
         if p in opt.state:
             named_states[n] = opt.state[p]
-            if "step" in named_states[n]:
+            if take_step and "step" in named_states[n]:
                 named_states[n]["step"] -= 1
     flat, _ = pytree.tree_flatten(named_states)
     if all(s is None for s in flat):  # plain SGD has no state
@@ -226,13 +229,13 @@ def eliminate_detach(gm):
     return gm
 
 
-def trace_train_step(func, args, kwargs, tracing_mode="fake"):
+def trace_train_step(func, args, kwargs, tracing_mode="fake", warm_up=True):
     """-> (params, buffers, named_states, traced GraphModule, module, opt).
     `gm._edb_grad_nodes` maps parameter names to the node of their final gradient."""
     module, opt = find_module_and_optimizer(args, kwargs)
     params = dict(module.named_parameters()) if module is not None else {}
     buffers = dict(module.named_buffers()) if module is not None else {}
-    named_states = warm_up_optimizer(module, opt) if module is not None else {}
+    named_states = warm_up_optimizer(module, opt, take_step=warm_up) if module is not None else {}
     grad_nodes = {}
     with _pretend_compiling():
         gm = make_fx(partial(_stateless_call, func, module, opt, grad_nodes),
@@ -304,12 +307,14 @@ class EDCompiledFunc:
     """Runs the lowered graph; same surface as the reference's EDCompiledFunc
     (compile_auto.py:720-815 / compile_dp.py:346-381)."""
 
-    def __init__(self, graph, params, buffers, named_states, input_transform=None, info=None):
+    def __init__(self, graph, params, buffers, named_states, input_transform=None, info=None,
+                 mono_compiler=None):
         self.graph = graph
         self._params = params
         self._buffers = buffers
         self._named_states = named_states
         self._input_transform = input_transform
+        self._mono_compiler = mono_compiler
         self.info = info or {}
 
     @torch.no_grad()
@@ -330,7 +335,12 @@ class EDCompiledFunc:
         return self.compiled_func(graph, *args, **kwargs)
 
     def compile_mono_graph(self, *args, **kwargs):
-        raise NotImplementedError("enable_mono_graph is not supported by the b200 backend")
+        """A second lowered graph for inputs of another shape over the SAME (already sharded) state
+        (reference: compile_auto.py:781-800 re-traces and re-applies the sharding strategy)."""
+        if self._mono_compiler is None:
+            raise NotImplementedError("enable_mono_graph: this parallel mode cannot re-lower for "
+                                      "new input shapes")
+        return self._mono_compiler(self, args, kwargs)
 
     def get_state(self):
         return self._params, self._buffers, self._named_states
