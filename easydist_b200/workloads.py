@@ -23,6 +23,9 @@ class GPT2Config:
     block_size: int = 512
     attn: str = "sdpa"  # "sdpa" (ATen fused attention) or "unfused" (matmul-softmax-matmul, as in
     #                      the reference's benchmark/torch/model/gpt.py:23-42)
+    pos_as_buffer: bool = False  # position ids from a registered buffer instead of torch.arange:
+    #                              the reference's sharding discovery cannot annotate tensor-less
+    #                              factory ops (used when a plan is recorded with its solver)
 
 
 GPT2_CONFIGS = {
@@ -83,6 +86,8 @@ class GPT2(nn.Module):
         self.ln_f = nn.LayerNorm(cfg.n_embd)
         self.lm_head = nn.Linear(cfg.n_embd, cfg.vocab_size, bias=False)
         self.lm_head.weight = self.wte.weight  # tied, as published
+        if cfg.pos_as_buffer:
+            self.register_buffer("pos_ids", torch.arange(cfg.block_size), persistent=False)
         self.apply(self._init)
 
     @staticmethod
@@ -94,7 +99,10 @@ class GPT2(nn.Module):
 
     def forward(self, idx, targets):
         B, T = idx.shape
-        pos = torch.arange(T, device=idx.device)
+        if self.cfg.pos_as_buffer:
+            pos = self.pos_ids if T == self.pos_ids.shape[0] else self.pos_ids[:T]
+        else:
+            pos = torch.arange(T, device=idx.device)
         x = self.wte(idx) + self.wpe(pos)
         for blk in self.h:
             x = blk(x)
@@ -194,6 +202,72 @@ class Llama(nn.Module):
             x = blk(x, cos, sin)
         logits = self.lm_head(self.norm(x))
         return F.cross_entropy(logits.view(-1, logits.size(-1)).float(), targets.view(-1))
+
+
+class _RefAttn(nn.Module):
+    def __init__(self, dim, heads):
+        super().__init__()
+        self.heads = heads
+        self.query, self.key, self.value, self.dense = (nn.Linear(dim, dim) for _ in range(4))
+
+    def forward(self, x):
+        B, T, C = x.shape
+        q, k, v = (f(x).view(B, T, self.heads, C // self.heads).permute(0, 2, 1, 3)
+                   for f in (self.query, self.key, self.value))
+        att = (q @ k.transpose(-1, -2)) / math.sqrt(C // self.heads)
+        keep = torch.ones(T, T, dtype=torch.uint8, device=x.device).tril().view(1, 1, T, T).bool()
+        att = torch.where(keep, att, -1e4).softmax(-1)
+        return self.dense((att @ v).transpose(1, 2).reshape(B, T, C))
+
+
+class _RefMlp(nn.Module):
+    def __init__(self, dim, ratio):
+        super().__init__()
+        self.dense_h_to_4h = nn.Linear(dim, dim * ratio)
+        self.dense_4h_to_h = nn.Linear(dim * ratio, dim)
+
+    def forward(self, x):
+        return self.dense_4h_to_h(F.gelu(self.dense_h_to_4h(x)))
+
+
+class _RefBlock(nn.Module):
+    def __init__(self, dim, heads, ratio):
+        super().__init__()
+        self.norm1 = nn.LayerNorm(dim, eps=1e-6)
+        self.attn = _RefAttn(dim, heads)
+        self.norm2 = nn.LayerNorm(dim, eps=1e-6)
+        self.mlp = _RefMlp(dim, ratio)
+
+    def forward(self, x):
+        x = x + self.attn(self.norm1(x))
+        return x + self.mlp(self.norm2(x))
+
+
+class EmbeddingGPT(nn.Module):
+    """The architecture of the reference's example / test model (benchmark/torch/model/gpt.py:
+    pre-LN blocks with eps 1e-6, separate q/k/v/dense Linears, matmul-softmax attention with a
+    -1e4 causal fill, GELU MLP; input = embeddings, no token layer) with the SAME parameter names,
+    so that plan bundles recorded with the reference's solver on that model (SURVEY.md config 1:
+    depth 4, dim 1024, 32 heads) can be lowered and run where the reference is not importable."""
+
+    def __init__(self, depth, dim, num_heads, mlp_ratio=4):
+        super().__init__()
+        self.blocks = nn.ModuleList(_RefBlock(dim, num_heads, mlp_ratio) for _ in range(depth))
+
+    def forward(self, x):
+        for blk in self.blocks:
+            x = blk(x)
+        return x
+
+
+def embedding_gpt_train_step(input, model, opt):
+    """examples/torch/gpt_train.py:37-43 / tests/test_torch/test_utils.py train_step."""
+    out = model(input)
+    loss = out.mean()
+    loss.backward()
+    opt.step()
+    opt.zero_grad()
+    return out
 
 
 def gpt2_train_step(tokens, targets, model, opt):

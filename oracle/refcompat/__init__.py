@@ -107,6 +107,25 @@ def _post_import_patches():
             raise
 
     ed_utils.create_meta_from_node = create_meta_from_node
+
+    # (7) fix_embedding.md_embedding range-checks the indices with `.item()` (fix_embedding.py:19-21);
+    # torch 2.11 FakeTensors turn that into an unbacked symbol and the flop-counting dry run of
+    # reachability.py:52-55 dies on it.  Keep the check for real tensors only.
+    import importlib
+    # (`easydist.torch.passes.fix_embedding` the attribute is the function of the same name)
+    fe = importlib.import_module("easydist.torch.passes.fix_embedding")
+    fe = sys.modules[fe.__module__] if not hasattr(fe, "md_embedding") else fe
+    from torch._subclasses.fake_tensor import FakeTensor
+
+    def md_embedding(weight, indices, padding_idx=-1, scale_grad_by_freq=False, sparse=False):
+        if not isinstance(indices, FakeTensor) and indices.numel() and \
+                int(torch.max(indices).item()) >= weight.shape[0]:
+            raise RuntimeError("embedding indice overflow")
+        return torch.ops.aten.embedding.default(weight, indices, padding_idx, scale_grad_by_freq,
+                                                sparse)
+
+    md_embedding.__module__ = fe.__name__
+    fe.md_embedding = md_embedding
     import easydist.torch.passes.sharding as sh
     import easydist.torch.passes.edinfo_utils as eu
     sh.create_meta_from_node = create_meta_from_node

@@ -40,6 +40,19 @@ def train_step(input, model, opt):
     return out
 
 
+def _comm_hist(gm):
+    hist = {}
+    for n in gm.graph.nodes:
+        if n.op == "call_function":
+            nm = getattr(n.target, "__name__", str(n.target))
+            if "inner" in nm:
+                nm = "box_exchange"  # the reference's do_p2p_comm_wrapper closure
+            if any(k in nm for k in ("all_", "reduce_scatter", "scatter_wrapper", "copy_wrapper",
+                                     "box_exchange")):
+                hist[nm] = hist.get(nm, 0) + 1
+    return hist
+
+
 def main():
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     mesh_shape = tuple(int(v) for v in os.environ.get("EDB_TEST_MESH", str(world)).split("x"))
@@ -71,12 +84,18 @@ def main():
     g = torch.Generator().manual_seed(7)
     if os.environ.get("EDB_MODEL", "foo") == "gpt":
         # the reference's own test model: TEST_GPT of tests/test_torch/test_utils.py:55-68
+        # (EDB_GPT="depth,dim,heads,batch,seq" scales it up, e.g. "4,1024,32,4,128" = SURVEY.md
+        # config 1, the reference's examples/torch/gpt_train.py)
         from benchmark.torch.model.gpt import GPT
-        model0 = GPT(depth=2, dim=64, num_heads=4)
-        batches = [torch.randn(4, 32, 64, generator=g) for _ in range(2)]
+        depth, dim, heads, gb, gs = (int(v) for v in os.environ.get("EDB_GPT", "2,64,4,4,32").split(","))
+        model0 = GPT(depth=depth, dim=dim, num_heads=heads)
+        batches = [torch.randn(gb, gs, dim, generator=g) for _ in range(2)]
+        model_tag = f"GPT(depth={depth}, dim={dim}, num_heads={heads})"
+        batch_shape = [gb, gs, dim]
     else:
         model0 = Foo()
         batches = [torch.randn(16, 64, generator=g) for _ in range(3)]
+        model_tag, batch_shape = "Foo(64)", [16, 64]
 
     def run(variant):
         model = copy.deepcopy(model0)
@@ -91,8 +110,17 @@ def main():
                     saved["plan"] = graph_io.dump_bundle(
                         fx_module, opt_strategy,
                         [(a.name, b.name) for a, b in state_io_map.items()],
-                        extra={"mesh": list(mesh_shape), "model": "Foo(64)", "seed": 42,
-                               "batch_seed": 7, "batch": [16, 64], "planner": planner})
+                        extra={"mesh": list(mesh_shape), "model": model_tag, "seed": 42,
+                               "batch_seed": 7, "batch": batch_shape, "planner": planner})
+                if os.environ.get("EDB_SAMEPLAN") == "1":
+                    # the reference's lowering of the VERY SAME plan (the ILP may return another
+                    # equal-cost plan on a second solve, so run A alone does not isolate the lowering)
+                    import torch.fx as fx
+                    g2 = fx.GraphModule(fx_module, copy.deepcopy(fx_module.graph))
+                    for n_old, n_new in zip(fx_module.graph.nodes, g2.graph.nodes):
+                        n_new.meta = dict(n_old.meta)
+                    ref_gm = orig(g2, opt_strategy, state_io_map)
+                    saved["hist_ref_same_plan"] = _comm_hist(ref_gm)
                 return lowering.sharding_transform(fx_module, opt_strategy, state_io_map,
                                                    ops=gloo_ops, mesh=my_mesh, planner=planner)
             ref_auto.sharding_transform = mine
@@ -103,16 +131,7 @@ def main():
             if variant == "B":
                 ref_auto.sharding_transform = orig
         cf = step.compiled_func
-        hist = {}
-        for n in cf.graph.graph.nodes:
-            if n.op == "call_function":
-                nm = getattr(n.target, "__name__", str(n.target))
-                if "inner" in nm:
-                    nm = "box_exchange"  # the reference's do_p2p_comm_wrapper closure
-                if any(k in nm for k in ("all_", "reduce_scatter", "scatter_wrapper", "copy_wrapper",
-                                         "box_exchange")):
-                    hist[nm] = hist.get(nm, 0) + 1
-        return outs, cf, hist, saved
+        return outs, cf, _comm_hist(cf.graph), saved
 
     # vanilla
     vmodel = copy.deepcopy(model0)
@@ -158,7 +177,10 @@ def main():
                     ok = False
                     msgs.append(f"param {name} {tag} differs")
     if rank == 0:
-        print(f"AUTO_PARITY ok={ok} hist_ref={hist_a} hist_b200={hist_b} {msgs}", flush=True)
+        same = saved.get("hist_ref_same_plan")
+        print(f"AUTO_PARITY ok={ok} hist_ref={hist_a} hist_b200={hist_b} {msgs}"
+              + (f" hist_ref_same_plan={same} same_plan_equal={same == hist_b}" if same else ""),
+              flush=True)
         if record and "plan" in saved:
             with open(record, "w") as f:
                 f.write(saved["plan"])

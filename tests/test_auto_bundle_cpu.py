@@ -124,3 +124,67 @@ def test_bucketed_small_collectives_match_vanilla(mesh_shape, port):
     plain = {(2,): (26, 3), (2, 2): (37, 5)}[mesh_shape]
     assert hist.get("all_gather_start", 0) < plain[0], hist
     assert hist.get("all_reduce_start", 0) <= plain[1], hist
+
+
+def run_c1_bundle(rank, world, ops, native, device, steps=2):
+    """SURVEY.md config 1 (the reference's examples/torch/gpt_train.py model: GPT depth 4, dim
+    1024, 32 heads, batch 4 x 128, fp32, world 2) with the plan the reference's solver produced for
+    it (tests/golden/auto_gpt_c1_mesh2.json.gz, recorded by tests/ref/auto_worker.py with
+    EDB_MODEL=gpt EDB_GPT=4,1024,32,4,128).  Returns (ok, message, comm histogram)."""
+    import gzip
+    import numpy as np
+    from easydist_b200 import api
+    from easydist_b200.device_mesh import set_device_mesh
+    from easydist_b200.workloads import EmbeddingGPT, embedding_gpt_train_step
+    set_device_mesh(np.arange(world).reshape((world,)), ["spmd0"], rank=rank)
+    bundle = gzip.open(os.path.join(GOLDEN, "auto_gpt_c1_mesh2.json.gz"), "rt").read()
+    torch.manual_seed(42)
+    model = EmbeddingGPT(4, 1024, 32).to(device)
+    ref = EmbeddingGPT(4, 1024, 32).to(device)
+    ref.load_state_dict(model.state_dict())
+    opt = torch.optim.SGD(model.parameters(), lr=0.1, momentum=0.9, foreach=True)
+    ropt = torch.optim.SGD(ref.parameters(), lr=0.1, momentum=0.9, foreach=True)
+    g = torch.Generator().manual_seed(7)
+    batches = [torch.randn(4, 128, 1024, generator=g).to(device) for _ in range(steps)]
+    compiled = api.compile_from_bundle(bundle, (batches[0], model, opt), {}, ops=ops, native=native)
+    ok, msg = True, ""
+    for b in batches:
+        out = compiled(b, model, opt)
+        want = embedding_gpt_train_step(b, ref, ropt)
+        if out.shape != want.shape or not torch.allclose(out, want.detach(), rtol=1e-4, atol=1e-5):
+            ok, msg = False, f"output differs by {(out - want).abs().max()}"
+    return ok, msg, compiled.info["comm_nodes"]
+
+
+def _c1_worker(rank, world, port, q):
+    os.environ["OMP_NUM_THREADS"] = "2"
+    torch.set_num_threads(2)
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank,
+                            world_size=world)
+    import numpy as np
+    from tests import gloo_ops
+    gloo_ops.init_groups(np.arange(world).reshape((world,)))
+    ok, msg, hist = run_c1_bundle(rank, world, gloo_ops, False, "cpu")
+    if rank == 0:
+        q.put((ok, msg, hist))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_config1_gpt_plan_from_the_reference_solver_matches_vanilla():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_c1_worker, args=(r, 2, 29866, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(600)
+    assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
+    ok, msg, hist = q.get(timeout=5)
+    assert ok, msg
+    # what the reference's own lowering produces for this very plan (tests/ref/auto_worker.py,
+    # EDB_SAMEPLAN=1: same_plan_equal=True)
+    want = {"all_gather_start": 429, "scatter_wrapper": 197, "reduce_scatter_start": 8,
+            "all_reduce_start": 17, "all_to_all_start": 52}
+    for k, v in want.items():
+        assert hist.get(k, 0) == v, (k, hist)
