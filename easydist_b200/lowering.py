@@ -21,6 +21,7 @@ The emitted `call_function` targets are the callables of an `ops` namespace with
 names and signatures (default: easydist_b200.reshard -> libedb.so).
 """
 import operator
+import os
 from typing import Dict, List, Optional
 
 import torch
@@ -244,9 +245,59 @@ def sharding_transform(fx_module: torch.fx.GraphModule, opt_strategy, state_io_m
                     insert_comm_node(fx_module, node, o, src, tgt, mesh, ops, planner,
                                      copy_innode=placeholders[in_node.name])
     fx_module.graph.lint()
+    legalize_views(fx_module, mesh, shard_env)
     fx_module.recompile()
     fx_module._edb_shard_env = shard_env
     return fx_module
+
+
+def legalize_views(gm, mesh, shard_env):
+    """`aten.view` is stride dependent: after a reshard its input may be a non-contiguous local
+    tensor and the traced view is no longer legal (the reference hits the same wall: SURVEY.md
+    hard part 1; its meta propagation only works under torch 2.11 with the reshape retry of
+    oracle/refcompat).  Dry-run the lowered graph on fake LOCAL placeholders and retarget exactly
+    the view nodes that fail to `aten.reshape` (same values, copies when it must).  Returns the
+    number of nodes changed; never raises (an op the dry run cannot execute just ends it)."""
+    from torch._subclasses.fake_tensor import FakeTensorMode
+    changed = 0
+    env = {}
+    try:
+        with FakeTensorMode(allow_non_fake_inputs=True):
+            for node in gm.graph.nodes:
+                if node.op == "placeholder":
+                    val = node.meta.get("val")
+                    if isinstance(val, torch.Tensor):
+                        strat = shard_env.get(node.name)
+                        shape = list(val.shape)
+                        if isinstance(strat, (M.VarSPMDStrategy, list, tuple)) and all(
+                                s is None or hasattr(s, "is_shard") for s in strat):
+                            shape = local_shape(shape, mesh, strat)
+                        env[node] = torch.empty(shape, dtype=val.dtype, device=val.device)
+                    else:
+                        env[node] = val
+                elif node.op == "call_function":
+                    args, kwargs = pytree.tree_map_only(Node, lambda n: env[n],
+                                                        (node.args, node.kwargs))
+                    try:
+                        env[node] = node.target(*args, **kwargs)
+                    except (RuntimeError, ValueError):
+                        if node.target not in (aten.view.default, aten._unsafe_view.default):
+                            raise
+                        node.target = aten.reshape.default
+                        env[node] = node.target(*args, **kwargs)
+                        changed += 1
+                elif node.op == "output":
+                    break
+                else:
+                    return changed
+    except Exception as e:  # noqa: BLE001 — best effort: the graph itself is left as lowered
+        import logging
+        logging.getLogger(__name__).debug("legalize_views stopped early: %r", e)
+        if os.environ.get("EDB_DEBUG_LEGALIZE"):
+            print("legalize_views stopped early:", repr(e)[:300], flush=True)
+    if os.environ.get("EDB_DEBUG_LEGALIZE"):
+        print("legalize_views changed", changed, flush=True)
+    return changed
 
 
 # ---- data-parallel rewrites (compile_dp.py:55-198) ---------------------------------------------------------

@@ -516,14 +516,15 @@ def main():
     n += run_auto_bundle(rank, world)
     if os.environ.get("EDB_TEST_EXPERIMENTAL") == "1":
         n += run_lane(rank, world, group)
-        if world == 2:
-            # SURVEY.md config 1 with the reference solver's plan, on real GPUs (fp32)
+        if world in (2, 4, 8):
+            # SURVEY.md config 1 with the reference solver's plans, on real GPUs (fp32)
             from tests.test_auto_bundle_cpu import run_c1_bundle
-            ok, msg, hist = run_c1_bundle(rank, world, reshard, True, "cuda")
-            assert ok, f"config-1 bundle on GPUs: {msg}"
-            if rank == 0:
-                print(f"AUTO_BUNDLE_C1_OK {hist}", flush=True)
-            n += 1
+            for tag in [str(world)] + (["2x2"] if world == 4 else []):
+                ok, msg, hist = run_c1_bundle(rank, world, reshard, True, "cuda", tag=tag)
+                assert ok, f"config-1 bundle mesh {tag} on GPUs: {msg}"
+                if rank == 0:
+                    print(f"AUTO_BUNDLE_C1_OK mesh={tag} {hist}", flush=True)
+                n += 1
     if world >= 4 and world % 2 == 0:
         # 2-D mesh: groups along each mesh dim (ranks in mesh-coordinate order)
         mesh = np.arange(world).reshape(2, world // 2)

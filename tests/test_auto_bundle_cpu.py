@@ -126,7 +126,7 @@ def test_bucketed_small_collectives_match_vanilla(mesh_shape, port):
     assert hist.get("all_reduce_start", 0) <= plain[1], hist
 
 
-def run_c1_bundle(rank, world, ops, native, device, steps=2):
+def run_c1_bundle(rank, world, ops, native, device, steps=2, tag=None):
     """SURVEY.md config 1 (the reference's examples/torch/gpt_train.py model: GPT depth 4, dim
     1024, 32 heads, batch 4 x 128, fp32, world 2) with the plan the reference's solver produced for
     it (tests/golden/auto_gpt_c1_mesh2.json.gz, recorded by tests/ref/auto_worker.py with
@@ -136,8 +136,11 @@ def run_c1_bundle(rank, world, ops, native, device, steps=2):
     from easydist_b200 import api
     from easydist_b200.device_mesh import set_device_mesh
     from easydist_b200.workloads import EmbeddingGPT, embedding_gpt_train_step
-    set_device_mesh(np.arange(world).reshape((world,)), ["spmd0"], rank=rank)
-    bundle = gzip.open(os.path.join(GOLDEN, "auto_gpt_c1_mesh2.json.gz"), "rt").read()
+    tag = tag or str(world)                      # "2", "4", "8" (1-D meshes) or "2x2"
+    mesh_shape = tuple(int(v) for v in tag.split("x"))
+    set_device_mesh(np.arange(world).reshape(mesh_shape), [f"spmd{i}" for i in range(len(mesh_shape))],
+                    rank=rank)
+    bundle = gzip.open(os.path.join(GOLDEN, f"auto_gpt_c1_mesh{tag}.json.gz"), "rt").read()
     torch.manual_seed(42)
     model = EmbeddingGPT(4, 1024, 32).to(device)
     ref = EmbeddingGPT(4, 1024, 32).to(device)
@@ -145,7 +148,8 @@ def run_c1_bundle(rank, world, ops, native, device, steps=2):
     opt = torch.optim.SGD(model.parameters(), lr=0.1, momentum=0.9, foreach=True)
     ropt = torch.optim.SGD(ref.parameters(), lr=0.1, momentum=0.9, foreach=True)
     g = torch.Generator().manual_seed(7)
-    batches = [torch.randn(4, 128, 1024, generator=g).to(device) for _ in range(steps)]
+    batch = 8 if tag == "8" else 4                # the (8,) plan was solved for a batch of 8
+    batches = [torch.randn(batch, 128, 1024, generator=g).to(device) for _ in range(steps)]
     compiled = api.compile_from_bundle(bundle, (batches[0], model, opt), {}, ops=ops, native=native)
     ok, msg = True, ""
     for b in batches:
@@ -188,3 +192,40 @@ def test_config1_gpt_plan_from_the_reference_solver_matches_vanilla():
             "all_reduce_start": 17, "all_to_all_start": 52}
     for k, v in want.items():
         assert hist.get(k, 0) == v, (k, hist)
+
+
+@pytest.mark.parametrize("tag,mesh_shape,rank,want", [
+    ("4", (4,), 3, {"all_gather_start": 429, "scatter_wrapper": 197, "reduce_scatter_start": 12,
+                    "all_reduce_start": 17, "all_to_all_start": 24}),
+    ("8", (8,), 5, {"all_gather_start": 437, "scatter_wrapper": 197, "reduce_scatter_start": 20,
+                    "all_reduce_start": 17, "all_to_all_start": 24}),
+    ("2x2", (2, 2), 2, {"all_gather_start": 675, "scatter_wrapper": 319, "reduce_scatter_start": 12,
+                        "all_reduce_start": 54, "all_to_all_start": 95}),
+])
+def test_config1_plans_for_larger_meshes_lower_to_the_recorded_structure(tag, mesh_shape, rank, want):
+    """The config-1 plans the reference solved for meshes (4,), (8,) and (2,2) (each verified against
+    vanilla inside the reference's pipeline when it was recorded, tests/ref/auto_worker.py) lower —
+    for an arbitrary rank of the mesh, in one process, nothing executed — to the communication
+    structure recorded with them.  (Execution of these meshes is the GPU worker's job.)"""
+    import gzip
+    import numpy as np
+    from easydist_b200 import api
+    from easydist_b200.device_mesh import set_device_mesh
+    from easydist_b200.workloads import EmbeddingGPT
+    from tests import gloo_ops
+    world = int(np.prod(mesh_shape))
+    set_device_mesh(np.arange(world).reshape(mesh_shape), [f"spmd{i}" for i in range(len(mesh_shape))],
+                    rank=rank)
+    bundle = gzip.open(os.path.join(GOLDEN, f"auto_gpt_c1_mesh{tag}.json.gz"), "rt").read()
+    torch.manual_seed(0)
+    model = EmbeddingGPT(4, 1024, 32)
+    opt = torch.optim.SGD(model.parameters(), lr=0.1, momentum=0.9, foreach=True)
+    batch = 8 if tag == "8" else 4
+    compiled = api.compile_from_bundle(bundle, (torch.randn(batch, 128, 1024), model, opt), {},
+                                       ops=gloo_ops, native=False)
+    hist = compiled.info["comm_nodes"]
+    for k, v in want.items():
+        assert hist.get(k, 0) == v, (k, hist)
+    # every parameter ended up with its local shard shape under the plan
+    full = dict(model.named_parameters())
+    assert any(p.shape != full[n].shape for n, p in compiled.named_parameters().items())
