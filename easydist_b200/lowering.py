@@ -292,11 +292,7 @@ def legalize_views(gm, mesh, shard_env):
                     return changed
     except Exception as e:  # noqa: BLE001 — best effort: the graph itself is left as lowered
         import logging
-        logging.getLogger(__name__).debug("legalize_views stopped early: %r", e)
-        if os.environ.get("EDB_DEBUG_LEGALIZE"):
-            print("legalize_views stopped early:", repr(e)[:300], flush=True)
-    if os.environ.get("EDB_DEBUG_LEGALIZE"):
-        print("legalize_views changed", changed, flush=True)
+        logging.getLogger(__name__).warning("legalize_views stopped early: %r", e)
     return changed
 
 
