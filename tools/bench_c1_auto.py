@@ -1,0 +1,84 @@
+"""Config 1 (the reference's examples/torch/gpt_train.py model: GPT depth 4 / dim 1024 / 32 heads,
+fp32) in AUTO-SPMD mode on N GPUs: the plan is the one the reference's solver produced for this
+mesh (tests/golden/auto_gpt_c1_mesh{N}.json.gz), lowered and executed by this backend.
+Prints one JSON line (samples/s, ms/step, comm histogram).  EDB_BUCKET_COMM=1 buckets the small
+collectives of the plan.
+
+    python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 tools/bench_c1_auto.py [--mesh 2x2]
+"""
+import argparse
+import gzip
+import json
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from easydist_b200 import api, runtime
+from easydist_b200.device_mesh import set_device_mesh
+from easydist_b200.workloads import EmbeddingGPT
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--mesh", default="")
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--no-cuda-graph", action="store_true")
+    args = ap.parse_args()
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    runtime.init(rank, world, local, heap_bytes=8 << 30)
+    tag = args.mesh or str(world)
+    mesh_shape = tuple(int(v) for v in tag.split("x"))
+    set_device_mesh(np.arange(world).reshape(mesh_shape), [f"spmd{i}" for i in range(len(mesh_shape))],
+                    rank=rank)
+    golden = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+    bundle = gzip.open(os.path.join(golden, f"auto_gpt_c1_mesh{tag}.json.gz"), "rt").read()
+    torch.manual_seed(42)
+    model = EmbeddingGPT(4, 1024, 32).cuda()
+    opt = torch.optim.SGD(model.parameters(), lr=1e-3, momentum=0.9, foreach=True)
+    batch = 8 if tag == "8" else 4
+    x = torch.randn(batch, 128, 1024, device="cuda")
+    compiled = api.compile_from_bundle(bundle, (x, model, opt), {})
+    step = lambda: compiled(x, model, opt)
+    for _ in range(2):
+        step()
+    torch.cuda.synchronize()
+    if not args.no_cuda_graph:
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            step()
+        step = graph.replay
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1) / args.steps], device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        ms = t.item()
+        print(json.dumps({"metric": "train_step_throughput", "value": batch / ms * 1e3, "unit": "samples/s",
+                          "n_gpus": world, "ms_per_step": ms, "dtype": "f32",
+                          "config": {"workload": "config 1: GPT depth 4 dim 1024 heads 32, batch "
+                                                 f"{batch}x128, auto-SPMD plan of the reference solver",
+                                     "mesh": list(mesh_shape), "cuda_graph": not args.no_cuda_graph,
+                                     "bucket_comm": os.environ.get("EDB_BUCKET_COMM", "0")},
+                          "comm_nodes": compiled.info["comm_nodes"]}), flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
