@@ -182,7 +182,7 @@ def _stateless_call(func, module, opt, grad_nodes, params, buffers, named_states
 
 def warm_up_optimizer(module, opt, take_step=True):
     """One zero-gradient step so that the optimizer materialises its state tensors
-    (compile.py:52-66); `step` counters are rewound by one.  `take_step=False` only collects the
+    (reference: compile.py:52-66, which takes the step as is); `step` counters are rewound by one.  `take_step=False` only collects the
     state that already exists (re-tracing for a mono graph must not touch a live optimizer: a
     zero-gradient step still moves parameters along their momentum)."""
     named_states = {}
@@ -190,11 +190,27 @@ def warm_up_optimizer(module, opt, take_step=True):
     if opt is None:
         return named_states
     if take_step:
+        # weight decay makes even a zero-gradient step move the parameters (and, for SGD, fill
+        # the momentum buffers with wd * p): switch it off for this step and put the parameter
+        # values back afterwards, so that compiling never changes what is being trained
         with torch.no_grad():
+            saved = [p.detach().clone() for p in params.values()]
             for p in params.values():
                 p.grad = torch.zeros_like(p)
-        opt.step()
+        decay = [g.get("weight_decay", 0) for g in opt.param_groups]
+        for g in opt.param_groups:
+            if "weight_decay" in g:
+                g["weight_decay"] = 0
+        try:
+            opt.step()
+        finally:
+            for g, wd in zip(opt.param_groups, decay):
+                if "weight_decay" in g:
+                    g["weight_decay"] = wd
         opt.zero_grad(True)
+        with torch.no_grad():
+            for p, old in zip(params.values(), saved):
+                p.copy_(old)
     for n, p in params.items():
         if p in opt.state:
             named_states[n] = opt.state[p]

@@ -1097,9 +1097,89 @@ def reinplace_optimizer_updates(gm):
             graph.erase_node(cp)
             graph.erase_node(getitems[i])
         n_fixed += 1
+    n_fixed += _reinplace_fused_optimizers(gm, order)
     if n_fixed:
         graph.lint()
         gm.recompile()
+    return n_fixed
+
+
+def _reinplace_fused_optimizers(gm, order):
+    """Same for the fused optimizers (`_fused_adam`, `_fused_adamw`, `_fused_sgd`: what
+    torch.optim(..., fused=True) calls and what the reference's DP rewrites are written around,
+    compile_dp.py:55-198).  Tracing turned `_fused_x_(params, grads, states...)` into the functional
+    op plus one copy_ per written tensor (compile.py `_fused_multi_output`); when every output is
+    only used for that copy the in-place op comes back and 3 copies per parameter disappear."""
+    graph = gm.graph
+    table = {}
+    for name, n_lists, skip in (("_fused_adam", 5, (1,)), ("_fused_adamw", 5, (1,)),
+                                ("_fused_sgd", 3, (1,))):
+        if hasattr(aten, name) and hasattr(aten, name + "_"):
+            table[getattr(aten, name).default] = (getattr(aten, name + "_").default, n_lists, skip)
+    n_fixed = 0
+    for node in list(graph.nodes):
+        if node.op != "call_function" or node.target not in table:
+            continue
+        inplace, n_lists, skip = table[node.target]
+        lists = list(node.args[:n_lists])
+        if any(not isinstance(lst, (list, tuple)) for lst in lists):
+            continue
+        outer = {}
+        ok = all(u.target == operator.getitem for u in node.users)
+        for u in node.users:
+            if ok:
+                outer[u.args[1]] = u
+        dead, redirect = [], []
+        for k, lst in enumerate(lists):
+            if not ok:
+                break
+            if k in skip or not lst:
+                # an output list nobody copies back must be unused altogether
+                if k in outer and outer[k].users:
+                    ok = False
+                continue
+            if k not in outer:
+                ok = False
+                break
+            inner = {}
+            for u in outer[k].users:
+                if u.target != operator.getitem or u.args[1] in inner:
+                    ok = False
+                    break
+                inner[u.args[1]] = u
+            if not ok or len(inner) != len(lst) or len(set(lst)) != len(lst):
+                ok = False
+                break
+            for i, orig in enumerate(lst):
+                users = list(inner[i].users)
+                if not isinstance(orig, Node) or len(users) != 1 or \
+                        users[0].target != aten.copy_.default or users[0].args[0] is not orig or \
+                        users[0].args[1] is not inner[i]:
+                    ok = False
+                    break
+                for other in orig.users:
+                    if other is node or other is users[0] or other.op == "output":
+                        continue
+                    if order[other] > order[node]:
+                        ok = False
+                        break
+                if not ok:
+                    break
+                redirect.append((users[0], orig))
+                dead.append(inner[i])
+            dead.append(outer[k])
+        if not ok:
+            continue
+        node.target = inplace
+        for cp, orig in redirect:
+            cp.replace_all_uses_with(orig)
+            graph.erase_node(cp)
+        for d in dead:
+            graph.erase_node(d)
+        for k, u in list(outer.items()):
+            if not u.users and u not in dead:
+                graph.erase_node(u)
+        n_fixed += 1
     return n_fixed
 
 

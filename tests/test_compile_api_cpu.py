@@ -86,3 +86,28 @@ def test_compile_only_returns_the_compiled_object():
 def test_unknown_parallel_mode_is_rejected_like_the_reference():
     with pytest.raises(NotImplementedError):
         api.easydist_compile(train_step, parallel_mode="nope")
+
+
+@pytest.mark.parametrize("make", [
+    lambda ps: torch.optim.SGD(ps, lr=0.1, momentum=0.9, weight_decay=0.1, foreach=True),
+    lambda ps: torch.optim.AdamW(ps, lr=1e-2, weight_decay=0.1, fused=True),
+])
+def test_compiling_does_not_change_parameters_or_seed_optimizer_state(make):
+    """The warm-up step that materialises optimizer state must leave the model as it was, also with
+    weight decay (parameters would shrink; SGD's momentum buffers would start at wd * p)."""
+    from easydist_b200.compile import warm_up_optimizer
+    set_device_mesh([0], ["dp"], rank=0)
+    torch.manual_seed(0)
+    model = Net()
+    before = {k: v.detach().clone() for k, v in model.named_parameters()}
+    opt = make(model.parameters())
+    states = warm_up_optimizer(model, opt)
+    for k, v in model.named_parameters():
+        assert torch.equal(v, before[k]), k
+    assert opt.param_groups[0]["weight_decay"] == 0.1
+    for name, st in states.items():
+        for key, t in st.items():
+            if isinstance(t, torch.Tensor) and key != "step":
+                assert float(t.abs().max()) == 0.0, (name, key)
+            if key == "step":
+                assert float(t) == 0.0

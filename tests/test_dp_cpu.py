@@ -40,6 +40,10 @@ def make_opt(kind, params):
         return torch.optim.SGD(params, lr=0.1, momentum=0.9, foreach=True)
     if kind == "sgd_plain":
         return torch.optim.SGD(params, lr=0.1, foreach=True)
+    if kind == "adam_fused":
+        return torch.optim.Adam(params, lr=1e-2, fused=True)
+    if kind == "adamw_fused":
+        return torch.optim.AdamW(params, lr=1e-2, weight_decay=0.05, fused=True)
     return torch.optim.Adam(params, lr=1e-2, foreach=True)
 
 
@@ -263,3 +267,24 @@ def test_overlap_schedule_keeps_results(mode):
     assert hist.get("lane_grad", 0) == 4, hist           # one collective per parameter gradient
     if mode == "zero3":
         assert hist.get("lane_ag", 0) >= 4, hist         # parameter shards gathered on the lane
+
+
+@pytest.mark.parametrize("mode,opt_kind", [("ddp", "adamw_fused"), ("zero2", "adamw_fused"),
+                                           ("zero3", "adam_fused"), ("zero3", "adamw_fused")])
+def test_fused_adam_in_dp_modes(mode, opt_kind):
+    """torch.optim.Adam/AdamW(fused=True) — the `_fused_adam` node the reference's DP rewrites are
+    written around (compile_dp.py:55-198) — through ddp / zero2 / zero3; in ddp / zero3 the traced
+    functional op + copies are re-inplaced to `_fused_adam_`.  AdamW also pins that compiling does not
+    touch the parameters: the warm-up step that materialises the optimizer state runs without weight
+    decay and the parameter values are restored (the reference's warm-up decays them once)."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29920 + ["ddp", "zero2", "zero3"].index(mode) + 3 * (opt_kind == "adamw_fused")
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, mode, opt_kind, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(180)
+    assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
+    ok, msg, hist = q.get(timeout=5)
+    assert ok, msg
