@@ -35,6 +35,16 @@ def train_step(input, model, opt):
     return loss
 
 
+def train_step_clipped(input, model, opt):
+    out = model(input)
+    loss = out.mean()
+    loss.backward()
+    torch.nn.utils.clip_grad_norm_(model.parameters(), 0.05)
+    opt.step()
+    opt.zero_grad()
+    return loss
+
+
 def make_opt(kind, params):
     if kind == "sgd":
         return torch.optim.SGD(params, lr=0.1, momentum=0.9, foreach=True)
@@ -124,7 +134,9 @@ def test_fusion_rewrite_on_cpu(defer):
         assert info["comm_nodes"].get("mm_rs") == 2, info
 
 
-def _worker(rank, world, port, mode, opt_kind, q, bucket=0, generic_bucket="0", overlap="0"):
+def _worker(rank, world, port, mode, opt_kind, q, bucket=0, generic_bucket="0", overlap="0",
+            clip=False):
+    step_fn = train_step_clipped if clip else train_step
     os.environ["OMP_NUM_THREADS"] = "1"
     os.environ["EDB_BUCKET_COMM"] = generic_bucket
     os.environ["EDB_OVERLAP"] = overlap
@@ -143,8 +155,8 @@ def _worker(rank, world, port, mode, opt_kind, q, bucket=0, generic_bucket="0", 
     ref_opt = make_opt(opt_kind, ref_model.parameters())
     g = torch.Generator().manual_seed(123)
     batches = [torch.randn(world * 4, 32, generator=g) for _ in range(3)]
-    compiled = api._compile_dp(train_step, mode, "fake", (batches[0][rank * 4:(rank + 1) * 4], model,
-                                                         opt), {}, ops=gloo_ops, native=False,
+    compiled = api._compile_dp(step_fn, mode, "fake", (batches[0][rank * 4:(rank + 1) * 4], model,
+                                                      opt), {}, ops=gloo_ops, native=False,
                                bucket_numel=bucket)
     # the optimizer rewrite of the native path (on CPU the fused node takes its ATen branch): the
     # sharded update of every mode must still match vanilla
@@ -156,7 +168,7 @@ def _worker(rank, world, port, mode, opt_kind, q, bucket=0, generic_bucket="0", 
     msg = ""
     for b in batches:
         loss = compiled(b[rank * 4:(rank + 1) * 4], model, opt)
-        ref_loss = train_step(b, ref_model, ref_opt)
+        ref_loss = step_fn(b, ref_model, ref_opt)
         # local loss is the mean over the local micro-batch; the global mean is their average
         loss_all = loss.detach().clone()
         dist.all_reduce(loss_all)
@@ -281,6 +293,23 @@ def test_fused_adam_in_dp_modes(mode, opt_kind):
     q = ctx.Queue()
     port = 29920 + ["ddp", "zero2", "zero3"].index(mode) + 3 * (opt_kind == "adamw_fused")
     procs = [ctx.Process(target=_worker, args=(r, 2, port, mode, opt_kind, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(180)
+    assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
+    ok, msg, hist = q.get(timeout=5)
+    assert ok, msg
+
+
+def test_ddp_with_gradient_clipping_clips_the_averaged_gradients():
+    """clip_grad_norm_ between backward and the optimizer: the norm must be taken over the
+    all-reduced gradients (what eager DDP does), i.e. every reader of a gradient is rewired to the
+    collective's result, not only the optimizer."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, 29930, "ddp", "sgd", q, 0, "0", "0", True))
+             for r in range(2)]
     for p in procs:
         p.start()
     for p in procs:
