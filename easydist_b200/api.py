@@ -378,15 +378,20 @@ def easydist_compile(func=None, parallel_mode="auto", tracing_mode="fake", cuda_
     return wrap(func) if func else wrap
 
 
-def register(reference_api=None, reference_compile_auto=None):
-    """Plug this backend into an importable reference (`easydist.torch`)."""
+def register(reference_api=None, reference_compile_auto=None, **compile_kwargs):
+    """Plug this backend into an importable reference (`easydist.torch`).  `compile_kwargs` are
+    forwarded to `_compile_dp` (tests run the plugged modes over gloo with `ops=`, `native=False`)."""
     import easydist.torch.api as ref_api
     import easydist.torch.compile_auto as ref_auto
     reference_api = reference_api or ref_api
     reference_compile_auto = reference_compile_auto or ref_auto
 
     def dp_entry(original_func, parallel_mode, tracing_mode, args, kwargs):
-        return _compile_dp(original_func, parallel_mode, tracing_mode, args, kwargs)
+        # the reference's device mesh is the source of truth when this backend is a plugin
+        from easydist.torch.device_mesh import get_device_mesh as ref_mesh
+        from .device_mesh import set_device_mesh
+        set_device_mesh(ref_mesh(), rank=torch.distributed.get_rank())
+        return _compile_dp(original_func, parallel_mode, tracing_mode, args, kwargs, **compile_kwargs)
 
     for mode in DP_MODES:
         reference_api.register_parallel_method(f"b200_{mode}", dp_entry)

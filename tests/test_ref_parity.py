@@ -21,14 +21,30 @@ def test_dropin_lowering_equals_reference_lowering(mesh, nproc, port, planner, m
     if not os.path.isdir("/root/reference/easydist"):
         pytest.skip("reference not present (GPU box)")
     env = dict(os.environ, EDB_TEST_MESH=mesh, OMP_NUM_THREADS="1", EDB_PLANNER=planner,
-               EDB_MODEL=model)
+               EDB_MODEL=model, EDB_SAMEPLAN="1")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
            f"--nproc-per-node={nproc}", "--master-addr", "127.0.0.1", "--master-port", str(port),
            os.path.join(ROOT, "tests", "ref", "auto_worker.py")]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=280, cwd=ROOT, env=env)
     line = next((l for l in r.stdout.splitlines() if l.startswith("AUTO_PARITY")), "")
     assert r.returncode == 0 and "ok=True" in line, r.stdout[-2000:] + r.stderr[-3000:]
-    # same communication structure as the reference's lowering
-    ref_hist = line.split("hist_ref=")[1].split(" hist_b200=")[0]
-    my_hist = line.split("hist_b200=")[1].rsplit(" [", 1)[0]
-    assert ref_hist == my_hist, line
+    # same communication structure as the reference's lowering OF THE VERY SAME PLAN (run A solves
+    # again and the ILP may return another equal-cost plan, so its histogram is informative only)
+    assert "same_plan_equal=True" in line, line
+
+
+@pytest.mark.parametrize("mode,port", [("b200_ddp", 29796), ("b200_zero3", 29797)])
+def test_plugin_hook_through_the_reference_decorator(mode, port):
+    """Hook A of INTEGRATION.md: `easydist_b200.api.register()` adds the modes to the reference's
+    registry (`register_parallel_method`, api.py:39-50); the REFERENCE's own `easydist_compile`
+    decorator and CompiledFuncWrapper then drive this backend's compiled object (`.graph`,
+    `.run_with_graph`, state accessors) — tests/ref/plugin_worker.py."""
+    if not os.path.isdir("/root/reference/easydist"):
+        pytest.skip("reference not present (GPU box)")
+    env = dict(os.environ, OMP_NUM_THREADS="1", EDB_PLUGIN_MODE=mode)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+           "--master-addr", "127.0.0.1", "--master-port", str(port),
+           os.path.join(ROOT, "tests", "ref", "plugin_worker.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=280, cwd=ROOT, env=env)
+    line = next((l for l in r.stdout.splitlines() if l.startswith("PLUGIN_PARITY")), "")
+    assert r.returncode == 0 and "ok=True" in line, r.stdout[-2000:] + r.stderr[-3000:]
