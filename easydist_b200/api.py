@@ -400,7 +400,8 @@ def register(reference_api=None, reference_compile_auto=None, **compile_kwargs):
         from easydist.torch.device_mesh import get_device_mesh as ref_mesh
         from .device_mesh import set_device_mesh
         mesh = set_device_mesh(ref_mesh("spmd"), rank=torch.distributed.get_rank())
-        return lowering.sharding_transform(fx_module, opt_strategy, state_io_map, mesh=mesh)
+        return lowering.sharding_transform(fx_module, opt_strategy, state_io_map, mesh=mesh,
+                                           ops=compile_kwargs.get("ops", _default_ops))
 
     reference_compile_auto.sharding_transform = sharding_transform
     return reference_api

@@ -33,12 +33,13 @@ def test_dropin_lowering_equals_reference_lowering(mesh, nproc, port, planner, m
     assert "same_plan_equal=True" in line, line
 
 
-@pytest.mark.parametrize("mode,port", [("b200_ddp", 29796), ("b200_zero3", 29797)])
+@pytest.mark.parametrize("mode,port", [("b200_ddp", 29796), ("b200_zero3", 29797), ("auto", 29798)])
 def test_plugin_hook_through_the_reference_decorator(mode, port):
     """Hook A of INTEGRATION.md: `easydist_b200.api.register()` adds the modes to the reference's
     registry (`register_parallel_method`, api.py:39-50); the REFERENCE's own `easydist_compile`
     decorator and CompiledFuncWrapper then drive this backend's compiled object (`.graph`,
-    `.run_with_graph`, state accessors) — tests/ref/plugin_worker.py."""
+    `.run_with_graph`, state accessors); "auto" = Hook B, the `sharding_transform` name rebound by
+    the same call — tests/ref/plugin_worker.py."""
     if not os.path.isdir("/root/reference/easydist"):
         pytest.skip("reference not present (GPU box)")
     env = dict(os.environ, OMP_NUM_THREADS="1", EDB_PLUGIN_MODE=mode)
