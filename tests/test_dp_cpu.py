@@ -134,16 +134,12 @@ def test_fusion_rewrite_on_cpu(defer):
         assert info["comm_nodes"].get("mm_rs") == 2, info
 
 
-def _worker(rank, world, port, mode, opt_kind, q, bucket=0, generic_bucket="0", overlap="0",
-            clip=False):
+def _run_case(rank, world, mode, opt_kind, bucket=0, generic_bucket="0", overlap="0", clip=False):
+    """One DP case inside an initialised 2-rank gloo job -> (ok, message, comm histogram)."""
     step_fn = train_step_clipped if clip else train_step
-    os.environ["OMP_NUM_THREADS"] = "1"
     os.environ["EDB_BUCKET_COMM"] = generic_bucket
     os.environ["EDB_OVERLAP"] = overlap
-    torch.set_num_threads(1)
-    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank,
-                            world_size=world)
-    from easydist_b200 import api
+    from easydist_b200 import api, lowering
     from easydist_b200.device_mesh import set_device_mesh
     from tests import gloo_ops
     set_device_mesh([list(range(world))][0], ["dp"], rank=rank)
@@ -160,7 +156,6 @@ def _worker(rank, world, port, mode, opt_kind, q, bucket=0, generic_bucket="0", 
                                bucket_numel=bucket)
     # the optimizer rewrite of the native path (on CPU the fused node takes its ATen branch): the
     # sharded update of every mode must still match vanilla
-    from easydist_b200 import lowering
     n_opt = lowering.fuse_optimizer_updates(compiled.graph)
     # zero2 updates parameter shards out of place (the new shards are all-gathered): no triple
     assert n_opt == (1 if opt_kind == "sgd" and mode != "zero2" else 0), (mode, opt_kind, n_opt)
@@ -188,25 +183,72 @@ def _worker(rank, world, port, mode, opt_kind, q, bucket=0, generic_bucket="0", 
     if overlap == "1":
         # structure of the overlap schedule: every gradient collective runs on the lane and its end
         # sits right in front of its first reader; parameter gathers start ahead of their use
-        from tests import gloo_ops as G
         nodes = list(compiled.graph.graph.nodes)
         pos = {n: i for i, n in enumerate(nodes)}
-        hist["overlap"] = compiled.info.get("overlap")
         for n in nodes:
-            if n.op == "call_function" and n.target in (G.reduce_scatter_start, G.all_reduce_start) \
+            if n.op == "call_function" and n.target in (gloo_ops.reduce_scatter_start,
+                                                        gloo_ops.all_reduce_start) \
                     and n.kwargs.get("_lane") == 1:
                 end = next(iter(n.users))
                 first = min(end.users, key=lambda u: pos[u])
                 between = nodes[pos[end] + 1:pos[first]]
-                if any(b.target not in G.COMM_SYNC_FUNCS for b in between):
+                if any(b.target not in gloo_ops.COMM_SYNC_FUNCS for b in between):
                     ok, msg = False, f"{end.name} is not sunk to its first reader"
                 hist["lane_grad"] = hist.get("lane_grad", 0) + 1
-            if n.op == "call_function" and n.target is G.all_gather_start and n.kwargs.get("_lane") == 1:
+            if n.op == "call_function" and n.target is gloo_ops.all_gather_start and \
+                    n.kwargs.get("_lane") == 1:
                 hist["lane_ag"] = hist.get("lane_ag", 0) + 1
+    return ok, msg, hist
+
+
+# every case of this file that runs the Foo MLP through a DP mode; executed once, in ONE 2-rank
+# gloo job (process start-up dominates these tests), looked up by the test functions below
+CASES = {}
+for _mode, _opt, _bucket in [("ddp", "sgd", 0), ("ddp", "sgd_plain", 0), ("zero2", "sgd", 0),
+                             ("zero3", "sgd", 0), ("zero3", "sgd_plain", 0), ("zero2", "sgd_plain", 0),
+                             ("zero3", "sgd", 100), ("zero2", "sgd", 100), ("ddp", "sgd", 100)]:
+    CASES[f"vanilla-{_mode}-{_opt}-{_bucket}"] = dict(mode=_mode, opt_kind=_opt, bucket=_bucket)
+for _mode in ("ddp", "zero3"):
+    CASES[f"generic-bucket-{_mode}"] = dict(mode=_mode, opt_kind="sgd", generic_bucket="1")
+for _mode in ("ddp", "zero2", "zero3"):
+    CASES[f"overlap-{_mode}"] = dict(mode=_mode, opt_kind="sgd", overlap="1")
+for _mode, _opt in [("ddp", "adamw_fused"), ("zero2", "adamw_fused"), ("zero3", "adam_fused"),
+                    ("zero3", "adamw_fused")]:
+    CASES[f"fused-{_mode}-{_opt}"] = dict(mode=_mode, opt_kind=_opt)
+CASES["clip-ddp"] = dict(mode="ddp", opt_kind="sgd", clip=True)
+
+
+def _batch_worker(rank, world, port, q):
+    os.environ["OMP_NUM_THREADS"] = "1"
+    torch.set_num_threads(1)
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank,
+                            world_size=world)
+    results = {}
+    for name, case in CASES.items():
+        try:
+            results[name] = _run_case(rank, world, **case)
+        except Exception as e:  # noqa: BLE001 — reported per case
+            import traceback
+            results[name] = (False, f"{type(e).__name__}: {e}\n{traceback.format_exc()[-1500:]}", {})
+        dist.barrier()
     if rank == 0:
-        q.put((ok, msg, hist))
+        q.put(results)
     dist.barrier()
     dist.destroy_process_group()
+
+
+@pytest.fixture(scope="module")
+def dp_results():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_batch_worker, args=(r, 2, 29650, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = q.get(timeout=600)
+    for p in procs:
+        p.join(60)
+    assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
+    return results
 
 
 @pytest.mark.parametrize("mode,opt_kind,bucket", [("ddp", "sgd", 0), ("ddp", "sgd_plain", 0),
@@ -214,18 +256,8 @@ def _worker(rank, world, port, mode, opt_kind, q, bucket=0, generic_bucket="0", 
                                                   ("zero3", "sgd_plain", 0), ("zero2", "sgd_plain", 0),
                                                   ("zero3", "sgd", 100), ("zero2", "sgd", 100),
                                                   ("ddp", "sgd", 100)])
-def test_dp_modes_match_vanilla(mode, opt_kind, bucket):
-    ctx = mp.get_context("spawn")
-    q = ctx.Queue()
-    port = 29650 + abs(hash((mode, opt_kind, bucket))) % 200
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, mode, opt_kind, q, bucket))
-             for r in range(2)]
-    for p in procs:
-        p.start()
-    for p in procs:
-        p.join(180)
-    assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
-    ok, msg, hist = q.get(timeout=5)
+def test_dp_modes_match_vanilla(dp_results, mode, opt_kind, bucket):
+    ok, msg, hist = dp_results[f"vanilla-{mode}-{opt_kind}-{bucket}"]
     assert ok, msg
     if mode == "ddp" and bucket == 0:
         assert hist.get("all_reduce_start", 0) == 4      # one per parameter
@@ -240,19 +272,10 @@ def test_dp_modes_match_vanilla(mode, opt_kind, bucket):
 
 
 @pytest.mark.parametrize("mode", ["ddp", "zero3"])
-def test_generic_comm_bucketing_in_dp_graphs(mode):
+def test_generic_comm_bucketing_in_dp_graphs(dp_results, mode):
     """EDB_BUCKET_COMM=1 (lowering.bucket_small_comm) on the tensor-by-tensor DP graphs: the four
     per-parameter collectives of each kind collapse into buckets and training still matches vanilla."""
-    ctx = mp.get_context("spawn")
-    q = ctx.Queue()
-    port = 29890 + (mode == "zero3")
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, mode, "sgd", q, 0, "1")) for r in range(2)]
-    for p in procs:
-        p.start()
-    for p in procs:
-        p.join(180)
-    assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
-    ok, msg, hist = q.get(timeout=5)
+    ok, msg, hist = dp_results[f"generic-bucket-{mode}"]
     assert ok, msg
     if mode == "ddp":
         assert hist.get("all_reduce_start", 0) == 1, hist   # 4 gradients, one bucket
@@ -261,20 +284,10 @@ def test_generic_comm_bucketing_in_dp_graphs(mode):
 
 
 @pytest.mark.parametrize("mode", ["ddp", "zero2", "zero3"])
-def test_overlap_schedule_keeps_results(mode):
+def test_overlap_schedule_keeps_results(dp_results, mode):
     """EDB_OVERLAP=1 (lowering.overlap_schedule): gradient collectives on the communication lane
     with deferred *_end, parameter gathers prefetched; same training results as vanilla."""
-    ctx = mp.get_context("spawn")
-    q = ctx.Queue()
-    port = 29895 + ["ddp", "zero2", "zero3"].index(mode)
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, mode, "sgd", q, 0, "0", "1"))
-             for r in range(2)]
-    for p in procs:
-        p.start()
-    for p in procs:
-        p.join(180)
-    assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
-    ok, msg, hist = q.get(timeout=5)
+    ok, msg, hist = dp_results[f"overlap-{mode}"]
     assert ok, msg
     assert hist.get("lane_grad", 0) == 4, hist           # one collective per parameter gradient
     if mode == "zero3":
@@ -283,37 +296,19 @@ def test_overlap_schedule_keeps_results(mode):
 
 @pytest.mark.parametrize("mode,opt_kind", [("ddp", "adamw_fused"), ("zero2", "adamw_fused"),
                                            ("zero3", "adam_fused"), ("zero3", "adamw_fused")])
-def test_fused_adam_in_dp_modes(mode, opt_kind):
+def test_fused_adam_in_dp_modes(dp_results, mode, opt_kind):
     """torch.optim.Adam/AdamW(fused=True) — the `_fused_adam` node the reference's DP rewrites are
     written around (compile_dp.py:55-198) — through ddp / zero2 / zero3; in ddp / zero3 the traced
     functional op + copies are re-inplaced to `_fused_adam_`.  AdamW also pins that compiling does not
     touch the parameters: the warm-up step that materialises the optimizer state runs without weight
     decay and the parameter values are restored (the reference's warm-up decays them once)."""
-    ctx = mp.get_context("spawn")
-    q = ctx.Queue()
-    port = 29920 + ["ddp", "zero2", "zero3"].index(mode) + 3 * (opt_kind == "adamw_fused")
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, mode, opt_kind, q)) for r in range(2)]
-    for p in procs:
-        p.start()
-    for p in procs:
-        p.join(180)
-    assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
-    ok, msg, hist = q.get(timeout=5)
+    ok, msg, _ = dp_results[f"fused-{mode}-{opt_kind}"]
     assert ok, msg
 
 
-def test_ddp_with_gradient_clipping_clips_the_averaged_gradients():
+def test_ddp_with_gradient_clipping_clips_the_averaged_gradients(dp_results):
     """clip_grad_norm_ between backward and the optimizer: the norm must be taken over the
     all-reduced gradients (what eager DDP does), i.e. every reader of a gradient is rewired to the
     collective's result, not only the optimizer."""
-    ctx = mp.get_context("spawn")
-    q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, 2, 29930, "ddp", "sgd", q, 0, "0", "0", True))
-             for r in range(2)]
-    for p in procs:
-        p.start()
-    for p in procs:
-        p.join(180)
-    assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
-    ok, msg, hist = q.get(timeout=5)
+    ok, msg, _ = dp_results["clip-ddp"]
     assert ok, msg
