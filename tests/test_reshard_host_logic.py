@@ -159,3 +159,34 @@ def test_product_path_has_no_cpu_fallback():
         reshard.all_gather_start(torch.ones(2, 2), 0, [0, 1])
     with pytest.raises(_lib.EdbError, match="no CPU path"):
         reshard.scatter_wrapper(torch.ones(2, 2), 2, 0, 0)
+
+
+def test_runtime_group_registry_and_lanes():
+    """Runtime.group: one C-ABI group per (lane, ranks); slots follow creation order; the lane's
+    group has the same members but its own gid / slot (flag block, op sequence)."""
+    from easydist_b200.runtime import Runtime
+
+    class Lib:
+        def __init__(self):
+            self.created = []
+
+        def edb_group_create(self, ranks, n, slot, out):
+            self.created.append(([ranks[i] for i in range(n)], slot))
+            out._obj.value = len(self.created) - 1
+            return 0
+
+        def edb_group_info(self, gid, n, me):
+            n._obj.value = len(self.created[gid][0])
+            me._obj.value = 1
+            return 0
+
+    rt = object.__new__(Runtime)
+    rt.lib, rt._groups, rt._group_meta, rt._attached = Lib(), {}, {}, True
+    g0 = rt.group([0, 1])
+    assert rt.group((0, 1)) == g0 and rt.group([0, 1], lane=0) == g0        # cached, lane 0 = default
+    g1 = rt.group([0, 1], lane=1)
+    g2 = rt.group([0, 2])
+    assert len({g0, g1, g2}) == 3
+    assert rt.lib.created == [([0, 1], 0), ([0, 1], 1), ([0, 2], 2)]
+    assert rt.group_size(g1) == 2 and rt.group_index(g1) == 1
+    assert rt.group([0, 1], lane=1) == g1
