@@ -18,9 +18,8 @@ are rank-local by construction and are sliced locally when the plan shards them.
 import contextlib
 import copy
 import logging
-import operator
 from functools import partial
-from typing import Any, Dict
+from typing import Any
 
 import torch
 import torch.utils._pytree as pytree

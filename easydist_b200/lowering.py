@@ -22,7 +22,7 @@ names and signatures (default: easydist_b200.reshard -> libedb.so).
 """
 import operator
 import os
-from typing import Dict, List, Optional
+from typing import Dict
 
 import torch
 import torch.utils._pytree as pytree

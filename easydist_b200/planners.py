@@ -9,7 +9,7 @@ Checked against the reference on 885 placement pairs through the oracle fixtures
 """
 from itertools import permutations
 
-from .metair import SPMD, R, VarSPMDStrategy
+from .metair import R, VarSPMDStrategy
 
 
 def plan_greedy(src, dst):

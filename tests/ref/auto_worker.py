@@ -74,7 +74,7 @@ def main():
     tmesh = DeviceMesh("cpu", torch.arange(world).reshape(mesh_shape), mesh_dim_names=names)
     set_device_mesh(tmesh)
 
-    from easydist_b200 import lowering, metair
+    from easydist_b200 import lowering
     from easydist_b200.device_mesh import set_device_mesh as edb_set_mesh
     from tests import gloo_ops
     my_mesh = edb_set_mesh(torch.arange(world).reshape(mesh_shape).numpy(), names, rank=rank)

@@ -72,7 +72,6 @@ def test_collectives_world1_are_identities(rt):
 
 def test_box_copy_general_strides(rt):
     """Strided N-D boxes (Partition boxes, sharding.py:427-446) vs numpy slicing."""
-    from easydist_b200 import _lib
     from easydist_b200._lib import check, i64_array
     rng = np.random.RandomState(1)
     src = rng.randint(0, 1000, size=(6, 10, 14)).astype(np.int32)

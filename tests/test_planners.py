@@ -5,7 +5,6 @@ import json
 import os
 
 import numpy as np
-import pytest
 
 from easydist_b200 import metair as M
 from easydist_b200 import planners

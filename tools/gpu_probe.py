@@ -1,9 +1,9 @@
 """First-contact probe on a B200: runtime bring-up, local reshard ops, GEMM layouts + timing.
 Run under gpurun; prints one line per check. Not a test (tests/ holds the parity tests)."""
-import sys, time, traceback
+import sys, traceback
 import torch
 sys.path.insert(0, ".")
-from easydist_b200 import runtime, reshard, gemm, _lib
+from easydist_b200 import runtime, reshard, gemm
 
 def section(name):
     print(f"\n=== {name}", flush=True)
