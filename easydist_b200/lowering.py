@@ -980,8 +980,10 @@ def fuse_collective_gemms(gm, io, rt, ranks, ops=_default_ops):
             if defer:
                 state = rt.alloc(16, align=16)
                 state.tensor(torch.int64, (2,)).zero_()
-                tok = graph.call_function(ops.mm_rs_push, args=(a, b, list(ranks)),
-                                          kwargs={"_buf": (recv.offset, state.offset)})
+                push_kw = {"_buf": (recv.offset, state.offset)}
+                if os.environ.get("EDB_RS_LANE", "0") == "1":
+                    push_kw["_lane"] = 1  # wgrad GEMM + pushes on the communication stream
+                tok = graph.call_function(ops.mm_rs_push, args=(a, b, list(ranks)), kwargs=push_kw)
                 pushed.append((tok, recv, state, M // n * N, rs_e))
                 fused = None
             else:

@@ -456,26 +456,30 @@ def mm_rs(a, b, group, *, _buf, _scale=1.0, _out_dtype=None):
     return out
 
 
-def mm_rs_push(a, b, group, *, _buf):
+def mm_rs_push(a, b, group, *, _buf, _lane=0):
     """Deferred half of mm_rs: computes a @ b and pushes every tile into its owner's receive slot
     (no waiting, no reduction).  _buf = (symmetric offset of the n receive slots, symmetric offset
     of 16 zeroed state bytes), both private to this GEMM.  Returns an empty token that `rs_finish`
-    takes so that the graph keeps the order."""
+    takes so that the graph keeps the order.  `_lane=1`: the kernel runs on the communication
+    stream (own group / op sequence), so the weight-gradient GEMM and its pushes overlap the
+    data-gradient GEMM that follows on the compute stream; rs_finish joins."""
     if _is_fake(a):
         return a.new_empty((0,))
     _require_cuda(a, "mm_rs_push")
     from . import gemm as _gemm
-    rt, gid, n, me = _group(group)
+    rt, gid, n, me = _group(group, _lane)
     M, K = a.shape
     N = b.shape[1]
     pa, pb = _gemm._prepare(a, 1), _gemm._prepare(b, 0)
     if pa is None or pb is None:
         raise _lib.EdbUnsupported(_lib.EDB_E_UNSUPPORTED, "mm_rs_push: operand layout")
     (ta, a_k, lda), (tb, b_k, ldb) = pa, pb
-    check(rt.lib.edb_gemm_rs_push_bf16(gid, int(_buf[0]), int(_buf[1]), ta.data_ptr(), tb.data_ptr(),
-                                       M, N, K, lda, ldb, 1 if a_k else 0, 1 if b_k else 0,
-                                       rt.stream()))
-    return torch.empty((0,), dtype=a.dtype, device=a.device)
+    token = torch.empty((0,), dtype=a.dtype, device=a.device)
+    with _Lane(_lane and n > 1) as lane:
+        check(rt.lib.edb_gemm_rs_push_bf16(gid, int(_buf[0]), int(_buf[1]), ta.data_ptr(),
+                                           tb.data_ptr(), M, N, K, lda, ldb, 1 if a_k else 0,
+                                           1 if b_k else 0, rt.stream()))
+    return lane.tag(token, ta, tb)
 
 
 def rs_finish(tokens, group, *, _bufs, _numels, _scale=1.0, _out_dtype=None):
@@ -485,7 +489,11 @@ def rs_finish(tokens, group, *, _bufs, _numels, _scale=1.0, _out_dtype=None):
     out_dtype = _out_dtype or torch.bfloat16
     if tokens and _is_fake(tokens[0]):
         return [tokens[0].new_empty((int(k),), dtype=out_dtype) for k in _numels]
-    rt, gid, n, me = _group(group)
+    lane_id = 1 if any(hasattr(t, "_edb_pending") for t in tokens) else 0
+    for t in tokens:
+        _join(t)  # pushes issued on the communication lane: wait for them on this stream
+    # the reduction belongs to the op sequence the pushes ran in
+    rt, gid, n, me = _group(group, lane_id)
     dev = tokens[0].device
     outs = [torch.empty((int(k),), dtype=out_dtype, device=dev) for k in _numels]
     cnt = len(outs)

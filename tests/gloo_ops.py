@@ -142,7 +142,7 @@ def mm_rs(a, b, group, *, _buf=None, _scale=1.0, _out_dtype=None):
     return out.to(_out_dtype or a.dtype)
 
 
-def mm_rs_push(a, b, group, *, _buf=None):
+def mm_rs_push(a, b, group, *, _buf=None, _lane=0):
     """CPU stand-in of reshard.mm_rs_push: the 'token' carries the partial product itself."""
     if _fake(a):
         return a.new_empty((a.shape[0], b.shape[1]))

@@ -74,6 +74,7 @@ class Wide(torch.nn.Module):
 def _fusion_worker(rank, world, port, q, defer="0"):
     os.environ["OMP_NUM_THREADS"] = "1"
     os.environ["EDB_DEFER_RS"] = defer
+    os.environ["EDB_RS_LANE"] = defer  # deferred pushes also go to the communication lane
     torch.set_num_threads(1)
     dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank,
                             world_size=world)
@@ -102,8 +103,12 @@ def _fusion_worker(rank, world, port, q, defer="0"):
         loss_all /= world
         if not torch.allclose(loss_all, ref_loss.detach().float(), rtol=3e-2, atol=1e-3):
             ok, msg = False, f"loss {loss_all} vs {ref_loss}"
+    info = dict(compiled.info)
+    info["lane_pushes"] = sum(1 for n in compiled.graph.graph.nodes
+                              if n.op == "call_function" and n.target is gloo_ops.mm_rs_push
+                              and n.kwargs.get("_lane") == 1)
     if rank == 0:
-        q.put((ok, msg, compiled.info))
+        q.put((ok, msg, info))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -130,6 +135,7 @@ def test_fusion_rewrite_on_cpu(defer):
     if defer == "1":
         assert info["comm_nodes"].get("mm_rs_push") == 2 and info["comm_nodes"].get("rs_finish") == 1, info
         assert "mm_rs" not in info["comm_nodes"], info
+        assert info["lane_pushes"] == 2, info
     else:
         assert info["comm_nodes"].get("mm_rs") == 2, info
 
