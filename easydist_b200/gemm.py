@@ -18,6 +18,7 @@ the share of native GEMMs is visible in `stats()`.
 """
 import torch
 from torch._subclasses.fake_tensor import FakeTensor
+from torch.fx.node import has_side_effect
 
 from . import _lib
 from ._lib import check, i64_array
@@ -83,7 +84,50 @@ def _prepare(t, unit_dim):
     return rowmajor, kmajor, ld
 
 
-def _launch(a, b, bias):
+class _SideStream:
+    """Second compute stream for GEMMs whose result is not needed right away (weight gradients:
+    `lowering.parallel_wgrad_gemms`, opt-in).  Two persistent GEMM kernels on two streams share the
+    SMs at CTA granularity: the 20 SMs a 128-tile GEMM leaves idle start on the other GEMM's tiles.
+    Fork = the side stream waits for the current one, join = `gemm.join` waits for the event."""
+    stream = None
+
+    def __init__(self, on):
+        self.on = bool(on)
+        self.done = None
+
+    def __enter__(self):
+        if self.on:
+            if _SideStream.stream is None:
+                _SideStream.stream = torch.cuda.Stream()
+            _SideStream.stream.wait_stream(torch.cuda.current_stream())
+            self._ctx = torch.cuda.stream(_SideStream.stream)
+            self._ctx.__enter__()
+        return self
+
+    def __exit__(self, *exc):
+        if self.on:
+            self.done = torch.cuda.Event()
+            self.done.record(_SideStream.stream)
+            self._ctx.__exit__(*exc)
+        return False
+
+
+@has_side_effect
+def join(x):
+    """Make the current stream wait for the side-stream GEMM that produces (the storage of) `x`.
+    Views taken of the result before the join carry the same pending event through `_base`."""
+    t = x
+    while t is not None:
+        pending = getattr(t, "_edb_gemm_pending", None)
+        if pending is not None:
+            torch.cuda.current_stream().wait_event(pending[0])
+            del t._edb_gemm_pending
+            break
+        t = t._base if isinstance(t, torch.Tensor) else None
+    return x
+
+
+def _launch(a, b, bias, side=0):
     pa = _prepare(a, 1)
     pb = _prepare(b, 0)
     if pa is None or pb is None:
@@ -96,9 +140,13 @@ def _launch(a, b, bias):
     if bias is not None and (N % 8 or bias.data_ptr() % 16 or not bias.is_contiguous()):
         return None
     lib = _lib.load()
-    check(lib.edb_gemm_bf16(out.data_ptr(), ta.data_ptr(), tb.data_ptr(),
-                            bias.data_ptr() if bias is not None else None, M, N, K, lda, ldb, ldc,
-                            1 if a_k else 0, 1 if b_k else 0, 0, _stream(a)))
+    # operands were staged and the output allocated on the caller's stream; only the kernel forks
+    with _SideStream(side) as fork:
+        check(lib.edb_gemm_bf16(out.data_ptr(), ta.data_ptr(), tb.data_ptr(),
+                                bias.data_ptr() if bias is not None else None, M, N, K, lda, ldb,
+                                ldc, 1 if a_k else 0, 1 if b_k else 0, 0, _stream(a)))
+    if fork.on:
+        out._edb_gemm_pending = (fork.done, (ta, tb))
     _stats["edb_gemm"] += 1
     if len(_calls) < 8192:
         _calls.append((M, N, K, bool(a_k), bool(b_k), tuple(a.stride()), tuple(b.stride())))
@@ -116,11 +164,12 @@ def _count_unsupported(a, b):
     _stats["aten_mm"] += 1
 
 
-def mm(a, b):
-    """aten.mm.default(a, b) with bf16 operands on the tcgen05 kernel."""
+def mm(a, b, *, _side=0):
+    """aten.mm.default(a, b) with bf16 operands on the tcgen05 kernel.  `_side=1`: launched on the
+    side stream; some later `join` of the result (or of a view of it) must precede its first use."""
     if isinstance(a, FakeTensor) or isinstance(b, FakeTensor) or a.is_meta:
         return torch.ops.aten.mm.default(a, b)
-    out = _launch(a, b, None) if _eligible(a, b) else None
+    out = _launch(a, b, None, _side) if _eligible(a, b) else None
     if out is None:
         _count_unsupported(a, b)
         return torch.ops.aten.mm.default(a, b)
