@@ -372,6 +372,8 @@ def box_exchange(tensor, dst_shape, boxes, peer_src_shapes, group, *, _buf=None)
 
     `boxes`: list of (member_index, src_start, dst_start, extents) for THIS rank's destination;
     `peer_src_shapes`: source-partition shape of every group member."""
+    if _is_fake(tensor):
+        return tensor.new_empty([int(s) for s in dst_shape])
     _require_cuda(tensor, "box_exchange")
     rt, gid, n, me = _group(group)
     x = tensor.contiguous()
