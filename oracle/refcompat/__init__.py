@@ -98,7 +98,7 @@ def _post_import_patches():
     def create_meta_from_node(node):
         try:
             return orig_meta(node)
-        except RuntimeError as e:
+        except (RuntimeError, ValueError) as e:  # utils.py:57-65 re-raises as ValueError(msg)
             aten = torch.ops.aten
             if node.target in (aten.view.default, aten._unsafe_view.default) and \
                     "view" in str(e).lower():
