@@ -44,6 +44,8 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-seqs", type=int, default=2)
     ap.add_argument("--heap-gb", type=float, default=12.0)
+    ap.add_argument("--no-parity", action="store_true",
+                    help="skip the pre-timing parity leg (compiled N-GPU steps vs vanilla fp32)")
     return ap.parse_args()
 
 
@@ -102,7 +104,7 @@ class ClockSampler:
 # ---- the reference arm / cpu baseline: oracle port on host cores ------------------------------------
 
 
-def cpu_train_step_throughput(args, n_seqs, steps=1):
+def cpu_train_step_throughput(args, n_seqs, steps=1, warmup=0):
     """The reference's path on CPU is ATen-CPU compute + gloo collectives driven by the FX graph
     (SURVEY.md §8d).  The oracle port runs the same train step (same model, fp32 on CPU — the
     reference's CPU runs are fp32) on the host cores; at world 1 there is no collective."""
@@ -116,21 +118,30 @@ def cpu_train_step_throughput(args, n_seqs, steps=1):
     # 128 threads: measured 88 s/step with 128 threads vs 4 s with 8 for the same sequence
     cores = max(1, min(avail, int(os.environ.get("EDB_CPU_THREADS", "32"))))
     torch.set_num_threads(cores)
-    t, loss = train_oracle.time_cpu_train_step(args.model, args.attn, n_seqs, args.seq, steps)
+    t, loss = train_oracle.time_cpu_train_step(args.model, args.attn, n_seqs, args.seq, steps,
+                                               warmup=warmup)
     return {"value": n_seqs * steps / t, "unit": "samples/s", "cores": cores, "kind": "port",
-            "sample": f"{steps} step(s) of {n_seqs} x {args.seq}-token sequences, fp32, "
-                      f"torch CPU eager ({cores} threads), {t:.1f} s", "loss": loss}
+            "sample": f"{steps} timed step(s) (+{warmup} warm-up) of {n_seqs} x {args.seq}-token "
+                      f"sequences each (bounded sample of the {args.batch_per_gpu}-sequence "
+                      f"per-GPU batch), fp32, torch CPU eager, single process ({cores} threads), "
+                      f"{t:.1f} s", "loss": loss, "seconds": t}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    base = cpu_train_step_throughput(args, args.cpu_sample_seqs, steps=max(1, min(args.steps, 2)))
+    # exactly --warmup untimed and --steps timed steps, each a bounded sample (--cpu-sample-seqs
+    # sequences) of the per-GPU batch: ~2 s per step on 32 threads, so the default 20 + 5 steps end
+    # within about a minute.  At N > 1 this is still ONE process on rank 0's host cores (the
+    # reference itself cannot travel to the GPU box).
+    base = cpu_train_step_throughput(args, args.cpu_sample_seqs, steps=max(1, args.steps),
+                                     warmup=max(0, args.warmup))
     line = {
         "impl": "reference", "metric": "train_step_throughput", "value": base["value"],
-        "unit": "samples/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": 1e3 * args.cpu_sample_seqs / base["value"], "higher_is_better": True,
+        "unit": "samples/s", "n_gpus": args.gpus, "steps": max(1, args.steps),
+        "warmup": max(0, args.warmup),
+        "ms_per_step": 1e3 * base["seconds"] / max(1, args.steps), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args, args.gpus),
         "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
@@ -152,12 +163,12 @@ def workload_config(args, world):
 # ---- this backend -----------------------------------------------------------------------------------------
 
 
-def gemm_roofline(torch, gemm, calls, peaks, sustained):
+def gemm_roofline(torch, gemm, calls, peaks, sustained, fused_calls=(), rank=0):
     """Dominant kernel = the tcgen05 GEMM.  Replays the step's GEMM launches (exact shapes, operand
     layouts and strides recorded from the compiled graph) back to back from a CUDA graph with CUDA
     events around the whole list on the launching stream; operands of consecutive launches differ
     and sum to far more than L2.  achieved = algorithmic FLOPs (2*M*N*K per launch) / measured time."""
-    if not calls:
+    if not calls and not fused_calls:
         return None
     ops = []
     flops = 0
@@ -168,8 +179,36 @@ def gemm_roofline(torch, gemm, calls, peaks, sustained):
         b = torch.empty_strided((K, N), b_stride, device="cuda", dtype=torch.bfloat16).normal_()
         ops.append((a, b))
         flops += 2 * M * N * K
+    # the fused collective GEMMs of the step (N > 1): the REAL kernels, replayed with their real
+    # symmetric buffers on every rank at once — epoch-mode AG+GEMM pulls the peers' (static) weight
+    # shards, the push GEMM stores into the peers' receive slots (scratch between steps), neither
+    # needs a handshake, so the replay carries the step's NVLink traffic
+    from easydist_b200 import reshard, runtime as _rtm
+    from easydist_b200.runtime import SymmBuffer
+    fused_ops = []
+    for c in fused_calls:
+        M, N, K = c["M"], c["N"], c["K"]
+        if c["kind"] == "ag":
+            x = torch.empty_strided((M, K), c["a_stride"], device="cuda", dtype=torch.bfloat16).normal_()
+            n = len(c["group"])
+            w = SymmBuffer(_rtm.get_runtime(), c["buf"][0], N // n * K * 2).tensor(torch.bfloat16, (N // n, K))
+            fused_ops.append(("ag", x, w, c))
+        else:
+            a = torch.empty_strided((M, K), c["a_stride"], device="cuda", dtype=torch.bfloat16).normal_()
+            b = torch.empty_strided((K, N), c["b_stride"], device="cuda", dtype=torch.bfloat16).normal_()
+            fused_ops.append(("push", a, b, c))
+        flops += 2 * M * N * K
+
+    def run_fused():
+        for kind, u, v, c in fused_ops:
+            if kind == "ag":
+                reshard.ag_mm(u, v, c["group"], c["N"], c["K"], None, _buf=c["buf"], _epoch=1)
+            else:
+                reshard.mm_push(u, v, c["group"], _buf=c["buf"])
+
     for a, b in ops:
         gemm.mm(a, b)
+    run_fused()
     torch.cuda.synchronize()
     # replayed from a CUDA graph like the step itself: eager launches of 30-us kernels would measure
     # the host (ctypes + tensor-map encode per call), not the kernel
@@ -181,6 +220,8 @@ def gemm_roofline(torch, gemm, calls, peaks, sustained):
             with torch.cuda.graph(graph, stream=side):
                 for a, b in ops:
                     mm(a, b)
+                if mm is gemm.mm:
+                    run_fused()
             graph.replay()
             side.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -195,21 +236,93 @@ def gemm_roofline(torch, gemm, calls, peaks, sustained):
 
     ms = graph_ms(gemm.mm)
     achieved = flops / ms / 1e9  # TFLOP/s
-    # context only: what cuBLAS reaches on the very same list of GEMMs (same operands, same
-    # graph replay); shapes cuBLAS cannot align (LM head, vocab 50257) hit its sm_75-class
-    # `align1` kernels
-    for a, b in ops:
-        torch.mm(a, b)
-    torch.cuda.synchronize()
-    cublas_tf = flops / graph_ms(torch.mm) / 1e9
+    n_launch = len(calls) + len(fused_ops)
+    # context only: what cuBLAS reaches on the plain GEMMs of the list (same operands, same graph
+    # replay); shapes cuBLAS cannot align (LM head, vocab 50257) hit its sm_75-class `align1` kernels
+    cublas_tf = None
+    if ops and not fused_ops:
+        for a, b in ops:
+            torch.mm(a, b)
+        torch.cuda.synchronize()
+        cublas_tf = flops / graph_ms(torch.mm) / 1e9
+    # the replay is a ~10-20 ms burst timed on its own, so the burst peak is the denominator
+    # (the sustained figure is reported beside it)
     peak = peaks["bf16_tflops_sustained"] if sustained else peaks["bf16_tflops"]
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r02_gemm_dram_traffic.json")
+    if os.path.exists(tpath) and not fused_ops:
+        with open(tpath) as f:
+            traffic = json.load(f)
     return {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-            "frac": achieved / peak, "traffic": None, "kernel": "edb::k_gemm_bf16",
-            "launches_per_step": len(calls), "avg_launch_us": 1e3 * ms / len(calls),
+            "frac": achieved / peak, "frac_of_sustained_peak": achieved / peaks["bf16_tflops_sustained"],
+            "traffic": (traffic or {}).get("dram_bytes_per_launch"),
+            "traffic_algorithmic_bytes_per_launch": (traffic or {}).get("algorithmic_bytes_per_launch"),
+            "traffic_source": (traffic or {}).get("source"),
+            "kernel": "edb::k_gemm_bf16 (plain" + (", AG-fused and push-fused" if fused_ops else "") + ")",
+            "launches_per_step": n_launch, "fused_launches_per_step": len(fused_ops),
+            "avg_launch_us": 1e3 * ms / n_launch,
             "gemm_ms_per_step": ms, "flops_per_step": flops,
             "cublas_same_launch_list_tflops": cublas_tf,
-            "peak_source": peaks["source"] + (", sustained figure (kernel runs inside a long step)"
-                                              if sustained else ", burst figure")}
+            "peak_source": peaks["source"] + (", sustained figure" if sustained else
+                                              ", burst figure (the launch list is replayed on its own)")}
+
+
+def parity_leg(torch, dist, args, cfg, GPT2, step_fn, model, opt, state0, par_host, first_loss,
+               rank, world):
+    """Pre-timing parity (outside every timed region): the compiled N-GPU train step against
+    vanilla fp32 PyTorch on the same global batches — loss of every step, EVERY parameter and
+    EVERY momentum buffer (the reference's comparator, tests/test_torch/test_spmd.py:97-113).
+    The first compiled call already ran the first batch twice (eager warm-up + first CUDA-graph
+    replay, the same as the reference's wrapper, api.py:183-222), so the vanilla run does too."""
+    from tools import parity as P
+    B, S = args.batch_per_gpu, args.seq
+    n_par = len(par_host)
+    losses = [first_loss]
+    for b in range(1, n_par):
+        t, y = par_host[b][rank]
+        losses.append(float(step_fn(t.cuda(), y.cuda(), model, opt)))
+    torch.cuda.synchronize()
+    graph_on = not args.no_cuda_graph
+    sched = ([0, 0] if graph_on else [0]) + list(range(1, n_par))
+    steps = [par_host[b] for b in sched]
+    mk_opt = lambda ps: torch.optim.SGD(ps, lr=1e-3, momentum=0.9, foreach=True)
+    ref_losses, ref_p, ref_s = P.vanilla_run(lambda: GPT2(cfg), state0, steps, mk_opt,
+                                             torch.float32, "cuda")
+    van_losses, van_p, van_s = P.vanilla_run(lambda: GPT2(cfg), state0, steps, mk_opt,
+                                             torch.bfloat16, "cuda")
+    got_p, got_s = P.compiled_state(step_fn.compiled_func, ref_p, ref_s, world)
+    ours = P.compare(got_p, got_s, ref_p, ref_s, low_precision=True)
+    van = P.compare({k: v.to(torch.bfloat16) for k, v in van_p.items()},
+                    {k: {kk: vv.to(torch.bfloat16) for kk, vv in st.items()} for k, st in van_s.items()},
+                    ref_p, ref_s, low_precision=True)
+    # our losses are the local (per-rank) means of each call; with a CUDA graph the first call
+    # returns the loss of its replay = the second vanilla step on batch 0
+    idx = [1 if graph_on else 0] + list(range(2 if graph_on else 1, len(sched)))
+    loss_rel = max(abs(l - ref_losses[i][rank]) / abs(ref_losses[i][rank])
+                   for l, i in zip(losses, idx))
+    van_loss_rel = max(abs(van_losses[i][rank] - ref_losses[i][rank]) / abs(ref_losses[i][rank])
+                       for i in idx)
+    tol_state = max(2e-2, 2.0 * van["state_rel_l2"])
+    tol_ulp = max(2.0, 2.0 * van["param_max_ulp"])
+    ok = loss_rel <= 2e-2 and ours["state_rel_l2"] <= tol_state and ours["param_max_ulp"] <= tol_ulp
+    res = {"ok": bool(ok), "checks": ours["checks"] + len(losses),
+           "max_rel_err": max(ours["state_rel_l2"], loss_rel),
+           "loss_rel_err": loss_rel, "momentum_rel_l2": ours["state_rel_l2"],
+           "param_max_bf16_ulp": ours["param_max_ulp"], "worst": ours["worst"],
+           "vanilla_bf16_vs_fp32": {"loss_rel_err": van_loss_rel, "momentum_rel_l2": van["state_rel_l2"],
+                                    "param_max_bf16_ulp": van["param_max_ulp"]},
+           "tolerance": {"loss_rel": 2e-2, "momentum_rel_l2": tol_state, "param_bf16_ulp": tol_ulp},
+           "what": f"{len(sched)} optimisation steps ({n_par} calls) of the compiled {world}-GPU "
+                   f"{args.mode} step vs vanilla fp32 PyTorch on the same global batches: loss per "
+                   "call, every parameter, every momentum buffer"}
+    if world > 1:
+        flags = torch.tensor([0.0 if ok else 1.0, res["max_rel_err"], res["param_max_bf16_ulp"]],
+                             device="cuda")
+        dist.all_reduce(flags, op=dist.ReduceOp.MAX)
+        res["ok"] = bool(flags[0].item() == 0.0)
+        res["max_rel_err"] = flags[1].item()
+        res["param_max_bf16_ulp"] = flags[2].item()
+    return res
 
 
 def run_edb(args):
@@ -242,10 +355,17 @@ def run_edb(args):
     dev = [(t.cuda(), y.cuda()) for t, y in host]
     step_fn = easydist_compile(gpt2_train_step, parallel_mode=args.mode, tracing_mode="fake",
                                cuda_graph=not args.no_cuda_graph, fuse=not args.no_fuse)
+    state0 = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    # parity batches: one per (step, rank); every rank can rebuild all of them for the reference
+    n_par = 3
+    par_host = [[synthetic_tokens(cfg, B, S, seed=7000 + 1000 * b + r) for r in range(world)]
+                for b in range(n_par)]
+    first = par_host[0][rank] if not args.no_parity else host[0]
+    first = (first[0].cuda(), first[1].cuda())
     launches0 = rt.launch_count()
     gemm.reset_stats()
     t0 = time.time()
-    loss = step_fn(dev[0][0], dev[0][1], model, opt)  # compile + eager warm-up (+ graph capture)
+    loss = step_fn(first[0], first[1], model, opt)  # compile + eager warm-up (+ graph capture)
     torch.cuda.synchronize()
     compile_s = time.time() - t0
     info = step_fn.compiled_func.info
@@ -283,6 +403,10 @@ def run_edb(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return ms.item(), float(last)
 
+    parity = None
+    if not args.no_parity:
+        parity = parity_leg(torch, dist, args, cfg, GPT2, step_fn, model, opt, state0, par_host,
+                            float(loss), rank, world)
     for _ in range(max(3, args.warmup)):
         step_fn(dev[0][0], dev[0][1], model, opt)
     sampler = ClockSampler(local)
@@ -300,7 +424,13 @@ def run_edb(args):
     peaks = measured_peaks()
     # GEMM shapes of one step, recorded by the dispatcher during the eager warm-up
     calls = gemm.recorded_calls()[:gemm_calls_per_step]
-    roof = gemm_roofline(torch, gemm, calls, peaks, sustained=True) if rank == 0 else None
+    fused_all = gemm.recorded_fused_calls()
+    fused_calls = fused_all[:len(fused_all) // passes]
+    # every rank replays (the fused kernels talk to the peers); rank 0 reports
+    barrier()
+    roof = gemm_roofline(torch, gemm, calls, peaks, sustained=False, fused_calls=fused_calls,
+                         rank=rank)
+    barrier()
     step_flops = train_flops_per_step(cfg, B, S)
     line = {
         "metric": "train_step_throughput", "value": value, "unit": "samples/s", "n_gpus": world,
@@ -319,6 +449,8 @@ def run_edb(args):
                      "symm_bytes": info.get("symm_bytes")},
         "clocks": clocks, "loss": loss_v, "compile_s": compile_s,
     }
+    if parity is not None:
+        line["parity"] = parity
     if roof:
         roof["share_of_step"] = roof["gemm_ms_per_step"] / ms_per_step
         line["roofline"] = roof
@@ -333,6 +465,8 @@ def run_edb(args):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    if parity is not None and not parity["ok"]:
+        raise SystemExit("parity leg failed: " + json.dumps(parity))
 
 
 def main():

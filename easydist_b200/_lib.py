@@ -38,6 +38,7 @@ SIGNATURES = {
     "edb_init": (c_int, [c_int, c_int, c_int, c_size_t]),
     "edb_finalize": (c_int, []),
     "edb_is_initialized": (c_int, []),
+    "edb_health": (c_int, []),
     "edb_heap_info": (c_int, [POINTER(c_void_p), POINTER(c_size_t), POINTER(c_size_t)]),
     "edb_ipc_export": (c_int, [c_void_p]),
     "edb_ipc_attach": (c_int, [c_int, c_void_p]),
@@ -75,6 +76,13 @@ SIGNATURES = {
                                       c_int64, c_int64, c_int64, c_int, c_int, c_void_p]),
     "edb_rs_finish": (c_int, [c_int, c_int, c_void_p, c_void_p, c_void_p, _I64P, c_float, c_int,
                               c_void_p]),
+    "edb_epoch_barrier": (c_int, [c_int, c_void_p]),
+    "edb_ag_gemm_epoch_bf16": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_uint64, c_uint64,
+                                       c_int64, c_int64, c_int64, c_int64, c_int64, c_void_p]),
+    "edb_gemm_push_bf16": (c_int, [c_int, c_uint64, c_void_p, c_void_p, c_int64, c_int64, c_int64,
+                                   c_int64, c_int64, c_int, c_int, c_void_p]),
+    "edb_rs_finish_local": (c_int, [c_int, c_int, c_void_p, c_void_p, _I64P, c_float, c_int,
+                                    c_void_p]),
     "edb_layer_norm_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                    c_int64, c_int64, c_float, c_int, c_void_p]),
     "edb_layer_norm_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,

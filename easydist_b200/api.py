@@ -150,6 +150,11 @@ def _compile_dp(func, parallel_mode, tracing_mode, args, kwargs, *, ops=_default
     info = _finish(gm, params, buffers, named_states, args, kwargs, ops, native, io=io,
                    ranks=ranks, fuse=fuse, fuse_rt=fuse_rt)
     info.update(mode=mode, dp_size=n)
+    if native and n > 1:
+        # nobody enters the first step (peer waits have a fatal timeout) before everybody has
+        # finished compiling and re-homing its parameter shards into the symmetric heap
+        from .runtime import get_runtime
+        get_runtime().host_barrier()
 
     def mono_compiler(compiled, a, kw):
         """Same rewrite for another input shape, lowered against the live (sharded) state.  The
@@ -204,6 +209,10 @@ def _lower_auto(gm, plan, state_io_map, params, buffers, named_states, args, kwa
     largs, lkwargs = input_transform(args, kwargs)
     info = _finish(gm, params, buffers, named_states, largs, lkwargs, ops, native)
     info.update(mode="auto", mesh=mesh.shape)
+    if native:
+        from .runtime import get_runtime, is_initialized
+        if is_initialized():
+            get_runtime().host_barrier()
     return EDCompiledFunc(gm, params, buffers, named_states, input_transform=input_transform,
                           info=info)
 
@@ -358,6 +367,8 @@ class CompiledFuncWrapper:
             for dst, src in zip(space["cuda_graph_input"], flat):
                 if isinstance(dst, torch.Tensor):
                     dst.copy_(src, non_blocking=True)
+        from .compile import _check_health
+        _check_health()  # replay launches nothing of ours on the host: check the error record here
         space["cuda_graph"].replay()
         return space["cuda_graph_output"]
 

@@ -57,15 +57,34 @@ def needs_build():
 
 
 def build(force=False, verbose=False):
-    """Compile every .cu under csrc/ and link libedb.so. Returns the library path."""
+    """Compile every .cu under csrc/ and link libedb.so. Returns the library path.
+
+    Safe under torchrun (N ranks importing at once): the build is serialised with an exclusive
+    file lock and re-checked under the lock, objects go to a private temporary directory, and the
+    library and its stamp are moved into place with os.replace (atomic), so no rank can link
+    against half-written objects or dlopen a half-written .so."""
     if not force and not needs_build():
         return LIB_PATH
+    import fcntl
+    os.makedirs(BUILD_DIR, exist_ok=True)
+    with open(os.path.join(BUILD_DIR, ".lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not needs_build():
+                return LIB_PATH  # another process built it while we waited
+            return _build_locked(verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(verbose):
+    import tempfile
     nvcc = _nvcc()
     if nvcc is None:
         raise RuntimeError("nvcc not found: cannot build libedb.so")
-    os.makedirs(BUILD_DIR, exist_ok=True)
     srcs = sources()
-    objs = [os.path.join(BUILD_DIR, os.path.basename(s)[:-3] + ".o") for s in srcs]
+    tmp = tempfile.mkdtemp(prefix="tmp_", dir=BUILD_DIR)
+    objs = [os.path.join(tmp, os.path.basename(s)[:-3] + ".o") for s in srcs]
 
     def compile_one(args):
         src, obj = args
@@ -81,13 +100,18 @@ def build(force=False, verbose=False):
         logs = list(ex.map(compile_one, zip(srcs, objs)))
     if verbose:
         sys.stderr.write("\n".join(logs))
-    cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB_PATH, *objs]
+    tmp_lib = os.path.join(tmp, "libedb.so")
+    cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", tmp_lib, *objs]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
     deps = srcs + [os.path.join(CSRC, h) for h in HEADERS] + [os.path.join(INCLUDE, "edb.h")]
-    with open(os.path.join(BUILD_DIR, "stamp"), "w") as f:
+    tmp_stamp = os.path.join(tmp, "stamp")
+    with open(tmp_stamp, "w") as f:
         f.write(_digest(deps))
+    os.replace(tmp_lib, LIB_PATH)
+    os.replace(tmp_stamp, os.path.join(BUILD_DIR, "stamp"))
+    shutil.rmtree(tmp, ignore_errors=True)
     return LIB_PATH
 
 

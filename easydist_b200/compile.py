@@ -318,6 +318,15 @@ class GraphIO:
 # ---- executor -----------------------------------------------------------------------------------------------
 
 
+def _check_health():
+    """A collective that timed out on a peer traps its kernel (edb_internal.cuh fatal_timeout); the
+    next step must raise instead of training on (the reference's NCCL watchdog aborts the process).
+    Reads one word of pinned host memory: no synchronisation, no device access."""
+    from . import runtime
+    if runtime.is_initialized():
+        runtime.get_runtime().health()
+
+
 class EDCompiledFunc:
     """Runs the lowered graph; same surface as the reference's EDCompiledFunc
     (compile_auto.py:720-815 / compile_dp.py:346-381)."""
@@ -334,6 +343,7 @@ class EDCompiledFunc:
 
     @torch.no_grad()
     def compiled_func(self, graph, *args, **kwargs):
+        _check_health()
         if self._input_transform is not None:
             args, kwargs = self._input_transform(args, kwargs)
         params, buffers, named_states, grads, out = graph(self._params, self._buffers,

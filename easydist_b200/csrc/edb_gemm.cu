@@ -283,6 +283,10 @@ struct GemmParams {
   int splits, kb_per_split;
   float* partial;
   int64_t ldp;
+  // push mode (MODE_PLAIN, edb_gemm_push_bf16): row block m of C belongs to group member
+  // m / push_mtc and is TMA-stored into that member's receive slot (store map cm.m[owner]) instead
+  // of C; m_rot rotates the m order so that the ranks do not all push to the same owner at once
+  int push_n, push_mtc, m_rot;
 };
 
 // Fusion modes of the GEMM kernel
@@ -320,6 +324,10 @@ struct FusedArgs {
   // number of that reduction, which guards the slots against the next step's pushes)
   int rs_defer;
   uint64_t* rs_state;
+  // epoch mode (edb_ag_gemm_epoch_bf16): no handshake with the peers inside the kernel — an
+  // edb_epoch_barrier earlier on the stream made every member's shard final, and the next barrier
+  // comes before anybody overwrites it.  Only the local chunk flags (comm CTAs -> MMA CTAs) remain.
+  int epoch;
 };
 constexpr int F_PUSHED = F_CHUNK + 8;  // [40..47] PUSHED[p]: peer p's deferred-RS tiles of op q landed
 
@@ -346,7 +354,7 @@ __device__ __forceinline__ void tile_coords(int t, const GemmParams& p, const Fu
     n_blk = w / mtc;
   } else {
     chunk = 0;
-    m_blk = t % p.m_tiles;
+    m_blk = (t % p.m_tiles + p.m_rot) % p.m_tiles;
     n_blk = t / p.m_tiles;
   }
 }
@@ -392,7 +400,9 @@ __device__ __forceinline__ void ag_comm_role(const FusedArgs& fa, uint8_t* smem,
   }
   __syncthreads();
   if (threadIdx.x != 0) return;
-  if (comm_idx == 0) {
+  const bool epoch = fa.epoch != 0;
+  const int w_chunk = epoch ? F_AGCHUNK : F_CHUNK, w_tile = epoch ? F_AGTILE : F_TILECNT;
+  if (comm_idx == 0 && !epoch) {
     // my shard was written by earlier kernels of this stream: publish it
     __threadfence_system();
     for (int pidx = 0; pidx < f.n; ++pidx)
@@ -405,7 +415,7 @@ __device__ __forceinline__ void ag_comm_role(const FusedArgs& fa, uint8_t* smem,
   const int64_t nblk = hi > lo ? (hi - lo + SLOT - 1) / SLOT : 0;
   for (int k = 0; k < f.n; ++k) {
     const int c = (f.me + k) % f.n;
-    if (c != f.me) spin_wait_sys(f.local + F_READY + c, q, f.timeout_ns, f.local + F_ERR);
+    if (c != f.me && !epoch) spin_wait_sys(f.local + F_READY + c, q, f.timeout_ns, f.local + F_ERR);
     const char* src = fa.shard_src[c] + lo;
     char* dst = fa.full_dst + (int64_t)c * fa.shard_bytes + lo;
     for (int64_t i = 0; i < nblk + D; ++i) {
@@ -433,12 +443,24 @@ __device__ __forceinline__ void ag_comm_role(const FusedArgs& fa, uint8_t* smem,
     fence_proxy_async_all();
     __threadfence();
     const unsigned long long prev =
-        atomicAdd(reinterpret_cast<unsigned long long*>(f.local + F_TILECNT + c), 1ULL);
+        atomicAdd(reinterpret_cast<unsigned long long*>(f.local + w_tile + c), 1ULL);
     if (prev == (unsigned long long)fa.n_comm - 1) {
-      f.local[F_TILECNT + c] = 0;
+      f.local[w_tile + c] = 0;
       __threadfence();
-      st_release_gpu(f.local + F_CHUNK + c, q);
+      st_release_gpu(f.local + w_chunk + c, q);
     }
+  }
+  if (epoch) {
+    // advance the launch number once every CTA of this launch has read the old one
+    const unsigned long long prev =
+        atomicAdd(reinterpret_cast<unsigned long long*>(f.local + F_AGDONE), 1ULL);
+    if (prev == (unsigned long long)fa.n_comm - 1) {
+      f.local[F_AGDONE] = 0;
+      while (ld_acquire_gpu(f.local + F_AGCNT) < (uint64_t)gridDim.x) __nanosleep(64);
+      f.local[F_AGCNT] = 0;
+      st_release_gpu(f.local + F_AGSEQ, q);
+    }
+    return;
   }
   // end of the op: DONE to the peers, SEQ locally — but only after every CTA of this launch has
   // read the old SEQ (slow starters would otherwise compute the wrong op number)
@@ -563,16 +585,19 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
     }
   } else if (MODE == MODE_AG) {
     if (threadIdx.x == 0) {
-      s_q = ld_relaxed_gpu(fa.f.local + F_SEQ) + 1;
-      atomicAdd(reinterpret_cast<unsigned long long*>(fa.f.local + F_CNT_C), 1ULL);
+      s_q = ld_relaxed_gpu(fa.f.local + (fa.epoch ? F_AGSEQ : F_SEQ)) + 1;
+      atomicAdd(reinterpret_cast<unsigned long long*>(fa.f.local + (fa.epoch ? F_AGCNT : F_CNT_C)), 1ULL);
     }
     __syncthreads();
     q = s_q;
-    if ((int)blockIdx.x >= n_gemm_ctas) {
-      ag_comm_role(fa, smem, (int)blockIdx.x - n_gemm_ctas, q);
+    // the comm CTAs are the producers the MMA CTAs spin on: they get the LOWEST block indices so
+    // that they are scheduled first even when the grid is not fully co-resident
+    if ((int)blockIdx.x < fa.n_comm) {
+      ag_comm_role(fa, smem, (int)blockIdx.x, q);
       return;
     }
   }
+  const int cta = (MODE == MODE_AG) ? (int)blockIdx.x - fa.n_comm : (int)blockIdx.x;
 
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + kStages * kSmemABytes;
@@ -592,7 +617,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
   const int pm_tiles = (CL == 2) ? (p.m_tiles + 1) / 2 : p.m_tiles;
   const int num_tiles = pm_tiles * p.n_tiles;
   const int num_units = (MODE == MODE_PLAIN) ? num_tiles * p.splits : num_tiles;
-  const int unit0 = (CL == 2) ? (int)blockIdx.x / 2 : (int)blockIdx.x;
+  const int unit0 = (CL == 2) ? cta / 2 : cta;
   const int unit_stride = (CL == 2) ? n_gemm_ctas / 2 : n_gemm_ctas;
 
   if (warp == 0 && lane == 0) {
@@ -638,7 +663,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
         int m_blk, n_blk, chunk;
         if (CL == 2) {
           chunk = 0;
-          m_blk = 2 * (t % pm_tiles) + crank;
+          m_blk = 2 * ((t % pm_tiles + p.m_rot) % pm_tiles) + crank;
           n_blk = t / pm_tiles;
         } else {
           tile_coords<MODE>(t, p, fa, m_blk, n_blk, chunk);
@@ -651,7 +676,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
             bmap = &cm.m[0];  // entirely inside my own shard: no transfer needed
             b_row = n_blk * BN - fa.f.me * fa.ag_rows;
           } else if (n_blk != ready_chunk) {
-            for (int c = c_lo; c <= c_hi; ++c) spin_wait_gpu(fa.f.local + F_CHUNK + c, q);
+            for (int c = c_lo; c <= c_hi; ++c)
+              spin_wait_gpu(fa.f.local + (fa.epoch ? F_AGCHUNK : F_CHUNK) + c, q);
             fence_proxy_async_all();
             ready_chunk = n_blk;
           }
@@ -775,7 +801,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
       int m_blk, n_blk, chunk;
       if (CL == 2) {
         chunk = 0;
-        m_blk = 2 * (t % pm_tiles) + crank;
+        m_blk = 2 * ((t % pm_tiles + p.m_rot) % pm_tiles) + crank;
         n_blk = t / pm_tiles;
       } else {
         tile_coords<MODE>(t, p, fa, m_blk, n_blk, chunk);
@@ -824,6 +850,11 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
       if (MODE == MODE_RS) {
         cmap = &cm.m[chunk];  // receive slot [me] of the rank that owns these rows
         c_row = (m_blk - chunk * (p.m_tiles / fa.f.n)) * BM;
+      }
+      if (MODE == MODE_PLAIN && p.push_n > 0) {
+        const int owner = m_blk / p.push_mtc;
+        cmap = &cm.m[owner];
+        c_row = (m_blk - owner * p.push_mtc) * BM;
       }
       mbar_wait(&tmem_full[as], aphase);
       tcgen05_fence_after();
@@ -905,7 +936,15 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
         aphase ^= 1;
       }
     }
-    if (issuer) tma_store_wait_all();
+    if (issuer) {
+      tma_store_wait_all();
+      if (MODE == MODE_PLAIN && p.push_n > 0) {
+        // the tiles went into peer memory: make them visible system-wide before this CTA retires
+        // (the next edb_epoch_barrier on the stream then orders them before its signal)
+        fence_proxy_async_all();
+        __threadfence_system();
+      }
+    }
   }
 
   tcgen05_fence_before();
@@ -947,6 +986,7 @@ struct RsFinishItem {
 };
 struct RsFinishDesc {
   FlagCtx f;
+  int local_only;  // epoch mode: an edb_epoch_barrier earlier on the stream replaced every handshake
   int n_items;
   float scale;
   int out_dtype;
@@ -964,6 +1004,7 @@ __global__ void __launch_bounds__(kRsFinishThreads)
     s_need = 0;
   }
   __syncthreads();
+  if (!d.local_only) {
   // every source must have landed its tiles of the latest push among the items (flags are
   // monotonic and a source's pushes complete in stream order, so the latest covers the earlier)
   unsigned long long need = 0;
@@ -976,6 +1017,7 @@ __global__ void __launch_bounds__(kRsFinishThreads)
   if ((int)threadIdx.x < d.f.n)
     spin_wait_sys(d.f.local + F_PUSHED + threadIdx.x, s_need, d.f.timeout_ns, d.f.local + F_ERR);
   __syncthreads();
+  }
   const uint64_t q = s_q;
   const int total_units = d.first_unit[d.n_items];
   const int n = d.f.n;
@@ -1032,6 +1074,7 @@ __global__ void __launch_bounds__(kRsFinishThreads)
       }
     }
   }
+  if (d.local_only) return;
   // remember which op reduced these slots (the next pushes check the owners' DONE against it)
   if (blockIdx.x == 0)
     for (int i = threadIdx.x; i < d.n_items; i += blockDim.x) d.it[i].state[1] = q;
@@ -1039,16 +1082,25 @@ __global__ void __launch_bounds__(kRsFinishThreads)
 }
 
 // out[r, c] = bf16( sum_s partial[s][r][c] (s ascending) + bias[c] ): the second half of a split-K GEMM
+// push mode: row r of C belongs to member r / rows_per and goes to base[owner] + (r % rows_per) * ldc
+struct PushDst {
+  int n;
+  int64_t rows_per, row_rot;
+  __nv_bfloat16* base[kMaxGroup];
+};
+
 __global__ void __launch_bounds__(256)
     k_splitk_reduce(__nv_bfloat16* __restrict__ C, int64_t ldc, const float* __restrict__ partial,
-                    int64_t ldp, int splits, int M, int N, const __nv_bfloat16* __restrict__ bias) {
+                    int64_t ldp, int splits, int M, int N, const __nv_bfloat16* __restrict__ bias,
+                    const __grid_constant__ PushDst pd) {
   const int64_t groups_per_row = ldp / 4;
   const int64_t total = (int64_t)M * groups_per_row;
   const int64_t slice = (int64_t)M * ldp;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t r = i / groups_per_row;
+    int64_t r = i / groups_per_row;
     const int c = (int)(i - r * groups_per_row) * 4;
+    if (pd.n > 0) r = (r + pd.row_rot) % M;  // start at the next member's rows (no incast)
     const float* src = partial + r * ldp + c;
     float4 acc = *reinterpret_cast<const float4*>(src);
     for (int s = 1; s < splits; ++s) {
@@ -1060,11 +1112,29 @@ __global__ void __launch_bounds__(256)
     }
     float o[4] = {acc.x, acc.y, acc.z, acc.w};
     __nv_bfloat16* dst = C + r * ldc + c;
+    if (pd.n > 0) {
+      const int64_t owner = r / pd.rows_per;
+      dst = pd.base[owner] + (r - owner * pd.rows_per) * ldc + c;
+    }
+    if (c + 3 < N) {
+      // whole group inside the row: one 8-byte store (ldc % 8 == 0 and c % 4 == 0 => aligned)
+      if (bias) {
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      if (c + e < N) {
-        if (bias) o[e] += __bfloat162float(bias[c + e]);
-        dst[e] = __float2bfloat16_rn(o[e]);
+        for (int e = 0; e < 4; ++e) o[e] += __bfloat162float(bias[c + e]);
+      }
+      __nv_bfloat162 h0 = __floats2bfloat162_rn(o[0], o[1]);
+      __nv_bfloat162 h1 = __floats2bfloat162_rn(o[2], o[3]);
+      uint2 v;
+      v.x = *reinterpret_cast<uint32_t*>(&h0);
+      v.y = *reinterpret_cast<uint32_t*>(&h1);
+      *reinterpret_cast<uint2*>(dst) = v;
+    } else {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        if (c + e < N) {
+          if (bias) o[e] += __bfloat162float(bias[c + e]);
+          dst[e] = __float2bfloat16_rn(o[e]);
+        }
       }
     }
   }
@@ -1240,17 +1310,25 @@ using namespace edb;
 
 extern "C" {
 
-int edb_gemm_bf16(void* C, const void* A, const void* B, const void* bias, int64_t M, int64_t N,
-                  int64_t K, int64_t lda, int64_t ldb, int64_t ldc, int a_kmajor, int b_kmajor,
-                  int accumulate_into_c, void* stream) {
-  if (accumulate_into_c) return set_error(EDB_E_UNSUPPORTED, "edb_gemm_bf16: accumulate_into_c");
+// push: NULL, or the receive slots of the group members (C rows are spread over them)
+struct PushSpec {
+  int n, me;
+  int64_t rows_per;          // M / n, a multiple of BM
+  char* slot[kMaxGroup];     // member p's receive slot for MY rows: [rows_per, N] bf16, ld = N
+};
+
+static int gemm_plain_impl(void* C, const void* A, const void* B, const void* bias, int64_t M,
+                           int64_t N, int64_t K, int64_t lda, int64_t ldb, int64_t ldc, int a_kmajor,
+                           int b_kmajor, void* stream, const PushSpec* push) {
   int rc = check_operands(A, B, C, bias, M, N, K, lda, ldb, ldc, "edb_gemm_bf16");
   if (rc) return rc;
   const int sms = sm_count_now();
   int bn = pick_bn(M, N, sms);
   if (rt().gemm_force_bn == 128 || rt().gemm_force_bn == 256) bn = (int)rt().gemm_force_bn;
-  // CTA pairs (cta_group::2) whenever there are at least two tile rows
-  const int cl = (rt().gemm_cluster >= 2 && M > BM) ? 2 : 1;
+  // CTA pairs (cta_group::2) whenever there are at least two tile rows (push: an even number, so
+  // that no pair has a phantom tile whose owner index would be out of range)
+  int cl = (rt().gemm_cluster >= 2 && M > BM) ? 2 : 1;
+  if (push && ((M / BM) & 1)) cl = 1;
   CUtensorMap ta, tb, tc;
   if (a_kmajor) rc = make_tmap(&ta, A, K, M, lda, BK, BM);
   else rc = make_tmap(&ta, A, M, K, lda, 64, BK);
@@ -1258,7 +1336,7 @@ int edb_gemm_bf16(void* C, const void* A, const void* B, const void* bias, int64
   if (b_kmajor) rc = make_tmap(&tb, B, K, N, ldb, BK, bn / cl);
   else rc = make_tmap(&tb, B, N, K, ldb, 64, BK);
   if (rc) return rc;
-  rc = make_tmap(&tc, C, N, M, ldc, 64, BM);
+  rc = make_tmap(&tc, C, N, push ? push->rows_per : M, ldc, 64, BM);
   if (rc) return rc;
   GemmParams p;
   p.C = static_cast<__nv_bfloat16*>(C);
@@ -1269,10 +1347,30 @@ int edb_gemm_bf16(void* C, const void* A, const void* B, const void* bias, int64
   p.K = (int)K;
   p.m_tiles = (int)((M + BM - 1) / BM);
   p.n_tiles = (int)((N + bn - 1) / bn);
+  p.push_n = 0;
+  p.push_mtc = 1;
+  p.m_rot = 0;
   FusedArgs fa;
   memset(&fa, 0, sizeof(fa));
   CMaps cm;
   memset(&cm, 0, sizeof(cm));
+  PushDst pd;
+  memset(&pd, 0, sizeof(pd));
+  if (push) {
+    p.push_n = push->n;
+    p.push_mtc = (int)(push->rows_per / BM);
+    // start with the rows of the next member, end with my own (a local store)
+    const int first_m = ((push->me + 1) % push->n) * p.push_mtc;
+    p.m_rot = (cl == 2) ? first_m / 2 : first_m;
+    pd.n = push->n;
+    pd.rows_per = push->rows_per;
+    pd.row_rot = (int64_t)first_m * BM;
+    for (int q = 0; q < push->n; ++q) {
+      rc = make_tmap(&cm.m[q], push->slot[q], N, push->rows_per, N, 64, BM);
+      if (rc) return rc;
+      pd.base[q] = reinterpret_cast<__nv_bfloat16*>(push->slot[q]);
+    }
+  }
   p.splits = 1;
   p.kb_per_split = 0;
   p.partial = nullptr;
@@ -1313,16 +1411,52 @@ int edb_gemm_bf16(void* C, const void* A, const void* B, const void* bias, int64
   const int64_t groups = (int64_t)M * (p.ldp / 4);
   int rgrid = (int)((groups + 255) / 256);
   if (rgrid > 4 * sms) rgrid = 4 * sms;
-  k_splitk_reduce<<<rgrid, 256, 0, st>>>(p.C, ldc, p.partial, p.ldp, p.splits, (int)M, (int)N, p.bias);
+  k_splitk_reduce<<<rgrid, 256, 0, st>>>(p.C, ldc, p.partial, p.ldp, p.splits, (int)M, (int)N, p.bias,
+                                        pd);
   count_launch();
   return cuda_check(cudaGetLastError(), "k_splitk_reduce launch");
 }
 
-int edb_ag_gemm_bf16(int gid, void* C, const void* A, const void* bias, uint64_t b_shard_off,
-                     uint64_t b_full_off, int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldc,
-                     void* stream) {
+int edb_gemm_bf16(void* C, const void* A, const void* B, const void* bias, int64_t M, int64_t N,
+                  int64_t K, int64_t lda, int64_t ldb, int64_t ldc, int a_kmajor, int b_kmajor,
+                  int accumulate_into_c, void* stream) {
+  if (accumulate_into_c) return set_error(EDB_E_UNSUPPORTED, "edb_gemm_bf16: accumulate_into_c");
+  return gemm_plain_impl(C, A, B, bias, M, N, K, lda, ldb, ldc, a_kmajor, b_kmajor, stream, nullptr);
+}
+
+int edb_gemm_push_bf16(int gid, uint64_t recv_off, const void* A, const void* B, int64_t M,
+                       int64_t N, int64_t K, int64_t lda, int64_t ldb, int a_kmajor, int b_kmajor,
+                       void* stream) {
+  Runtime& r = rt();
+  if (!r.inited) return set_error(EDB_E_STATE, "runtime not initialised (call edb_init)");
+  if (gid < 0 || gid >= r.ngroups) return set_error(EDB_E_INVALID, "bad group id %d", gid);
+  const Group& g = r.groups[gid];
+  const int n = g.n, me = g.me;
+  if (M % n || (M / n) % BM)
+    return set_error(EDB_E_UNSUPPORTED, "edb_gemm_push_bf16: rows per rank must be a multiple of 128");
+  if (N & 7) return set_error(EDB_E_UNSUPPORTED, "edb_gemm_push_bf16: N must be a multiple of 8");
+  const int64_t rows = M / n;
+  const size_t chunk_bytes = (size_t)rows * N * 2;
+  if (recv_off < kUserOffset || recv_off + chunk_bytes * n > r.heap_bytes || (recv_off & 1023))
+    return set_error(EDB_E_INVALID, "edb_gemm_push_bf16: bad symmetric offset");
+  PushSpec ps;
+  memset(&ps, 0, sizeof(ps));
+  ps.n = n;
+  ps.me = me;
+  ps.rows_per = rows;
+  for (int q = 0; q < n; ++q)
+    ps.slot[q] = r.peer_heap[g.ranks[q]] + recv_off + (size_t)me * chunk_bytes;
+  // C itself is never written in push mode; my own slot stands in for the checks / the unused map
+  return gemm_plain_impl(ps.slot[me], A, B, nullptr, M, N, K, lda, ldb, N, a_kmajor, b_kmajor, stream,
+                         &ps);
+}
+
+static int ag_gemm_impl(int gid, void* C, const void* A, const void* bias, uint64_t b_shard_off,
+                        uint64_t b_full_off, int64_t M, int64_t N, int64_t K, int64_t lda,
+                        int64_t ldc, void* stream, int epoch) {
   FusedArgs fa;
   memset(&fa, 0, sizeof(fa));
+  fa.epoch = epoch;
   int rc = fill_flagctx(&fa.f, gid);
   if (rc) return rc;
   Runtime& r = rt();
@@ -1371,6 +1505,9 @@ int edb_ag_gemm_bf16(int gid, void* C, const void* A, const void* bias, uint64_t
   p.kb_per_split = 0;
   p.partial = nullptr;
   p.ldp = 0;
+  p.push_n = 0;
+  p.push_mtc = 1;
+  p.m_rot = 0;
   const int sms = r.sm_count;
   int n_comm = (int)r.comm_ctas;
   if (n_comm < 1) n_comm = 1;
@@ -1388,6 +1525,18 @@ int edb_ag_gemm_bf16(int gid, void* C, const void* A, const void* bias, uint64_t
   if (gemm_ctas > tiles) gemm_ctas = tiles;
   return dispatch_gemm<MODE_AG>(bn, true, true, ta, tb, tc, p, fa, cm, gemm_ctas + n_comm,
                                 (cudaStream_t)stream);
+}
+
+int edb_ag_gemm_bf16(int gid, void* C, const void* A, const void* bias, uint64_t b_shard_off,
+                     uint64_t b_full_off, int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldc,
+                     void* stream) {
+  return ag_gemm_impl(gid, C, A, bias, b_shard_off, b_full_off, M, N, K, lda, ldc, stream, 0);
+}
+
+int edb_ag_gemm_epoch_bf16(int gid, void* C, const void* A, const void* bias, uint64_t b_shard_off,
+                           uint64_t b_full_off, int64_t M, int64_t N, int64_t K, int64_t lda,
+                           int64_t ldc, void* stream) {
+  return ag_gemm_impl(gid, C, A, bias, b_shard_off, b_full_off, M, N, K, lda, ldc, stream, 1);
 }
 
 static int gemm_rs_impl(int gid, void* dst, uint64_t recv_off, uint64_t state_off, bool defer,
@@ -1413,9 +1562,26 @@ int edb_gemm_rs_push_bf16(int gid, uint64_t recv_off, uint64_t state_off, const 
                       b_kmajor, 1.0f, EDB_BF16, stream);
 }
 
+static int rs_finish_impl(int gid, int n_items, void* const* dsts, const uint64_t* recv_offs,
+                          const uint64_t* state_offs, const int64_t* chunk_bytes, float post_scale,
+                          int out_dtype, void* stream, int local_only);
+
 int edb_rs_finish(int gid, int n_items, void* const* dsts, const uint64_t* recv_offs,
                   const uint64_t* state_offs, const int64_t* chunk_bytes, float post_scale,
                   int out_dtype, void* stream) {
+  return rs_finish_impl(gid, n_items, dsts, recv_offs, state_offs, chunk_bytes, post_scale,
+                        out_dtype, stream, 0);
+}
+
+int edb_rs_finish_local(int gid, int n_items, void* const* dsts, const uint64_t* recv_offs,
+                        const int64_t* chunk_bytes, float post_scale, int out_dtype, void* stream) {
+  return rs_finish_impl(gid, n_items, dsts, recv_offs, nullptr, chunk_bytes, post_scale, out_dtype,
+                        stream, 1);
+}
+
+static int rs_finish_impl(int gid, int n_items, void* const* dsts, const uint64_t* recv_offs,
+                          const uint64_t* state_offs, const int64_t* chunk_bytes, float post_scale,
+                          int out_dtype, void* stream, int local_only) {
   if (n_items <= 0) return EDB_OK;
   if (out_dtype != EDB_BF16 && out_dtype != EDB_F32)
     return set_error(EDB_E_UNSUPPORTED, "edb_rs_finish: out dtype must be bf16 or f32");
@@ -1427,6 +1593,7 @@ int edb_rs_finish(int gid, int n_items, void* const* dsts, const uint64_t* recv_
     int rc = fill_flagctx(&d.f, gid);
     if (rc) return rc;
     const int n = d.f.n;
+    d.local_only = local_only;
     d.scale = post_scale;
     d.out_dtype = out_dtype;
     d.first_unit[0] = 0;
@@ -1437,13 +1604,14 @@ int edb_rs_finish(int gid, int n_items, void* const* dsts, const uint64_t* recv_
       if (cb <= 0 || (cb & 15) || ((uintptr_t)dsts[done] & 15))
         return set_error(EDB_E_INVALID, "edb_rs_finish: item %d: chunk bytes / dst alignment", done);
       if (recv_offs[done] < kUserOffset || recv_offs[done] + (uint64_t)cb * n > r.heap_bytes ||
-          (recv_offs[done] & 15) || state_offs[done] < kUserOffset ||
-          state_offs[done] + 16 > r.heap_bytes || (state_offs[done] & 15))
+          (recv_offs[done] & 15) ||
+          (!local_only && (state_offs[done] < kUserOffset || state_offs[done] + 16 > r.heap_bytes ||
+                           (state_offs[done] & 15))))
         return set_error(EDB_E_INVALID, "edb_rs_finish: item %d: bad symmetric offset", done);
       d.it[k].recv = r.heap + recv_offs[done];
       d.it[k].dst = dsts[done];
       d.it[k].chunk_bytes = cb;
-      d.it[k].state = reinterpret_cast<uint64_t*>(r.heap + state_offs[done]);
+      d.it[k].state = local_only ? nullptr : reinterpret_cast<uint64_t*>(r.heap + state_offs[done]);
       units += (cb / 16 + kRsFinishChunkVecs - 1) / kRsFinishChunkVecs;
       if (units > 0x7fffffffLL) return set_error(EDB_E_UNSUPPORTED, "edb_rs_finish: too much work");
       d.first_unit[k + 1] = (int)units;
@@ -1512,6 +1680,9 @@ static int gemm_rs_impl(int gid, void* dst, uint64_t recv_off, uint64_t state_of
   p.kb_per_split = 0;
   p.partial = nullptr;
   p.ldp = 0;
+  p.push_n = 0;
+  p.push_mtc = 1;
+  p.m_rot = 0;
   fa.recv_base = recv;
   fa.chunk_bytes = (int64_t)chunk_bytes;
   fa.rs_dst = dst;

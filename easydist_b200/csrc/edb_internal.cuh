@@ -42,7 +42,18 @@ enum FlagWord : int {
   F_ERR = 28,     // != 0: a spin wait timed out (value = op number)
   F_LLSEQ = 29,   // sequence number of the low-latency ops of this group
   F_CNT_LL = 30,  // last-block counter of the LL kernels
-  F_CHUNK = 32,   // [32..95] per-chunk flags for fused kernels (written by peers / local CTAs)
+  F_ERRHOST = 31, // device pointer of the pinned host error record (written once at edb_init)
+  F_CHUNK = 32,   // [32..47] per-chunk flags for fused kernels (written by peers / local CTAs)
+  // ---- epoch protocol (edb_epoch_barrier + the *_epoch fused kernels) -------------------------
+  // One group-wide barrier per phase of the step instead of a handshake per op: between two
+  // barriers peers may read this rank's symmetric operands / write its receive slots freely.
+  F_EPOCH = 48,      // [48..55] ARRIVED[p]: member p reached barrier number e   (written by p)
+  F_EPOCH_SEQ = 56,  // barriers completed locally                                 (written by me)
+  F_AGSEQ = 57,      // launch number of the epoch-mode AG+GEMM kernels (local chunk-flag epochs)
+  F_AGCNT = 58,      // CTAs of the current AG+GEMM launch that have read F_AGSEQ
+  F_AGDONE = 59,     // comm CTAs of the current launch that have finished
+  F_AGCHUNK = 64,    // [64..71] local: peer shard c is in the gathered buffer (launch number)
+  F_AGTILE = 72,     // [72..79] comm CTAs done with shard c
 };
 
 struct Group {
@@ -64,7 +75,9 @@ struct Runtime {
   int64_t allreduce_oneshot_bytes = 512 * 1024;
   int64_t copy_ctas_per_sm = 4;
   int64_t comm_ctas = 16;
-  int64_t spin_timeout_ms = 10000;
+  int64_t spin_timeout_ms = 120000;  // fatal when exceeded (NCCL-watchdog-like; EDB_SPIN_TIMEOUT_MS)
+  uint64_t* host_err = nullptr;      // pinned + mapped: {flag, op, kind, -}; survives a trapped context
+  uint64_t* host_err_dev = nullptr;  // device alias of host_err
   int64_t ll_max_bytes = 128 * 1024;  // payload per rank up to which the LL protocol is used (0 = off)
   int64_t gemm_force_bn = 0;  // tuning aid: 128 / 256 overrides the tile-width heuristic
   int64_t gemm_splitk = 1;   // 1: split K over idle SMs when the tiles fill at most half of them
@@ -112,9 +125,9 @@ struct FlagCtx {
   uint64_t* peer[kMaxGroup];  // every member's flag block (peer[me] == local)
   int n, me;
   int n_war;                  // number of local flag blocks to check for write-after-read
-  uint64_t* war_block[4];
-  int war_n[4];
-  int war_me[4];
+  uint64_t* war_block[kMaxGroups];
+  uint8_t war_n[kMaxGroups];
+  uint8_t war_me[kMaxGroups];
   uint64_t timeout_ns;
 };
 
@@ -198,18 +211,35 @@ __device__ __forceinline__ uint64_t globaltimer_ns() {
   return t;
 }
 
-// Spin until *flag >= target (system scope acquire).  On timeout records the op in F_ERR and
-// returns false; callers carry on so that a lost peer never wedges the GPU.
+// A wait on a peer timed out: the peer is lost or more than `spin_timeout_ms` behind.  Carrying on
+// would reduce / copy stale peer data and publish the op as done, so the timeout is FATAL (what
+// NCCL's watchdog does for the reference): record {op, flag word, 1} in the pinned host error
+// record (readable after the context is gone: edb_health()), then trap, which fails this kernel
+// and every later CUDA call of the process.  `err_word` = the local flag block's F_ERR word.
+static __device__ __noinline__ void fatal_timeout(uint64_t* err_word, uint64_t target, int what) {
+  if (err_word) {
+    atomicMax((unsigned long long*)err_word, (unsigned long long)target);
+    volatile uint64_t* host = reinterpret_cast<volatile uint64_t*>(err_word[F_ERRHOST - F_ERR]);
+    if (host) {
+      host[1] = target;
+      host[2] = (uint64_t)what;
+      host[0] = 1;
+      __threadfence_system();
+    }
+  }
+  printf("edb: wait on a peer timed out (op/epoch %llu, kind %d) - aborting\n",
+         (unsigned long long)target, what);
+  asm volatile("trap;");
+}
+
+// Spin until *flag >= target (system scope acquire); fatal on timeout (see fatal_timeout).
 __device__ __forceinline__ bool spin_wait_sys(const uint64_t* flag, uint64_t target,
                                               uint64_t timeout_ns, uint64_t* err_word) {
   if (ld_acquire_sys(flag) >= target) return true;
   uint64_t t0 = globaltimer_ns();
   while (ld_acquire_sys(flag) < target) {
     __nanosleep(64);
-    if (globaltimer_ns() - t0 > timeout_ns) {
-      if (err_word) atomicMax((unsigned long long*)err_word, (unsigned long long)target);
-      return false;
-    }
+    if (globaltimer_ns() - t0 > timeout_ns) fatal_timeout(err_word, target, 1);
   }
   return true;
 }
@@ -219,9 +249,10 @@ __device__ __forceinline__ bool spin_wait_sys(const uint64_t* flag, uint64_t tar
 // Returns the op number of this launch after the write-after-read guard.
 __device__ __forceinline__ uint64_t begin_op(const FlagCtx& f, uint64_t* s_q) {
   if (threadIdx.x == 0) *s_q = ld_relaxed_gpu(f.local + F_SEQ) + 1;
-  if (threadIdx.x < 32) {
-    const int b = threadIdx.x >> 3, p = threadIdx.x & 7;
-    if (b < f.n_war && p < f.war_n[b] && p != f.war_me[b]) {
+  // one thread per (group of this rank, member): every group's readers must be done
+  for (int i = threadIdx.x; i < f.n_war * kMaxGroup; i += blockDim.x) {
+    const int b = i >> 3, p = i & 7;
+    if (p < f.war_n[b] && p != f.war_me[b]) {
       const uint64_t* blk = f.war_block[b];
       const uint64_t seq = ld_relaxed_gpu(blk + F_SEQ);
       spin_wait_sys(blk + F_DONE + p, seq, f.timeout_ns, f.local + F_ERR);
@@ -282,5 +313,31 @@ __device__ __forceinline__ void finish_op(const FlagCtx& f, uint64_t q, int* s_l
   }
 }
 
+// ---- epoch protocol ------------------------------------------------------------------------------
+// Group-wide barrier executed by ONE CTA (>= 32 threads): thread p signals member p and waits for
+// it.  The system-scope fence + release stores order everything this rank did earlier on the
+// stream (kernel boundaries included: its stores into peer memory, its reads of peer memory)
+// before the signal; the acquire loads order the peers' work before whatever follows here.
+__device__ __forceinline__ void epoch_barrier_cta(const FlagCtx& f, uint64_t* s_e) {
+  if (threadIdx.x == 0) {
+    *s_e = ld_relaxed_gpu(f.local + F_EPOCH_SEQ) + 1;
+    __threadfence_system();
+  }
+  __syncthreads();
+  const uint64_t e = *s_e;
+  if ((int)threadIdx.x < f.n && (int)threadIdx.x != f.me) {
+    st_release_sys(f.peer[threadIdx.x] + F_EPOCH + f.me, e);
+    const uint64_t* flag = f.local + F_EPOCH + threadIdx.x;
+    if (ld_acquire_sys(flag) < e) {
+      const uint64_t t0 = globaltimer_ns();
+      while (ld_acquire_sys(flag) < e) {
+        __nanosleep(32);
+        if (globaltimer_ns() - t0 > f.timeout_ns) fatal_timeout(f.local + F_ERR, e, 2);
+      }
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) st_release_gpu(f.local + F_EPOCH_SEQ, e);
+}
 
 }  // namespace edb

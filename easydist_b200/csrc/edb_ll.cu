@@ -49,10 +49,7 @@ __device__ __forceinline__ uint32_t wait_pkt(const uint2* p, uint32_t flag, uint
   while (true) {
     v = ld_pkt(p);
     if (v.y == flag) return v.x;
-    if (globaltimer_ns() - t0 > timeout_ns) {
-      atomicMax((unsigned long long*)err, (unsigned long long)flag);
-      return v.x;
-    }
+    if (globaltimer_ns() - t0 > timeout_ns) fatal_timeout(err, flag, 3);  // never returns
   }
 }
 
@@ -207,7 +204,12 @@ int ll_try(int gid, int mode, void* dst, const void* src, int64_t in_bytes, int6
   const Group& g = r.groups[gid];
   if (g.n <= 1 || g.slot >= kLLGroups || r.ll_max_bytes <= 0) return -1;
   if (in_bytes <= 0 || in_bytes > r.ll_max_bytes || (in_bytes & 3) || (row_bytes & 3)) return -1;
-  if (((uintptr_t)src | (uintptr_t)dst) & 3) return -1;
+  // Eligibility must only depend on rank-invariant quantities (sizes, dtype, group slot, options
+  // that the host sets identically everywhere): a rank that picked the flag protocol while its
+  // peers use packets would never rendezvous.  Alignment is therefore a contract of the callers
+  // (every entry point requires 16-byte aligned bases), not a reason to switch protocols.
+  if (((uintptr_t)src | (uintptr_t)dst) & 3)
+    return set_error(EDB_E_INVALID, "collective operands must be at least 4-byte aligned");
   if (mode != LL_ALL_GATHER &&
       !(dtype == EDB_F32 || dtype == EDB_BF16 || dtype == EDB_F16 || dtype == EDB_I32))
     return -1;

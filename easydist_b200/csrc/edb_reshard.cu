@@ -143,6 +143,11 @@ __global__ void __launch_bounds__(32) k_guard(const __grid_constant__ FlagCtx f)
   begin_op(f, &s_q);
 }
 
+__global__ void __launch_bounds__(32) k_epoch_barrier(const __grid_constant__ FlagCtx f) {
+  __shared__ uint64_t s_e;
+  epoch_barrier_cta(f, &s_e);
+}
+
 // ---- reductions ------------------------------------------------------------------------------------
 
 template <typename T> struct Conv;
@@ -447,12 +452,11 @@ int fill_flagctx(FlagCtx* f, int gid) {
   f->me = g.me;
   f->local = flag_block(r.heap, g.slot);
   for (int p = 0; p < g.n; ++p) f->peer[p] = flag_block(r.peer_heap[g.ranks[p]], g.slot);
-  if (r.ngroups > 4) return set_error(EDB_E_UNSUPPORTED, "more than 4 groups per rank");
-  f->n_war = r.ngroups;
+  f->n_war = r.ngroups;  // <= kMaxGroups by construction (edb_group_create)
   for (int i = 0; i < r.ngroups; ++i) {
     f->war_block[i] = flag_block(r.heap, r.groups[i].slot);
-    f->war_n[i] = r.groups[i].n;
-    f->war_me[i] = r.groups[i].me;
+    f->war_n[i] = (uint8_t)r.groups[i].n;
+    f->war_me[i] = (uint8_t)r.groups[i].me;
   }
   f->timeout_ns = (uint64_t)r.spin_timeout_ms * 1000000ull;
   return EDB_OK;
@@ -936,6 +940,16 @@ int edb_all_reduce(int gid, void* dst, uint64_t stage_off, uint64_t stage2_off, 
   }
   d.n_pull = np;
   return launch_reduce(L, (cudaStream_t)stream);
+}
+
+int edb_epoch_barrier(int gid, void* stream) {
+  FlagCtx f;
+  int rc = fill_flagctx(&f, gid);
+  if (rc) return rc;
+  if (f.n <= 1) return EDB_OK;
+  k_epoch_barrier<<<1, 32, 0, (cudaStream_t)stream>>>(f);
+  count_launch();
+  return cuda_check(cudaGetLastError(), "k_epoch_barrier launch");
 }
 
 int edb_symm_guard(int gid, void* stream) {

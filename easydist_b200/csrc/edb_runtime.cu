@@ -59,6 +59,22 @@ int edb_init(int rank, int world, int device, size_t heap_bytes) {
   void* p = nullptr;
   EDB_CUDA(cudaMalloc(&p, heap_bytes));
   EDB_CUDA(cudaMemset(p, 0, kUserOffset));
+  // pinned host error record, visible to the kernels through word F_ERRHOST of every flag block
+  // (fatal_timeout writes it before trapping; edb_health reads it from the host)
+  if (!r.host_err) {
+    void* h = nullptr;
+    EDB_CUDA(cudaHostAlloc(&h, 64, cudaHostAllocMapped));
+    memset(h, 0, 64);
+    void* d = nullptr;
+    EDB_CUDA(cudaHostGetDevicePointer(&d, h, 0));
+    r.host_err = static_cast<uint64_t*>(h);
+    r.host_err_dev = static_cast<uint64_t*>(d);
+  }
+  for (int slot = 0; slot < kMaxGroups; ++slot) {
+    const uint64_t v = (uint64_t)(uintptr_t)r.host_err_dev;
+    EDB_CUDA(cudaMemcpy(flag_block(static_cast<char*>(p), slot) + F_ERRHOST, &v, sizeof(v),
+                        cudaMemcpyHostToDevice));
+  }
   EDB_CUDA(cudaDeviceSynchronize());
   r.rank = rank;
   r.world = world;
@@ -88,8 +104,23 @@ int edb_finalize(void) {
     r.peer_is_ipc[i] = false;
   }
   cudaFree(r.heap);
+  if (r.host_err) cudaFreeHost(r.host_err);
   r = Runtime();
   return EDB_OK;
+}
+
+int edb_health(void) {
+  Runtime& r = g_rt;
+  if (!r.inited || !r.host_err) return EDB_OK;
+  volatile uint64_t* h = r.host_err;
+  if (h[0] == 0) return EDB_OK;
+  static const char* kinds[] = {"?", "flag wait", "epoch barrier", "low-latency packet"};
+  const uint64_t kind = h[2] < 4 ? h[2] : 0;
+  return set_error(EDB_E_STATE,
+                   "a collective on rank %d timed out waiting for a peer (%s, op/epoch %llu, timeout "
+                   "%lld ms): a peer is lost or too far behind; the kernel trapped and this process's "
+                   "CUDA context is unusable",
+                   r.rank, kinds[kind], (unsigned long long)h[1], (long long)r.spin_timeout_ms);
 }
 
 int edb_heap_info(void** base, size_t* bytes, size_t* user_offset) {

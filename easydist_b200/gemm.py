@@ -38,10 +38,28 @@ def reset_stats():
     _stats["padded_operands"] = 0
     _stats["unsupported"] = {}
     del _calls[:]
+    del _fused_calls[:]
 
 
 def recorded_calls():
     return list(_calls)
+
+
+_fused_calls = []  # dicts: kind ("ag" | "push"), M, N, K, layouts / strides, group, _buf
+
+
+def note_fused_call(kind, M, N, K, a_k, b_k, a_stride, b_stride, group, buf):
+    """Fused collective GEMMs (reshard.ag_mm / mm_push) report here so that the bench can replay the
+    step's complete GEMM launch list — the fused kernels are the dominant ones at N > 1."""
+    if len(_fused_calls) < 8192:
+        _fused_calls.append({"kind": kind, "M": int(M), "N": int(N), "K": int(K), "a_k": bool(a_k),
+                             "b_k": bool(b_k), "a_stride": tuple(a_stride),
+                             "b_stride": tuple(b_stride), "group": list(group),
+                             "buf": tuple(int(b) for b in buf)})
+
+
+def recorded_fused_calls():
+    return list(_fused_calls)
 
 
 def _stream(t):

@@ -928,6 +928,7 @@ def fuse_collective_gemms(gm, io, rt, ranks, ops=_default_ops):
 
     Returns {placeholder name: SymmBuffer} for parameter shards that must live in the symmetric
     heap (peers read them directly), after inserting a symm_guard in front of the optimizer."""
+    import os
     graph = gm.graph
     n = len(ranks)
     if n <= 1:
@@ -936,6 +937,11 @@ def fuse_collective_gemms(gm, io, rt, ranks, ops=_default_ops):
     rehomed = {}
     n_ag = n_rs = 0
     bf16 = torch.bfloat16
+    # epoch protocol (default): no handshake inside the fused kernels; ONE group barrier in front
+    # of the optimizer (all gradient tiles have landed in their owners' slots, nobody still reads the
+    # old parameter shards) and ONE behind it (the new shards are final, the slots are free again).
+    # EDB_EPOCH=0 keeps the per-op flag protocol of the fused kernels.
+    epoch = os.environ.get("EDB_EPOCH", "1") == "1" and hasattr(ops, "epoch_barrier")
 
     def val(nd):
         return nd.meta.get("val") if isinstance(nd, Node) else None
@@ -975,8 +981,11 @@ def fuse_collective_gemms(gm, io, rt, ranks, ops=_default_ops):
         full = rt.alloc(n_out * k_in * 2, align=1024)
         rehomed[ph.name] = shard
         with graph.inserting_before(first):
+            ag_kw = {"_buf": (shard.offset, full.offset)}
+            if epoch:
+                ag_kw["_epoch"] = 1
             fused = graph.call_function(ops.ag_mm, args=(x, ph, list(ranks), n_out, k_in, bias),
-                                        kwargs={"_buf": (shard.offset, full.offset)})
+                                        kwargs=ag_kw)
             out = graph.call_function(operator.getitem, args=(fused, 0))
             wfull = graph.call_function(operator.getitem, args=(fused, 1))
             t_new = graph.call_function(aten.t.default, args=(wfull,))
@@ -990,8 +999,7 @@ def fuse_collective_gemms(gm, io, rt, ranks, ops=_default_ops):
     # ---- GEMM + reduce-scatter -------------------------------------------------------------
     # deferred form (EDB_DEFER_RS=1): the GEMM only pushes its tiles to the owners; one rs_finish
     # node in front of the first consumer reduces every weight gradient's slots in a single kernel
-    import os
-    defer = os.environ.get("EDB_DEFER_RS", "0") == "1" and hasattr(ops, "mm_rs_push")
+    defer = epoch or (os.environ.get("EDB_DEFER_RS", "0") == "1" and hasattr(ops, "mm_rs_push"))
     pushed = []  # (token node, recv buffer, state buffer, shard numel, rs_end node)
     for rs_s in [x for x in graph.nodes if x.op == "call_function" and x.target is ops.reduce_scatter_start]:
         f = rs_s.args[0]
@@ -1032,7 +1040,12 @@ def fuse_collective_gemms(gm, io, rt, ranks, ops=_default_ops):
                     nd.meta["val"] = src.t()
             else:
                 a, b = a0, b0
-            if defer:
+            if epoch:
+                tok = graph.call_function(ops.mm_push, args=(a, b, list(ranks)),
+                                          kwargs={"_buf": (recv.offset,)})
+                pushed.append((tok, recv, None, M // n * N, rs_e))
+                fused = None
+            elif defer:
                 state = rt.alloc(16, align=16)
                 state.tensor(torch.int64, (2,)).zero_()
                 push_kw = {"_buf": (recv.offset, state.offset)}
@@ -1071,10 +1084,15 @@ def fuse_collective_gemms(gm, io, rt, ranks, ops=_default_ops):
         groups.append(cur)
         for items in groups:
             with graph.inserting_before(first_use_of(items)):
-                fin = graph.call_function(
-                    ops.rs_finish, args=([it[0] for it in items], list(ranks)),
-                    kwargs={"_bufs": [(it[1].offset, it[2].offset) for it in items],
-                            "_numels": [it[3] for it in items], "_scale": 1.0 / n})
+                fin_kw = {"_bufs": [(it[1].offset, it[2].offset) if it[2] is not None
+                                    else (it[1].offset,) for it in items],
+                          "_numels": [it[3] for it in items], "_scale": 1.0 / n}
+                toks = [it[0] for it in items]
+                if epoch:
+                    # every member's tiles must have landed before anybody reduces its slots
+                    fin_kw["_epoch"] = 1
+                    toks[0] = graph.call_function(ops.epoch_barrier, args=(toks[0], list(ranks)))
+                fin = graph.call_function(ops.rs_finish, args=(toks, list(ranks)), kwargs=fin_kw)
                 for i, (tok, recv, state, numel, rs_e) in enumerate(items):
                     gi = graph.call_function(operator.getitem, args=(fin, i))
                     gi.meta = dict(rs_e.meta)
@@ -1082,7 +1100,32 @@ def fuse_collective_gemms(gm, io, rt, ranks, ops=_default_ops):
                     graph.erase_node(rs_e)
 
     # peers read parameter shards in place: keep the optimizer from overwriting them too early
-    if rehomed:
+    if epoch and (rehomed or pushed):
+        order = {nd: i for i, nd in enumerate(graph.nodes)}
+        fused_nodes = [nd for nd in graph.nodes if nd.op == "call_function"
+                       and nd.target in (ops.ag_mm, ops.mm_push)]
+        last_fused = max(fused_nodes, key=lambda nd: order[nd])
+        barriers = [nd for nd in graph.nodes if nd.op == "call_function"
+                    and nd.target is ops.epoch_barrier]
+        if not any(order[b_] > order[last_fused] for b_ in barriers):
+            # no gradient push (hence no barrier in front of an rs_finish) behind the last peer read:
+            # the optimizer, which is traced after the whole backward pass, must still not touch
+            # shards that a slower peer is reading
+            anchor = last_fused
+            while anchor.next.op == "call_function" and anchor.next.target is operator.getitem \
+                    and anchor.next.args[0] is last_fused:
+                anchor = anchor.next
+            with graph.inserting_after(anchor):
+                graph.call_function(ops.epoch_barrier, args=(anchor, list(ranks)))
+        # behind the optimizer: new shards final, receive slots free => the next step may start
+        out_node = next(nd for nd in graph.nodes if nd.op == "output")
+        some = next((nd for nd in reversed(list(graph.nodes)) if nd.op == "call_function"
+                     and isinstance(nd.meta.get("val"), torch.Tensor)), None)
+        if some is None:
+            some = next(nd for nd in graph.nodes if nd.op == "placeholder")
+        with graph.inserting_before(out_node):
+            graph.call_function(ops.epoch_barrier, args=(some, list(ranks)))
+    elif rehomed:
         region = optimizer_region(gm, io)
         if region:
             anchor = region[0]

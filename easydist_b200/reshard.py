@@ -22,6 +22,7 @@ from typing import List
 import ctypes
 
 import torch
+from torch.fx.node import has_side_effect
 from torch._subclasses.fake_tensor import FakeTensor
 
 from . import _lib
@@ -399,6 +400,7 @@ def box_exchange(tensor, dst_shape, boxes, peer_src_shapes, group, *, _buf=None)
 # ---- fused compute + collective (one kernel each) -----------------------------------------------------
 
 
+@has_side_effect
 def symm_guard(x, group):
     """Pass-through that makes the stream wait until no peer is still reading this rank's
     symmetric buffers (inserted in front of producers that write symmetric memory in place, e.g.
@@ -410,7 +412,21 @@ def symm_guard(x, group):
     return x
 
 
-def ag_mm(x, w_shard, group, n_out, k_in, bias=None, *, _buf):
+@has_side_effect
+def epoch_barrier(x, group):
+    """Pass-through that runs the group-wide epoch barrier on the stream (edb_epoch_barrier).
+    The epoch-mode fused kernels (`ag_mm(_epoch=1)`, `mm_push`) read peers' parameter shards and
+    write peers' receive slots without any per-op handshake; two of these per train step — one in
+    front of the optimizer, one behind it — are the only cross-rank rendezvous left
+    (reference: one NCCL rendezvous per collective, sharding.py:94-152)."""
+    if _is_fake(x) or len(group) <= 1:
+        return x
+    rt, gid, n, _ = _group(group)
+    check(rt.lib.edb_epoch_barrier(gid, rt.stream()))
+    return x
+
+
+def ag_mm(x, w_shard, group, n_out, k_in, bias=None, *, _buf, _epoch=0):
     """all_gather(weight shard, dim 0) fused into the consuming GEMM (all_gather_end -> aten.mm /
     addmm of the sharded graph).  `w_shard`: this rank's rows [n_out/n, k_in] (flat or 2-D) living
     at symmetric offset _buf[0]; _buf[1] = offset of the gathered [n_out, k_in] buffer that the
@@ -426,9 +442,12 @@ def ag_mm(x, w_shard, group, n_out, k_in, bias=None, *, _buf):
     M, K = xc.shape
     assert K == k_in
     out = torch.empty((M, n_out), dtype=torch.bfloat16, device=x.device)
-    check(rt.lib.edb_ag_gemm_bf16(gid, out.data_ptr(), xc.data_ptr(),
-                                  bias.data_ptr() if bias is not None else None, shard_off, full_off,
-                                  M, n_out, K, xc.stride(0), n_out, rt.stream()))
+    if _epoch:
+        from . import gemm as _gemm
+        _gemm.note_fused_call("ag", M, n_out, K, True, True, xc.stride(), (1, k_in), group, _buf)
+    fn = rt.lib.edb_ag_gemm_epoch_bf16 if _epoch else rt.lib.edb_ag_gemm_bf16
+    check(fn(gid, out.data_ptr(), xc.data_ptr(), bias.data_ptr() if bias is not None else None,
+             shard_off, full_off, M, n_out, K, xc.stride(0), n_out, rt.stream()))
     w_full = SymmBuffer(rt, full_off, n_out * k_in * 2).tensor(torch.bfloat16, (n_out, k_in))
     return out, w_full
 
@@ -484,7 +503,29 @@ def mm_rs_push(a, b, group, *, _buf, _lane=0):
     return lane.tag(token, ta, tb)
 
 
-def rs_finish(tokens, group, *, _bufs, _numels, _scale=1.0, _out_dtype=None):
+def mm_push(a, b, group, *, _buf):
+    """Epoch-mode push half of mm_rs: a @ b on the regular GEMM path (cta_group::2 pairs, split-K)
+    with every row block stored into its owner's receive slot over NVLink; no flags at all — the
+    epoch barrier in front of `rs_finish(_epoch=1)` makes the slots complete.  _buf = (symmetric
+    offset of the n receive slots,).  Returns an empty token for graph ordering."""
+    if _is_fake(a):
+        return a.new_empty((0,))
+    _require_cuda(a, "mm_push")
+    from . import gemm as _gemm
+    rt, gid, n, me = _group(group)
+    M, K = a.shape
+    N = b.shape[1]
+    pa, pb = _gemm._prepare(a, 1), _gemm._prepare(b, 0)
+    if pa is None or pb is None:
+        raise _lib.EdbUnsupported(_lib.EDB_E_UNSUPPORTED, "mm_push: operand layout")
+    (ta, a_k, lda), (tb, b_k, ldb) = pa, pb
+    check(rt.lib.edb_gemm_push_bf16(gid, int(_buf[0]), ta.data_ptr(), tb.data_ptr(), M, N, K, lda,
+                                    ldb, 1 if a_k else 0, 1 if b_k else 0, rt.stream()))
+    _gemm.note_fused_call("push", M, N, K, a_k, b_k, a.stride(), b.stride(), group, _buf)
+    return torch.empty((0,), dtype=a.dtype, device=a.device)
+
+
+def rs_finish(tokens, group, *, _bufs, _numels, _scale=1.0, _out_dtype=None, _epoch=0):
     """Reduce the receive slots of the pushed GEMMs `tokens` came from, all in one kernel:
     item i -> flat shard of _numels[i] elements = sum over ranks (rank order, fp32) * _scale.
     _bufs[i] = the (_buf) pair given to mm_rs_push i."""
@@ -501,14 +542,19 @@ def rs_finish(tokens, group, *, _bufs, _numels, _scale=1.0, _out_dtype=None):
     cnt = len(outs)
     dsts = (ctypes.c_void_p * cnt)(*[o.data_ptr() for o in outs])
     recv = (ctypes.c_uint64 * cnt)(*[int(b[0]) for b in _bufs])
-    state = (ctypes.c_uint64 * cnt)(*[int(b[1]) for b in _bufs])
+    state = (ctypes.c_uint64 * cnt)(*[int(b[1]) if len(b) > 1 else 0 for b in _bufs])
     chunk = (ctypes.c_int64 * cnt)(*[int(k) * 2 for k in _numels])  # slots hold bf16
-    check(rt.lib.edb_rs_finish(gid, cnt, dsts, recv, state, chunk, float(_scale),
-                               _TORCH_DTYPE_CODE[out_dtype], rt.stream()))
+    if _epoch:
+        # the caller put an epoch barrier in front: every slot is complete, nothing to wait for
+        check(rt.lib.edb_rs_finish_local(gid, cnt, dsts, recv, chunk, float(_scale),
+                                         _TORCH_DTYPE_CODE[out_dtype], rt.stream()))
+    else:
+        check(rt.lib.edb_rs_finish(gid, cnt, dsts, recv, state, chunk, float(_scale),
+                                   _TORCH_DTYPE_CODE[out_dtype], rt.stream()))
     return outs
 
 
 COMM_FUNCS = [all_reduce_start, all_gather_start, reduce_scatter_start, all_to_all_start]
 COMM_SYNC_FUNCS = [all_reduce_end, all_gather_end, reduce_scatter_end, all_to_all_end]
 CUSTOM_FUNCS = COMM_FUNCS + COMM_SYNC_FUNCS + [scatter_wrapper, copy_wrapper]
-FUSED_FUNCS = [ag_mm, mm_rs, mm_rs_push, rs_finish, symm_guard]
+FUSED_FUNCS = [ag_mm, mm_rs, mm_rs_push, mm_push, rs_finish, symm_guard, epoch_barrier]

@@ -77,6 +77,9 @@ class Runtime:
         self._ring_pos = 0
         self._static_limit = self._ring_base
         self._attached = self.world == 1
+        # a peer that stays away longer than this is fatal (the waiting kernel traps): same role as
+        # the NCCL watchdog timeout of the reference's process groups
+        self.set_option("spin_timeout_ms", int(os.environ.get("EDB_SPIN_TIMEOUT_MS", "120000")))
 
     # ---- bootstrap -------------------------------------------------------------------------
     def attach_peers(self, process_group=None):
@@ -94,6 +97,18 @@ class Runtime:
                 check(self.lib.edb_ipc_attach(int(r), ctypes.create_string_buffer(h, 64)))
         dist.barrier(group=process_group)
         self._attached = True
+        self._pg = process_group
+
+    def host_barrier(self):
+        """Host-level rendezvous (torch.distributed): used once after compilation so that no rank
+        starts its first step — whose kernels wait on peers with a finite, fatal timeout — while
+        another rank is still tracing / re-homing parameter shards."""
+        if self.world <= 1:
+            return
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            torch.cuda.synchronize(self.device)
+            dist.barrier(group=getattr(self, "_pg", None))
 
     def group(self, ranks, slot=None, lane=0):
         """gid of the group of global `ranks` (mesh-dim order); created on first use.
@@ -166,6 +181,11 @@ class Runtime:
 
     def launch_count(self):
         return int(self.lib.edb_launch_count())
+
+    def health(self):
+        """Raise if a collective of this process timed out on a peer (the kernel trapped; the
+        record lives in pinned host memory, so this works without touching the dead context)."""
+        check(self.lib.edb_health())
 
     def error_flags(self):
         """Op numbers whose spin waits timed out, per group slot (all zero when healthy)."""

@@ -56,6 +56,11 @@ const char* edb_last_error(void);
 int edb_init(int rank, int world, int device, size_t heap_bytes);
 int edb_finalize(void);
 int edb_is_initialized(void);
+/* 0 while healthy.  A wait on a peer that exceeds "spin_timeout_ms" is fatal (the kernel records
+ * the op in a pinned host word and traps — like the NCCL watchdog aborting the reference's
+ * process — instead of continuing with stale peer data); afterwards this returns EDB_E_STATE with
+ * the details in edb_last_error(), even though the CUDA context is gone. */
+int edb_health(void);
 /* base address / size of the local heap; `user_offset` = first byte usable by edb_symm_alloc */
 int edb_heap_info(void** base, size_t* bytes, size_t* user_offset);
 
@@ -201,6 +206,48 @@ int edb_gemm_rs_push_bf16(int gid, uint64_t recv_off, uint64_t state_off, const 
 int edb_rs_finish(int gid, int n_items, void* const* dsts, const uint64_t* recv_offs,
                   const uint64_t* state_offs, const int64_t* chunk_bytes, float post_scale,
                   int out_dtype, void* stream);
+
+/* ---- epoch protocol: one group barrier per phase of the step instead of a handshake per op ----
+ *
+ * The per-op protocol above costs several dependent system-scope round trips per collective
+ * (WAR guard, READY, DONE: ~18 us per fused op at n=2..8), which is what the reference pays per
+ * NCCL call as launch + rendezvous latency (sharding.py:94-152, serialized on one stream by
+ * CUDA_DEVICE_MAX_CONNECTIONS=1, easydist/torch/__init__.py:53).  A train step has only two
+ * points where ranks really depend on each other: (1) before the optimizer — every gradient
+ * contribution has arrived and nobody still reads the old parameters; (2) after it — the new
+ * parameter shards are final.  `edb_epoch_barrier` is that rendezvous (one 32-thread kernel,
+ * monotonic epoch words, CUDA-graph capturable); between two barriers the *_epoch / push kernels
+ * below read peers' symmetric operands and write peers' receive slots with no flag traffic. */
+
+/* Group-wide barrier on `stream`: returns (in stream order) once every member has reached its own
+ * call.  Everything a member did before its barrier — including its stores into peer memory — is
+ * visible to every member after it (system-scope fence + release / acquire). */
+int edb_epoch_barrier(int gid, void* stream);
+
+/* edb_ag_gemm_bf16 without the per-op handshake: the caller guarantees, with an
+ * edb_epoch_barrier earlier on every member's stream, that all shards at `b_shard_off` are final,
+ * and that nobody modifies its shard before the next barrier.  Same result. */
+int edb_ag_gemm_epoch_bf16(int gid, void* C, const void* A, const void* bias, uint64_t b_shard_off,
+                           uint64_t b_full_off, int64_t M, int64_t N, int64_t K, int64_t lda,
+                           int64_t ldc, void* stream);
+
+/* GEMM whose result is reduce-scattered over its rows, push half: C = A.B (operand layouts as
+ * edb_gemm_bf16, incl. cta_group::2 pairs and split-K); row block [p*M/n, (p+1)*M/n) is stored
+ * straight into member p's receive slot [me] at symmetric `recv_off` (n slots of (M/n)*N*2 bytes
+ * on every member, dedicated to this GEMM) over NVLink, next member's rows first, own rows last.
+ * No flags: after the next edb_epoch_barrier every slot of every member is complete, and
+ * edb_rs_finish_local may reduce them; the slots may be overwritten again after the barrier that
+ * follows that reduction.  (aten.mm -> reduce_scatter_start(avg) of the zero2/zero3 graphs,
+ * compile_dp.py:101-118, with the gradient scale + cast fused into the reduction.) */
+int edb_gemm_push_bf16(int gid, uint64_t recv_off, const void* A, const void* B, int64_t M,
+                       int64_t N, int64_t K, int64_t lda, int64_t ldb, int a_kmajor, int b_kmajor,
+                       void* stream);
+
+/* Reduce the receive slots of n_items pushed GEMMs in ONE launch: dsts[i][j] = out_dtype(
+ * post_scale * sum over members s in rank order (fp32) of slot_s[j]); purely local memory traffic
+ * (the barrier in front made the slots complete). */
+int edb_rs_finish_local(int gid, int n_items, void* const* dsts, const uint64_t* recv_offs,
+                        const int64_t* chunk_bytes, float post_scale, int out_dtype, void* stream);
 
 /* LayerNorm over the last dimension — aten.native_layer_norm / native_layer_norm_backward nodes of
  * the sharded graph (SURVEY.md App. B lists 8+8 per step in config 1).  x, y, dy, dx: [rows, H]

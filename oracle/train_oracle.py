@@ -40,12 +40,14 @@ def train_losses(model_name, attn, batch, seq, steps, lr=1e-3, momentum=0.9, see
     return losses, model
 
 
-def time_cpu_train_step(model_name, attn, n_seqs, seq, steps=1):
+def time_cpu_train_step(model_name, attn, n_seqs, seq, steps=1, warmup=0):
     from easydist_b200.workloads import gpt2_train_step, synthetic_tokens
     cfg, model = build(model_name, attn, seq)
     opt = torch.optim.SGD(model.parameters(), lr=1e-3, momentum=0.9, foreach=True)
     tok, tgt = synthetic_tokens(cfg, n_seqs, seq, seed=0)
-    loss = gpt2_train_step(tok[:1], tgt[:1], model, opt)  # warm-up (allocations, thread pool)
+    loss = gpt2_train_step(tok[:1], tgt[:1], model, opt)  # allocations, thread pool
+    for _ in range(warmup):
+        loss = gpt2_train_step(tok, tgt, model, opt)
     t0 = time.perf_counter()
     for _ in range(steps):
         loss = gpt2_train_step(tok, tgt, model, opt)

@@ -121,7 +121,29 @@ def symm_guard(x, group):
     return x
 
 
-def ag_mm(x, w_shard, group, n_out, k_in, bias=None, *, _buf=None):
+_EPOCHS = {"barriers": 0, "open_pushes": 0}
+
+
+def epoch_barrier(x, group):
+    """CPU stand-in of reshard.epoch_barrier: a real gloo barrier, counted; pushes issued since
+    the previous barrier become reducible."""
+    if _fake(x) or len(group) <= 1:
+        return x
+    dist.barrier(group=_pg(group))
+    _EPOCHS["barriers"] += 1
+    _EPOCHS["open_pushes"] = 0
+    return x
+
+
+def mm_push(a, b, group, *, _buf=None):
+    """CPU stand-in of reshard.mm_push (epoch mode): the token carries the partial product."""
+    if _fake(a):
+        return a.new_empty((a.shape[0], b.shape[1]))
+    _EPOCHS["open_pushes"] += 1
+    return a @ b
+
+
+def ag_mm(x, w_shard, group, n_out, k_in, bias=None, *, _buf=None, _epoch=0):
     if _fake(x):
         return x.new_empty((x.shape[0], n_out)), w_shard.new_empty((n_out, k_in))
     w = all_gather_start(w_shard.reshape(-1), 0, group).view(n_out, k_in)
@@ -149,10 +171,13 @@ def mm_rs_push(a, b, group, *, _buf=None, _lane=0):
     return a @ b
 
 
-def rs_finish(tokens, group, *, _bufs=None, _numels=None, _scale=1.0, _out_dtype=None):
+def rs_finish(tokens, group, *, _bufs=None, _numels=None, _scale=1.0, _out_dtype=None, _epoch=0):
     n = len(group)
     if tokens and _fake(tokens[0]):
         return [t.new_empty((int(k),), dtype=_out_dtype or t.dtype) for t, k in zip(tokens, _numels)]
+    if _epoch:
+        # epoch protocol: a barrier must separate the pushes from their reduction
+        assert _EPOCHS["open_pushes"] == 0, "rs_finish(_epoch=1) without an epoch barrier in front"
     me = list(group).index(dist.get_rank())
     outs = []
     for t in tokens:
@@ -202,7 +227,7 @@ class FakeSymmRuntime:
         return FakeSymmRuntime._Buf(off, nbytes)
 
 
-FUSED_FUNCS = [ag_mm, mm_rs, mm_rs_push, rs_finish, symm_guard]
+FUSED_FUNCS = [ag_mm, mm_rs, mm_rs_push, mm_push, rs_finish, symm_guard, epoch_barrier]
 COMM_FUNCS = [all_reduce_start, all_gather_start, reduce_scatter_start, all_to_all_start]
 COMM_SYNC_FUNCS = [all_reduce_end, all_gather_end, reduce_scatter_end, all_to_all_end]
 CUSTOM_FUNCS = COMM_FUNCS + COMM_SYNC_FUNCS + [scatter_wrapper, copy_wrapper]

@@ -73,6 +73,8 @@ class Wide(torch.nn.Module):
 
 def _fusion_worker(rank, world, port, q, defer="0"):
     os.environ["OMP_NUM_THREADS"] = "1"
+    os.environ["EDB_EPOCH"] = "1" if defer == "epoch" else "0"
+    defer = "0" if defer == "epoch" else defer
     os.environ["EDB_DEFER_RS"] = defer
     os.environ["EDB_RS_LANE"] = defer  # deferred pushes also go to the communication lane
     torch.set_num_threads(1)
@@ -107,13 +109,20 @@ def _fusion_worker(rank, world, port, q, defer="0"):
     info["lane_pushes"] = sum(1 for n in compiled.graph.graph.nodes
                               if n.op == "call_function" and n.target is gloo_ops.mm_rs_push
                               and n.kwargs.get("_lane") == 1)
+    info["barriers_run"] = gloo_ops._EPOCHS["barriers"]
+    nodes = list(compiled.graph.graph.nodes)
+    info["order"] = [n.target.__name__ for n in nodes if n.op == "call_function" and
+                     n.target in (gloo_ops.epoch_barrier, gloo_ops.rs_finish, gloo_ops.mm_push,
+                                  gloo_ops.ag_mm) or getattr(n.target, "__name__", "") == "sgd_momentum_"]
+    info["ag_epoch"] = [n.kwargs.get("_epoch", 0) for n in nodes
+                        if n.op == "call_function" and n.target is gloo_ops.ag_mm]
     if rank == 0:
         q.put((ok, msg, info))
     dist.barrier()
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("defer", ["0", "1"])
+@pytest.mark.parametrize("defer", ["0", "1", "epoch"])
 def test_fusion_rewrite_on_cpu(defer):
     """The AG+GEMM / GEMM+RS peephole (lowering.fuse_collective_gemms) rewrites the zero3 graph of
     a 2-layer MLP: both weights' all-gathers fuse into their forward GEMMs and both weight
@@ -121,7 +130,8 @@ def test_fusion_rewrite_on_cpu(defer):
     in front of the optimizer); training still matches vanilla."""
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_fusion_worker, args=(r, 2, 29871 + int(defer), q, defer))
+    procs = [ctx.Process(target=_fusion_worker,
+                         args=(r, 2, 29871 + {"0": 0, "1": 1, "epoch": 2}[defer], q, defer))
              for r in range(2)]
     for p in procs:
         p.start()
@@ -132,7 +142,19 @@ def test_fusion_rewrite_on_cpu(defer):
     assert ok, msg
     assert info["fused"] == {"ag_mm": 2, "mm_rs": 2}, info
     assert info["comm_nodes"].get("reduce_scatter_start", 0) == 0, info
-    if defer == "1":
+    if defer == "epoch":
+        # epoch protocol: flag-free fused kernels, exactly two barriers per step — one between the
+        # last push and the reduction of the slots (in front of the optimizer), one at the very end
+        assert info["comm_nodes"].get("mm_push") == 2 and info["comm_nodes"].get("rs_finish") == 1, info
+        assert info["comm_nodes"].get("epoch_barrier") == 2, info
+        assert "symm_guard" not in info["comm_nodes"] and "mm_rs" not in info["comm_nodes"], info
+        assert info["ag_epoch"] == [1, 1], info
+        order = info["order"]
+        assert order.index("rs_finish") == order.index("epoch_barrier") + 1, order
+        assert max(i for i, k in enumerate(order) if k == "mm_push") < order.index("epoch_barrier"), order
+        assert order[-1] == "epoch_barrier", order
+        assert info["barriers_run"] == 2 * 3, info  # 3 steps
+    elif defer == "1":
         assert info["comm_nodes"].get("mm_rs_push") == 2 and info["comm_nodes"].get("rs_finish") == 1, info
         assert "mm_rs" not in info["comm_nodes"], info
         assert info["lane_pushes"] == 2, info
