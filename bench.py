@@ -163,7 +163,7 @@ def workload_config(args, world):
 # ---- this backend -----------------------------------------------------------------------------------------
 
 
-def gemm_roofline(torch, gemm, calls, peaks, sustained, fused_calls=(), rank=0):
+def gemm_roofline(torch, gemm, calls, peaks, sustained, fused_calls=(), rank=0, pf_map=None):
     """Dominant kernel = the tcgen05 GEMM.  Replays the step's GEMM launches (exact shapes, operand
     layouts and strides recorded from the compiled graph) back to back from a CUDA graph with CUDA
     events around the whole list on the launching stream; operands of consecutive launches differ
@@ -206,8 +206,16 @@ def gemm_roofline(torch, gemm, calls, peaks, sustained, fused_calls=(), rank=0):
             else:
                 reshard.mm_push(u, v, c["group"], _buf=c["buf"])
 
-    for a, b in ops:
-        gemm.mm(a, b)
+    pf_map = pf_map or {}
+
+    def run_plain(mm):
+        for i, (a, b) in enumerate(ops):
+            if mm is gemm.mm and i in pf_map:
+                gemm.mm(a, b, _pf=pf_map[i])  # with its all-gather prefetch passengers
+            else:
+                mm(a, b)
+
+    run_plain(gemm.mm)
     run_fused()
     torch.cuda.synchronize()
     # replayed from a CUDA graph like the step itself: eager launches of 30-us kernels would measure
@@ -218,8 +226,7 @@ def gemm_roofline(torch, gemm, calls, peaks, sustained, fused_calls=(), rank=0):
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             with torch.cuda.graph(graph, stream=side):
-                for a, b in ops:
-                    mm(a, b)
+                run_plain(mm)
                 if mm is gemm.mm:
                     run_fused()
             graph.replay()
@@ -240,7 +247,7 @@ def gemm_roofline(torch, gemm, calls, peaks, sustained, fused_calls=(), rank=0):
     # context only: what cuBLAS reaches on the plain GEMMs of the list (same operands, same graph
     # replay); shapes cuBLAS cannot align (LM head, vocab 50257) hit its sm_75-class `align1` kernels
     cublas_tf = None
-    if ops and not fused_ops:
+    if ops and not fused_ops and not pf_map:
         for a, b in ops:
             torch.mm(a, b)
         torch.cuda.synchronize()
@@ -250,7 +257,7 @@ def gemm_roofline(torch, gemm, calls, peaks, sustained, fused_calls=(), rank=0):
     peak = peaks["bf16_tflops_sustained"] if sustained else peaks["bf16_tflops"]
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "r02_gemm_dram_traffic.json")
-    if os.path.exists(tpath) and not fused_ops:
+    if os.path.exists(tpath) and not fused_ops and not pf_map:
         with open(tpath) as f:
             traffic = json.load(f)
     return {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
@@ -258,8 +265,10 @@ def gemm_roofline(torch, gemm, calls, peaks, sustained, fused_calls=(), rank=0):
             "traffic": (traffic or {}).get("dram_bytes_per_launch"),
             "traffic_algorithmic_bytes_per_launch": (traffic or {}).get("algorithmic_bytes_per_launch"),
             "traffic_source": (traffic or {}).get("source"),
-            "kernel": "edb::k_gemm_bf16 (plain" + (", AG-fused and push-fused" if fused_ops else "") + ")",
+            "kernel": "edb::k_gemm_bf16 (plain" + (", with all-gather prefetch CTAs" if pf_map else "")
+                      + (", push-fused" if fused_ops else "") + ")",
             "launches_per_step": n_launch, "fused_launches_per_step": len(fused_ops),
+            "prefetch_carrying_launches_per_step": len(pf_map),
             "avg_launch_us": 1e3 * ms / n_launch,
             "gemm_ms_per_step": ms, "flops_per_step": flops,
             "cublas_same_launch_list_tflops": cublas_tf,
@@ -428,8 +437,9 @@ def run_edb(args):
     fused_calls = fused_all[:len(fused_all) // passes]
     # every rank replays (the fused kernels talk to the peers); rank 0 reports
     barrier()
+    pf_map = {i: d for i, d in gemm.recorded_prefetches().items() if i < len(calls)}
     roof = gemm_roofline(torch, gemm, calls, peaks, sustained=False, fused_calls=fused_calls,
-                         rank=rank)
+                         rank=rank, pf_map=pf_map)
     barrier()
     step_flops = train_flops_per_step(cfg, B, S)
     line = {

@@ -287,6 +287,10 @@ struct GemmParams {
   // m / push_mtc and is TMA-stored into that member's receive slot (store map cm.m[owner]) instead
   // of C; m_rot rotates the m order so that the ranks do not all push to the same owner at once
   int push_n, push_mtc, m_rot;
+  // how a pushing CTA retires: 2 = wait for the completion of its TMA stores + system-scope fence,
+  // 1 = completion only, 0 = only until the staging smem has been read (grid completion then
+  // covers the stores, as it does for every ordinary TMA-store epilogue)
+  int push_sync;
 };
 
 // Fusion modes of the GEMM kernel
@@ -301,6 +305,7 @@ struct GemmParams {
 //                kernel reduces the n slots in rank order with scale + cast
 //                (aten.mm -> reduce_scatter_start in one kernel)
 enum { MODE_PLAIN = 0, MODE_AG = 1, MODE_RS = 2 };
+constexpr int kMaxPfItems = 4;
 constexpr int F_TILECNT = 96;  // flag-block words [96,104): per-chunk completion counters
 
 struct FusedArgs {
@@ -328,6 +333,17 @@ struct FusedArgs {
   // edb_epoch_barrier earlier on the stream made every member's shard final, and the next barrier
   // comes before anybody overwrites it.  Only the local chunk flags (comm CTAs -> MMA CTAs) remain.
   int epoch;
+  // all-gather PREFETCH riding on a plain GEMM (edb_gemm_pf_bf16): the first pf_ctas CTAs of the
+  // grid do no MMA work; they copy, for each item and each group member p, the byte range
+  // [src_off, src_off + bytes) of p's symmetric heap into local dst_off + p * dst_stride — the
+  // operand of a LATER kernel (next layer's weight), so nobody in this kernel waits for the data
+  // and the consumer is an ordinary GEMM.  Epoch protocol: the sources are final since the last
+  // edb_epoch_barrier.
+  int pf_ctas, pf_items, pf_n;
+  const char* pf_heap[kMaxGroup];  // members' heaps (peer mapped), [pf_me] = local
+  char* pf_local;
+  uint64_t pf_src[kMaxPfItems], pf_dst[kMaxPfItems];
+  int64_t pf_bytes[kMaxPfItems], pf_stride[kMaxPfItems];
 };
 constexpr int F_PUSHED = F_CHUNK + 8;  // [40..47] PUSHED[p]: peer p's deferred-RS tiles of op q landed
 
@@ -388,6 +404,164 @@ __device__ __forceinline__ void spin_wait_gpu(const uint64_t* flag, uint64_t tar
   }
 }
 
+// Prefetch CTA (see FusedArgs::pf_*): one thread drives a TMA bulk-copy ring peer HBM -> smem ->
+// local HBM over the 16 KiB blocks of all (item, member) ranges; block b belongs to CTA
+// b % pf_ctas, so the CTAs stream neighbouring blocks and every range finishes at about the same
+// time.  No flags: the consumer is a later kernel on the stream.
+__device__ __forceinline__ void pf_role(const FusedArgs& fa, uint8_t* smem, int idx, int nctas) {
+  constexpr int S = 8, D = 5, SLOT = 16384;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + S * SLOT);
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < S; ++s) mbar_init(&full[s], 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
+  if (threadIdx.x != 0) return;
+  // flat block numbering: item-major, member-major inside an item, remote members first
+  uint32_t n_load = 0, n_store = 0;
+  struct Cur { int it, k; int64_t blk; };
+  auto advance = [&](Cur& c) {
+    // move to the next block owned by this CTA; returns false at the end
+    while (c.it < fa.pf_items) {
+      const int64_t nblk = (fa.pf_bytes[c.it] + SLOT - 1) / SLOT;
+      if (c.blk < nblk) return true;
+      c.blk -= nblk;  // keep the round-robin phase across ranges
+      if (++c.k == fa.pf_n) {
+        c.k = 0;
+        ++c.it;
+      }
+    }
+    return false;
+  };
+  Cur ld = {0, 0, (int64_t)idx}, stc = {0, 0, (int64_t)idx};
+  bool more = advance(ld);
+  int inflight = 0;
+  while (more || inflight > 0) {
+    if (more && inflight < D) {
+      const uint32_t slot = n_load % S;
+      if (n_load >= (uint32_t)S) tma_store_wait_read<S - D - 1>();
+      const int p = (fa.f.me + 1 + ld.k) % fa.pf_n;  // own range last (a local copy)
+      const int64_t off = ld.blk * SLOT;
+      const int64_t left = fa.pf_bytes[ld.it] - off;
+      const uint32_t bytes = (uint32_t)(left < SLOT ? left : SLOT);
+      mbar_expect_tx(&full[slot], bytes);
+      bulk_load(smem + slot * SLOT, fa.pf_heap[p] + fa.pf_src[ld.it] + off, bytes, &full[slot]);
+      ++n_load;
+      ++inflight;
+      ld.blk += nctas;
+      more = advance(ld);
+      continue;
+    }
+    // oldest load -> store
+    advance(stc);
+    const uint32_t slot = n_store % S;
+    mbar_wait(&full[slot], (n_store / S) & 1);
+    const int p = (fa.f.me + 1 + stc.k) % fa.pf_n;
+    const int64_t off = stc.blk * SLOT;
+    const int64_t left = fa.pf_bytes[stc.it] - off;
+    const uint32_t bytes = (uint32_t)(left < SLOT ? left : SLOT);
+    bulk_store(fa.pf_local + fa.pf_dst[stc.it] + (int64_t)p * fa.pf_stride[stc.it] + off,
+               smem + slot * SLOT, bytes);
+    tma_store_commit();
+    ++n_store;
+    --inflight;
+    stc.blk += nctas;
+  }
+  tma_store_wait_all();
+}
+
+__global__ void __launch_bounds__(32, 1) k_ag_prefetch(const __grid_constant__ FusedArgs fa) {
+  extern __shared__ uint8_t pf_smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(pf_smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  pf_role(fa, smem, (int)blockIdx.x, (int)gridDim.x);
+}
+
+// Epoch-mode comm CTA: the same TMA bulk-copy ring, but ONE software pipeline over the blocks of
+// all shards — no drain between shards (the per-op variant below pays a load + store latency per
+// shard, ~4 us x (n-1) at n = 8) and no flag traffic with the peers at all.  A shard is announced
+// to the MMA CTAs once `wait_group` proves its last store complete, which lags kLag stores behind.
+__device__ __forceinline__ void ag_comm_role_epoch(const FusedArgs& fa, uint8_t* smem, int comm_idx,
+                                                   uint64_t q) {
+  constexpr int S = 8, D = 5, SLOT = 16384, kLag = 2;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + S * SLOT);
+  const FlagCtx& f = fa.f;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < S; ++s) mbar_init(&full[s], 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
+  if (threadIdx.x != 0) return;
+  const int64_t per = ((fa.shard_bytes + fa.n_comm - 1) / fa.n_comm + SLOT - 1) / SLOT * SLOT;
+  const int64_t lo = (int64_t)comm_idx * per;
+  const int64_t hi = lo + per < fa.shard_bytes ? lo + per : fa.shard_bytes;
+  const int nblk = hi > lo ? (int)((hi - lo + SLOT - 1) / SLOT) : 0;
+  const int total = nblk * f.n;
+  auto announce = [&](int k) {
+    const int c = (f.me + k) % f.n;
+    const unsigned long long prev =
+        atomicAdd(reinterpret_cast<unsigned long long*>(f.local + F_AGTILE + c), 1ULL);
+    if (prev == (unsigned long long)fa.n_comm - 1) {
+      f.local[F_AGTILE + c] = 0;
+      __threadfence();
+      st_release_gpu(f.local + F_AGCHUNK + c, q);
+    }
+  };
+  if (nblk == 0) {
+    for (int k = 0; k < f.n; ++k) announce(k);  // nothing to move for this CTA: still counted
+  } else {
+    uint32_t n_load = 0, n_store = 0;
+    int next_announce = 0;  // shards [0, next_announce) have been announced
+    for (int g = 0; g < total + D; ++g) {
+      if (g < total) {
+        const int k = g / nblk, i = g - k * nblk;
+        const int c = (f.me + k) % f.n;
+        const uint32_t slot = n_load % S;
+        if (n_load >= (uint32_t)S) tma_store_wait_read<S - D - 1>();
+        const int64_t left = hi - lo - (int64_t)i * SLOT;
+        const uint32_t bytes = (uint32_t)(left < SLOT ? left : SLOT);
+        mbar_expect_tx(&full[slot], bytes);
+        bulk_load(smem + slot * SLOT, fa.shard_src[c] + lo + (int64_t)i * SLOT, bytes, &full[slot]);
+        ++n_load;
+      }
+      if (g >= D) {
+        const int j = g - D;
+        const int k = j / nblk, i = j - k * nblk;
+        const int c = (f.me + k) % f.n;
+        const uint32_t slot = n_store % S;
+        mbar_wait(&full[slot], (n_store / S) & 1);
+        const int64_t left = hi - lo - (int64_t)i * SLOT;
+        const uint32_t bytes = (uint32_t)(left < SLOT ? left : SLOT);
+        bulk_store(fa.full_dst + (int64_t)c * fa.shard_bytes + lo + (int64_t)i * SLOT,
+                   smem + slot * SLOT, bytes);
+        tma_store_commit();
+        ++n_store;
+        // shard `next_announce` ended with store number (next_announce + 1) * nblk: once kLag more
+        // stores have been committed, wait_group<kLag> proves it complete
+        if ((int)n_store - kLag >= (next_announce + 1) * nblk) {
+          asm volatile("cp.async.bulk.wait_group %0;" ::"n"(kLag) : "memory");
+          fence_proxy_async_all();
+          __threadfence();
+          while ((int)n_store - kLag >= (next_announce + 1) * nblk) announce(next_announce++);
+        }
+      }
+    }
+    tma_store_wait_all();
+    fence_proxy_async_all();
+    __threadfence();
+    while (next_announce < f.n) announce(next_announce++);
+  }
+  // advance the launch number once every CTA of this launch has read the old one
+  const unsigned long long prev =
+      atomicAdd(reinterpret_cast<unsigned long long*>(f.local + F_AGDONE), 1ULL);
+  if (prev == (unsigned long long)fa.n_comm - 1) {
+    f.local[F_AGDONE] = 0;
+    while (ld_acquire_gpu(f.local + F_AGCNT) < (uint64_t)gridDim.x) __nanosleep(64);
+    f.local[F_AGCNT] = 0;
+    st_release_gpu(f.local + F_AGSEQ, q);
+  }
+}
+
 // MODE_AG comm CTA: one thread drives a TMA bulk-copy ring  peer HBM -> smem -> local HBM.
 __device__ __forceinline__ void ag_comm_role(const FusedArgs& fa, uint8_t* smem, int comm_idx,
                                              uint64_t q) {
@@ -400,9 +574,8 @@ __device__ __forceinline__ void ag_comm_role(const FusedArgs& fa, uint8_t* smem,
   }
   __syncthreads();
   if (threadIdx.x != 0) return;
-  const bool epoch = fa.epoch != 0;
-  const int w_chunk = epoch ? F_AGCHUNK : F_CHUNK, w_tile = epoch ? F_AGTILE : F_TILECNT;
-  if (comm_idx == 0 && !epoch) {
+  const int w_chunk = F_CHUNK, w_tile = F_TILECNT;
+  if (comm_idx == 0) {
     // my shard was written by earlier kernels of this stream: publish it
     __threadfence_system();
     for (int pidx = 0; pidx < f.n; ++pidx)
@@ -415,7 +588,7 @@ __device__ __forceinline__ void ag_comm_role(const FusedArgs& fa, uint8_t* smem,
   const int64_t nblk = hi > lo ? (hi - lo + SLOT - 1) / SLOT : 0;
   for (int k = 0; k < f.n; ++k) {
     const int c = (f.me + k) % f.n;
-    if (c != f.me && !epoch) spin_wait_sys(f.local + F_READY + c, q, f.timeout_ns, f.local + F_ERR);
+    if (c != f.me) spin_wait_sys(f.local + F_READY + c, q, f.timeout_ns, f.local + F_ERR);
     const char* src = fa.shard_src[c] + lo;
     char* dst = fa.full_dst + (int64_t)c * fa.shard_bytes + lo;
     for (int64_t i = 0; i < nblk + D; ++i) {
@@ -449,18 +622,6 @@ __device__ __forceinline__ void ag_comm_role(const FusedArgs& fa, uint8_t* smem,
       __threadfence();
       st_release_gpu(f.local + w_chunk + c, q);
     }
-  }
-  if (epoch) {
-    // advance the launch number once every CTA of this launch has read the old one
-    const unsigned long long prev =
-        atomicAdd(reinterpret_cast<unsigned long long*>(f.local + F_AGDONE), 1ULL);
-    if (prev == (unsigned long long)fa.n_comm - 1) {
-      f.local[F_AGDONE] = 0;
-      while (ld_acquire_gpu(f.local + F_AGCNT) < (uint64_t)gridDim.x) __nanosleep(64);
-      f.local[F_AGCNT] = 0;
-      st_release_gpu(f.local + F_AGSEQ, q);
-    }
-    return;
   }
   // end of the op: DONE to the peers, SEQ locally — but only after every CTA of this launch has
   // read the old SEQ (slow starters would otherwise compute the wrong op number)
@@ -567,7 +728,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
   __shared__ uint64_t s_q;
   __shared__ int s_last;
   uint64_t q = 0;
-  const int n_gemm_ctas = (MODE == MODE_AG) ? (int)gridDim.x - fa.n_comm : (int)gridDim.x;
+  const int n_gemm_ctas = (MODE == MODE_AG) ? (int)gridDim.x - fa.n_comm
+                                             : (MODE == MODE_PLAIN ? (int)gridDim.x - fa.pf_ctas : (int)gridDim.x);
 
   if (MODE == MODE_RS) {
     if (fa.rs_defer) {
@@ -593,11 +755,18 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
     // the comm CTAs are the producers the MMA CTAs spin on: they get the LOWEST block indices so
     // that they are scheduled first even when the grid is not fully co-resident
     if ((int)blockIdx.x < fa.n_comm) {
-      ag_comm_role(fa, smem, (int)blockIdx.x, q);
+      if (fa.epoch) ag_comm_role_epoch(fa, smem, (int)blockIdx.x, q);
+      else ag_comm_role(fa, smem, (int)blockIdx.x, q);
       return;
     }
   }
-  const int cta = (MODE == MODE_AG) ? (int)blockIdx.x - fa.n_comm : (int)blockIdx.x;
+  if (MODE == MODE_PLAIN && fa.pf_ctas > 0 && (int)blockIdx.x < fa.pf_ctas) {
+    // prefetch CTAs (whole clusters when CL == 2): lowest block indices, no part in the GEMM
+    pf_role(fa, smem, (int)blockIdx.x, fa.pf_ctas);
+    return;
+  }
+  const int cta = (MODE == MODE_AG) ? (int)blockIdx.x - fa.n_comm
+                                    : (MODE == MODE_PLAIN ? (int)blockIdx.x - fa.pf_ctas : (int)blockIdx.x);
 
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + kStages * kSmemABytes;
@@ -937,12 +1106,16 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
       }
     }
     if (issuer) {
-      tma_store_wait_all();
-      if (MODE == MODE_PLAIN && p.push_n > 0) {
-        // the tiles went into peer memory: make them visible system-wide before this CTA retires
-        // (the next edb_epoch_barrier on the stream then orders them before its signal)
-        fence_proxy_async_all();
-        __threadfence_system();
+      if (MODE == MODE_PLAIN && p.push_n > 0 && p.push_sync == 0) {
+        tma_store_wait_read<0>();
+      } else {
+        tma_store_wait_all();
+        if (MODE == MODE_PLAIN && p.push_n > 0 && p.push_sync >= 2) {
+          // the tiles went into peer memory: make them visible system-wide before this CTA retires
+          // (the next edb_epoch_barrier on the stream then orders them before its signal)
+          fence_proxy_async_all();
+          __threadfence_system();
+        }
       }
     }
   }
@@ -1317,9 +1490,55 @@ struct PushSpec {
   char* slot[kMaxGroup];     // member p's receive slot for MY rows: [rows_per, N] bf16, ld = N
 };
 
+// pf: NULL, or the all-gather prefetch that rides on this GEMM
+struct PfSpec {
+  int gid, n_items;
+  const uint64_t* src_offs;
+  const uint64_t* dst_offs;
+  const int64_t* bytes;
+  const int64_t* dst_strides;
+};
+
+static int fill_prefetch(FusedArgs* fa, const PfSpec* pf, int want_ctas) {
+  Runtime& r = rt();
+  if (!r.inited) return set_error(EDB_E_STATE, "runtime not initialised (call edb_init)");
+  if (pf->gid < 0 || pf->gid >= r.ngroups) return set_error(EDB_E_INVALID, "bad group id %d", pf->gid);
+  if (pf->n_items < 0 || pf->n_items > kMaxPfItems)
+    return set_error(EDB_E_UNSUPPORTED, "prefetch: at most %d items per launch", kMaxPfItems);
+  const Group& g = r.groups[pf->gid];
+  fa->f.n = g.n;
+  fa->f.me = g.me;
+  fa->pf_n = g.n;
+  fa->pf_items = pf->n_items;
+  fa->pf_local = r.heap;
+  for (int p = 0; p < g.n; ++p) fa->pf_heap[p] = r.peer_heap[g.ranks[p]];
+  int64_t blocks = 0;
+  for (int i = 0; i < pf->n_items; ++i) {
+    const int64_t b = pf->bytes[i], st = pf->dst_strides[i];
+    if (b <= 0 || (b & 15) || (pf->src_offs[i] & 15) || (pf->dst_offs[i] & 15) || (st & 15) || st < b)
+      return set_error(EDB_E_INVALID, "prefetch item %d: ranges must be 16-byte aligned, stride >= bytes", i);
+    if (pf->src_offs[i] < kUserOffset || pf->src_offs[i] + (uint64_t)b > r.heap_bytes ||
+        pf->dst_offs[i] < kUserOffset ||
+        pf->dst_offs[i] + (uint64_t)st * (g.n - 1) + (uint64_t)b > r.heap_bytes)
+      return set_error(EDB_E_INVALID, "prefetch item %d: symmetric range out of bounds", i);
+    fa->pf_src[i] = pf->src_offs[i];
+    fa->pf_dst[i] = pf->dst_offs[i];
+    fa->pf_bytes[i] = b;
+    fa->pf_stride[i] = st;
+    blocks += (b + 16383) / 16384 * g.n;
+  }
+  int ctas = want_ctas;
+  if (blocks < ctas) ctas = (int)blocks;
+  ctas &= ~1;  // whole clusters when the GEMM runs CTA pairs
+  if (ctas < 2 && blocks > 0) ctas = 2;
+  fa->pf_ctas = pf->n_items > 0 ? ctas : 0;
+  return EDB_OK;
+}
+
 static int gemm_plain_impl(void* C, const void* A, const void* B, const void* bias, int64_t M,
                            int64_t N, int64_t K, int64_t lda, int64_t ldb, int64_t ldc, int a_kmajor,
-                           int b_kmajor, void* stream, const PushSpec* push) {
+                           int b_kmajor, void* stream, const PushSpec* push,
+                           const PfSpec* pf = nullptr) {
   int rc = check_operands(A, B, C, bias, M, N, K, lda, ldb, ldc, "edb_gemm_bf16");
   if (rc) return rc;
   const int sms = sm_count_now();
@@ -1350,12 +1569,22 @@ static int gemm_plain_impl(void* C, const void* A, const void* B, const void* bi
   p.push_n = 0;
   p.push_mtc = 1;
   p.m_rot = 0;
+  p.push_sync = (int)rt().push_sync;
   FusedArgs fa;
   memset(&fa, 0, sizeof(fa));
   CMaps cm;
   memset(&cm, 0, sizeof(cm));
   PushDst pd;
   memset(&pd, 0, sizeof(pd));
+  int sms_gemm = sms;  // SMs left to the GEMM when prefetch CTAs ride along
+  if (pf && pf->n_items > 0) {
+    int want = (int)rt().comm_ctas;
+    if (want < 2) want = 2;
+    if (want > sms / 4) want = sms / 4;
+    rc = fill_prefetch(&fa, pf, want);
+    if (rc) return rc;
+    sms_gemm = sms - fa.pf_ctas;
+  }
   if (push) {
     p.push_n = push->n;
     p.push_mtc = (int)(push->rows_per / BM);
@@ -1382,8 +1611,8 @@ static int gemm_plain_impl(void* C, const void* A, const void* B, const void* bi
   const int units = (cl == 2 ? ((p.m_tiles + 1) / 2) : p.m_tiles) * p.n_tiles;
   const int ctas = units * cl;
   const int k_blocks = (int)((K + BK - 1) / BK);
-  if (rt().gemm_splitk && 2 * ctas <= sms && k_blocks >= 16) {
-    int splits = sms / ctas;
+  if (rt().gemm_splitk && 2 * ctas <= sms_gemm && k_blocks >= 16) {
+    int splits = sms_gemm / ctas;
     if (splits > k_blocks / 8) splits = k_blocks / 8;
     if (splits > 8) splits = 8;
     while (splits > 1 && (size_t)splits * (size_t)M * (size_t)p.ldp * sizeof(float) > kSplitKBytes)
@@ -1400,12 +1629,13 @@ static int gemm_plain_impl(void* C, const void* A, const void* B, const void* bi
   int grid;
   if (cl == 2) {
     const int pairs = units * p.splits;
-    const int clusters = pairs < sms / 2 ? pairs : sms / 2;
+    const int clusters = pairs < sms_gemm / 2 ? pairs : sms_gemm / 2;
     grid = 2 * clusters;
   } else {
     const int tiles = units * p.splits;
-    grid = tiles < sms ? tiles : sms;
+    grid = tiles < sms_gemm ? tiles : sms_gemm;
   }
+  grid += fa.pf_ctas;
   rc = dispatch_gemm<MODE_PLAIN>(bn, a_kmajor != 0, b_kmajor != 0, ta, tb, tc, p, fa, cm, grid, st, cl);
   if (rc || p.splits == 1) return rc;
   const int64_t groups = (int64_t)M * (p.ldp / 4);
@@ -1422,6 +1652,42 @@ int edb_gemm_bf16(void* C, const void* A, const void* B, const void* bias, int64
                   int accumulate_into_c, void* stream) {
   if (accumulate_into_c) return set_error(EDB_E_UNSUPPORTED, "edb_gemm_bf16: accumulate_into_c");
   return gemm_plain_impl(C, A, B, bias, M, N, K, lda, ldb, ldc, a_kmajor, b_kmajor, stream, nullptr);
+}
+
+int edb_gemm_pf_bf16(void* C, const void* A, const void* B, const void* bias, int64_t M, int64_t N,
+                     int64_t K, int64_t lda, int64_t ldb, int64_t ldc, int a_kmajor, int b_kmajor,
+                     int gid, int n_items, const uint64_t* src_offs, const uint64_t* dst_offs,
+                     const int64_t* bytes, const int64_t* dst_strides, void* stream) {
+  PfSpec pf = {gid, n_items, src_offs, dst_offs, bytes, dst_strides};
+  return gemm_plain_impl(C, A, B, bias, M, N, K, lda, ldb, ldc, a_kmajor, b_kmajor, stream, nullptr,
+                         n_items > 0 ? &pf : nullptr);
+}
+
+int edb_ag_prefetch(int gid, int n_items, const uint64_t* src_offs, const uint64_t* dst_offs,
+                    const int64_t* bytes, const int64_t* dst_strides, void* stream) {
+  if (n_items <= 0) return EDB_OK;
+  Runtime& r = rt();
+  static bool configured = false;
+  const int smem = 8 * 16384 + 1024 + 128;
+  if (!configured) {
+    EDB_CUDA(cudaFuncSetAttribute(k_ag_prefetch, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  for (int done = 0; done < n_items; done += kMaxPfItems) {
+    const int k = n_items - done < kMaxPfItems ? n_items - done : kMaxPfItems;
+    PfSpec pf = {gid, k, src_offs + done, dst_offs + done, bytes + done, dst_strides + done};
+    FusedArgs fa;
+    memset(&fa, 0, sizeof(fa));
+    // nothing else needs the SMs: one CTA per SM (1 thread each drives a 5-deep 16 KiB ring)
+    int rc = fill_prefetch(&fa, &pf, r.sm_count);
+    if (rc) return rc;
+    if (fa.pf_ctas == 0) continue;
+    k_ag_prefetch<<<fa.pf_ctas, 32, smem, (cudaStream_t)stream>>>(fa);
+    count_launch();
+    rc = cuda_check(cudaGetLastError(), "k_ag_prefetch launch");
+    if (rc) return rc;
+  }
+  return EDB_OK;
 }
 
 int edb_gemm_push_bf16(int gid, uint64_t recv_off, const void* A, const void* B, int64_t M,
@@ -1508,6 +1774,7 @@ static int ag_gemm_impl(int gid, void* C, const void* A, const void* bias, uint6
   p.push_n = 0;
   p.push_mtc = 1;
   p.m_rot = 0;
+  p.push_sync = 0;
   const int sms = r.sm_count;
   int n_comm = (int)r.comm_ctas;
   if (n_comm < 1) n_comm = 1;
@@ -1683,6 +1950,7 @@ static int gemm_rs_impl(int gid, void* dst, uint64_t recv_off, uint64_t state_of
   p.push_n = 0;
   p.push_mtc = 1;
   p.m_rot = 0;
+  p.push_sync = 0;
   fa.recv_base = recv;
   fa.chunk_bytes = (int64_t)chunk_bytes;
   fa.rs_dst = dst;

@@ -242,6 +242,7 @@ int edb_set_option(const char* name, int64_t value) {
   else if (!strcmp(name, "gemm_splitk")) r.gemm_splitk = value;
   else if (!strcmp(name, "gemm_force_bn")) r.gemm_force_bn = value;
   else if (!strcmp(name, "ll_max_bytes")) r.ll_max_bytes = value;
+  else if (!strcmp(name, "push_sync")) r.push_sync = value;
   else return set_error(EDB_E_INVALID, "edb_set_option: unknown option '%s'", name);
   return EDB_OK;
 }
@@ -256,6 +257,7 @@ int edb_get_option(const char* name, int64_t* out) {
   else if (!strcmp(name, "gemm_splitk")) *out = r.gemm_splitk;
   else if (!strcmp(name, "gemm_force_bn")) *out = r.gemm_force_bn;
   else if (!strcmp(name, "ll_max_bytes")) *out = r.ll_max_bytes;
+  else if (!strcmp(name, "push_sync")) *out = r.push_sync;
   else if (!strcmp(name, "sm_count")) *out = r.sm_count;
   else if (!strcmp(name, "rank")) *out = r.rank;
   else if (!strcmp(name, "world")) *out = r.world;

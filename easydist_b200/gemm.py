@@ -39,12 +39,14 @@ def reset_stats():
     _stats["unsupported"] = {}
     del _calls[:]
     del _fused_calls[:]
+    _pf_calls.clear()
 
 
 def recorded_calls():
     return list(_calls)
 
 
+_pf_calls = {}  # index into _calls -> prefetch descriptor carried by that launch
 _fused_calls = []  # dicts: kind ("ag" | "push"), M, N, K, layouts / strides, group, _buf
 
 
@@ -145,7 +147,26 @@ def join(x):
     return x
 
 
-def _launch(a, b, bias, side=0):
+def _pf_arrays(pf):
+    import ctypes
+    items = pf["items"]
+    k = len(items)
+    return (k, (ctypes.c_uint64 * k)(*[int(i[0]) for i in items]),
+            (ctypes.c_uint64 * k)(*[int(i[1]) for i in items]),
+            (ctypes.c_int64 * k)(*[int(i[2]) for i in items]),
+            (ctypes.c_int64 * k)(*[int(i[3]) for i in items]))
+
+
+def prefetch_standalone(pf, device):
+    """The all-gather prefetch `pf` as its own launch (edb_ag_prefetch)."""
+    from .runtime import get_runtime
+    rt = get_runtime()
+    gid = rt.group(pf["group"])
+    k, src, dst, nbytes, stride = _pf_arrays(pf)
+    check(rt.lib.edb_ag_prefetch(gid, k, src, dst, nbytes, stride, rt.stream()))
+
+
+def _launch(a, b, bias, side=0, pf=None):
     pa = _prepare(a, 1)
     pb = _prepare(b, 0)
     if pa is None or pb is None:
@@ -160,14 +181,26 @@ def _launch(a, b, bias, side=0):
     lib = _lib.load()
     # operands were staged and the output allocated on the caller's stream; only the kernel forks
     with _SideStream(side) as fork:
-        check(lib.edb_gemm_bf16(out.data_ptr(), ta.data_ptr(), tb.data_ptr(),
-                                bias.data_ptr() if bias is not None else None, M, N, K, lda, ldb,
-                                ldc, 1 if a_k else 0, 1 if b_k else 0, 0, _stream(a)))
+        if pf:
+            # the GEMM carries an all-gather prefetch for a later kernel (lowering.prefetch_param_gathers)
+            from .runtime import get_runtime
+            gid = get_runtime().group(pf["group"])
+            k, src, dst, nbytes, stride = _pf_arrays(pf)
+            check(lib.edb_gemm_pf_bf16(out.data_ptr(), ta.data_ptr(), tb.data_ptr(),
+                                       bias.data_ptr() if bias is not None else None, M, N, K, lda,
+                                       ldb, ldc, 1 if a_k else 0, 1 if b_k else 0, gid, k, src, dst,
+                                       nbytes, stride, _stream(a)))
+        else:
+            check(lib.edb_gemm_bf16(out.data_ptr(), ta.data_ptr(), tb.data_ptr(),
+                                    bias.data_ptr() if bias is not None else None, M, N, K, lda, ldb,
+                                    ldc, 1 if a_k else 0, 1 if b_k else 0, 0, _stream(a)))
     if fork.on:
         out._edb_gemm_pending = (fork.done, (ta, tb))
     _stats["edb_gemm"] += 1
     if len(_calls) < 8192:
         _calls.append((M, N, K, bool(a_k), bool(b_k), tuple(a.stride()), tuple(b.stride())))
+        if pf:
+            _pf_calls[len(_calls) - 1] = pf
     return out if ldc == N else out[:, :N]
 
 
@@ -182,30 +215,40 @@ def _count_unsupported(a, b):
     _stats["aten_mm"] += 1
 
 
-def mm(a, b, *, _side=0):
+def mm(a, b, *, _side=0, _pf=None):
     """aten.mm.default(a, b) with bf16 operands on the tcgen05 kernel.  `_side=1`: launched on the
-    side stream; some later `join` of the result (or of a view of it) must precede its first use."""
+    side stream; some later `join` of the result (or of a view of it) must precede its first use.
+    `_pf`: all-gather prefetch carried by this launch ({"group": ranks, "items": [(src_off,
+    dst_off, bytes, dst_stride), ...]}, see edb_gemm_pf_bf16)."""
     if isinstance(a, FakeTensor) or isinstance(b, FakeTensor) or a.is_meta:
         return torch.ops.aten.mm.default(a, b)
-    out = _launch(a, b, None, _side) if _eligible(a, b) else None
+    out = _launch(a, b, None, _side, _pf) if _eligible(a, b) else None
     if out is None:
+        if _pf:
+            prefetch_standalone(_pf, a.device)  # the gather must happen whoever runs the GEMM
         _count_unsupported(a, b)
         return torch.ops.aten.mm.default(a, b)
     return out
 
 
-def addmm(bias, a, b):
+def recorded_prefetches():
+    return dict(_pf_calls)
+
+
+def addmm(bias, a, b, *, _pf=None):
     """aten.addmm.default(bias, a, b) = bias + a @ b, bias added in the GEMM epilogue."""
     if isinstance(a, FakeTensor) or isinstance(b, FakeTensor) or a.is_meta:
         return torch.ops.aten.addmm.default(bias, a, b)
     if _eligible(a, b) and bias.dim() == 1 and bias.dtype == torch.bfloat16 and \
             bias.shape[0] == b.shape[1]:
-        out = _launch(a, b, bias)
+        out = _launch(a, b, bias, 0, _pf)
         if out is not None:
             return out
     if _eligible(a, b):
-        out = _launch(a, b, None)
+        out = _launch(a, b, None, 0, _pf)
         if out is not None:
             return torch.ops.aten.add.Tensor(out, bias)
+    if _pf:
+        prefetch_standalone(_pf, a.device)
     _count_unsupported(a, b)
     return torch.ops.aten.addmm.default(bias, a, b)

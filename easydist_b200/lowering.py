@@ -910,14 +910,143 @@ def dispatch_compute(gm):
             continue
         if node.target == aten.mm.default:
             node.target = gemm.mm
+            if "edb_pf" in node.meta:
+                node.kwargs = {"_pf": node.meta["edb_pf"]}
             n += 1
         elif node.target == aten.addmm.default and not node.kwargs:
             node.target = gemm.addmm
+            if "edb_pf" in node.meta:
+                node.kwargs = {"_pf": node.meta["edb_pf"]}
             n += 1
     gm.recompile()
     if os.environ.get("EDB_GEMM_SIDE", "0") == "1":
         n += parallel_wgrad_gemms(gm)
     return n
+
+
+def prefetch_param_gathers(gm, io, rt, ranks, ops=_default_ops):
+    """Epoch mode: every dim-0 all-gather of a parameter shard (zero3: compile_dp.py:136-150 puts
+    one in front of each use) becomes a PREFETCH.
+
+    Between the barrier behind the optimizer and the barrier in front of the next one, parameter
+    shards never change, so a parameter is gathered ONCE per step into a persistent symmetric
+    buffer and every use reads that buffer (`ops.gathered`, a view).  The copies ride on the bf16
+    GEMMs that run earlier in the step: `edb_gemm_pf_bf16` gives a GEMM kernel a few extra CTAs
+    that pull the peers' shards of an upcoming layer over NVLink while the other CTAs compute, so
+    the all-gather of layer i+1 overlaps the tensor-core work of layer i and neither waits
+    (the reference issues a blocking NCCL all-gather in front of every use, sharding.py:105-119).
+    Packing is earliest-first under a per-GEMM byte budget (its FLOPs at ~900 TFLOP/s times
+    EDB_PF_GBPS, default 300 GB/s of NVLink pull); whatever is needed before the first GEMM
+    (embeddings, first layer) goes into one stand-alone `ops.ag_prefetch` at the top of the graph.
+
+    Returns ({placeholder name: SymmBuffer home of the shard}, number of parameters handled)."""
+    import os
+    from collections import deque
+    graph = gm.graph
+    n = len(ranks)
+    order = {nd: i for i, nd in enumerate(graph.nodes)}
+    uses = {}
+    for ag_s in [x for x in graph.nodes if x.op == "call_function" and x.target is ops.all_gather_start]:
+        ph = ag_s.args[0]
+        if not (isinstance(ph, Node) and ph.op == "placeholder" and ph in io.param_ph):
+            continue
+        if ag_s.args[1] != 0 or list(ag_s.args[2]) != list(ranks) or ag_s.kwargs or len(ag_s.users) != 1:
+            continue
+        ag_e = next(iter(ag_s.users))
+        if ag_e.target is not ops.all_gather_end:
+            continue
+        val = ph.meta.get("val")
+        if not isinstance(val, torch.Tensor) or (val.numel() * val.element_size()) % 16 or val.numel() == 0:
+            continue
+        uses.setdefault(ph, []).append((ag_s, ag_e))
+    if not uses:
+        return {}, 0
+    rehomed, bufs = {}, {}
+    for ph in uses:
+        nbytes = _nbytes(ph.meta["val"])
+        shard = rt.alloc(nbytes, align=1024)
+        full = rt.alloc(nbytes * n, align=1024)
+        rehomed[ph.name] = shard
+        bufs[ph] = (shard, full, nbytes)
+    first_use = {ph: min(order[a] for a, _ in lst) for ph, lst in uses.items()}
+    gathered_nodes = {}
+    for ph, lst in uses.items():
+        shard, full, nbytes = bufs[ph]
+        for ag_s, ag_e in lst:
+            with graph.inserting_before(ag_s):
+                g = graph.call_function(ops.gathered, args=(ph, list(ranks)),
+                                        kwargs={"_buf": (shard.offset, full.offset)})
+            g.meta = dict(ag_e.meta)
+            ag_e.replace_all_uses_with(g)
+            graph.erase_node(ag_e)
+            graph.erase_node(ag_s)
+            gathered_nodes.setdefault(ph, []).append(g)
+    # ---- schedule ----------------------------------------------------------------------------
+    order = {nd: i for i, nd in enumerate(graph.nodes)}
+    first_use = {ph: min(order[g] for g in gathered_nodes[ph]) for ph in uses}
+    carriers = []
+    for nd in graph.nodes:
+        if nd.op != "call_function" or nd.target not in (aten.mm.default, aten.addmm.default):
+            continue
+        v = nd.meta.get("val")
+        a = nd.args[-2].meta.get("val") if isinstance(nd.args[-2], Node) else None
+        if isinstance(v, torch.Tensor) and v.dtype == torch.bfloat16 and v.dim() == 2 and \
+                isinstance(a, torch.Tensor) and a.dim() == 2:
+            carriers.append((nd, 2.0 * v.shape[0] * v.shape[1] * a.shape[1]))
+    gbps = float(os.environ.get("EDB_PF_GBPS", "300"))
+    BLK = 16384
+    need = sorted(uses, key=lambda ph: first_use[ph])
+    start_of_carriers = order[carriers[0][0]] if carriers else float("inf")
+    initial = [ph for ph in need if first_use[ph] < start_of_carriers]
+    queue = deque([ph, 0] for ph in need if ph not in initial)
+    late = {}  # ph -> items that found no carrier in time (stand-alone prefetch at the use)
+    deps = {ph: [] for ph in uses}
+
+    def item(ph, done, take):
+        shard, full, nbytes = bufs[ph]
+        return (shard.offset + done, full.offset + done, take, nbytes)
+
+    for nd, flops in carriers:
+        budget = flops / 9e14 * gbps * 1e9 / max(1, n - 1) * 1.0  # bytes per member range
+        items = []
+        while queue and len(items) < 4:
+            ph, done = queue[0]
+            if order[nd] >= first_use[ph]:
+                # too late for this carrier: the rest is gathered right in front of the use
+                late.setdefault(ph, []).append(item(ph, done, bufs[ph][2] - done))
+                queue.popleft()
+                continue
+            left = bufs[ph][2] - done
+            take = left if left <= budget else max(BLK, int(budget) // BLK * BLK)
+            take = min(take, left)
+            items.append(item(ph, done, take))
+            deps[ph].append(nd)
+            budget -= take
+            if take == left:
+                queue.popleft()
+            else:
+                queue[0][1] = done + take
+            if budget < BLK:
+                break
+        if items:
+            nd.meta["edb_pf"] = {"group": list(ranks), "items": items}
+    for ph, done in queue:
+        late.setdefault(ph, []).append(item(ph, done, bufs[ph][2] - done))
+    if initial:
+        first_node = next(nd for nd in graph.nodes if nd.op != "placeholder")
+        with graph.inserting_before(first_node):
+            graph.call_function(ops.ag_prefetch, args=(initial[0], list(ranks)),
+                                kwargs={"_items": [item(ph, 0, bufs[ph][2]) for ph in initial]})
+    for ph, items in late.items():
+        g0 = min(gathered_nodes[ph], key=lambda g: order[g])
+        with graph.inserting_before(g0):
+            graph.call_function(ops.ag_prefetch, args=(ph, list(ranks)), kwargs={"_items": items})
+    for ph, lst in gathered_nodes.items():
+        for g in lst:
+            g.args = (ph, list(ranks)) + tuple(dict.fromkeys(d for d in deps[ph] if order[d] < order[g]))
+    graph.lint()
+    gm.recompile()
+    return rehomed, len(uses)
 
 
 def fuse_collective_gemms(gm, io, rt, ranks, ops=_default_ops):
@@ -932,7 +1061,7 @@ def fuse_collective_gemms(gm, io, rt, ranks, ops=_default_ops):
     graph = gm.graph
     n = len(ranks)
     if n <= 1:
-        return {}, {"ag_mm": 0, "mm_rs": 0}
+        return {}, {"ag_mm": 0, "ag_pf": 0, "mm_rs": 0}
     order = {nd: i for i, nd in enumerate(graph.nodes)}
     rehomed = {}
     n_ag = n_rs = 0
@@ -942,6 +1071,11 @@ def fuse_collective_gemms(gm, io, rt, ranks, ops=_default_ops):
     # old parameter shards) and ONE behind it (the new shards are final, the slots are free again).
     # EDB_EPOCH=0 keeps the per-op flag protocol of the fused kernels.
     epoch = os.environ.get("EDB_EPOCH", "1") == "1" and hasattr(ops, "epoch_barrier")
+    n_pf = 0
+    if epoch and os.environ.get("EDB_AG_PREFETCH", "1") == "1" and hasattr(ops, "gathered"):
+        # all parameter gathers as prefetches riding on earlier GEMMs (no AG left to fuse below)
+        rehomed, n_pf = prefetch_param_gathers(gm, io, rt, ranks, ops)
+        order = {nd: i for i, nd in enumerate(graph.nodes)}
 
     def val(nd):
         return nd.meta.get("val") if isinstance(nd, Node) else None
@@ -1102,8 +1236,9 @@ def fuse_collective_gemms(gm, io, rt, ranks, ops=_default_ops):
     # peers read parameter shards in place: keep the optimizer from overwriting them too early
     if epoch and (rehomed or pushed):
         order = {nd: i for i, nd in enumerate(graph.nodes)}
+        peer_touch = (ops.ag_mm, ops.mm_push) + ((ops.ag_prefetch,) if hasattr(ops, "ag_prefetch") else ())
         fused_nodes = [nd for nd in graph.nodes if nd.op == "call_function"
-                       and nd.target in (ops.ag_mm, ops.mm_push)]
+                       and (nd.target in peer_touch or "edb_pf" in nd.meta)]
         last_fused = max(fused_nodes, key=lambda nd: order[nd])
         barriers = [nd for nd in graph.nodes if nd.op == "call_function"
                     and nd.target is ops.epoch_barrier]
@@ -1135,7 +1270,7 @@ def fuse_collective_gemms(gm, io, rt, ranks, ops=_default_ops):
                 graph.call_function(ops.symm_guard, args=(some_input, list(ranks)))
     graph.lint()
     gm.recompile()
-    return rehomed, {"ag_mm": n_ag, "mm_rs": n_rs}
+    return rehomed, {"ag_mm": n_ag, "ag_pf": n_pf, "mm_rs": n_rs}
 
 
 def reinplace_optimizer_updates(gm):

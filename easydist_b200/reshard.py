@@ -426,6 +426,34 @@ def epoch_barrier(x, group):
     return x
 
 
+@has_side_effect
+def ag_prefetch(x, group, *, _items):
+    """Stand-alone all-gather prefetch (edb_ag_prefetch): for every item (src_off, dst_off, bytes,
+    dst_stride) and every member p, copy p's symmetric range into local dst_off + p*dst_stride.
+    Epoch mode: the start-of-step gathers (embeddings, first layer) that have no earlier GEMM to
+    ride on.  Pass-through of `x`."""
+    if _is_fake(x) or len(group) <= 1 or not _items:
+        return x
+    from . import gemm as _gemm
+    _gemm.prefetch_standalone({"group": list(group), "items": list(_items)}, x.device)
+    return x
+
+
+def gathered(w_shard, group, *deps, _buf):
+    """The dim-0 all-gather of parameter shard `w_shard` (all_gather_start/_end of the zero3 /
+    auto-SPMD graphs, sharding.py:105-119) in epoch mode: the data was already put into the
+    symmetric buffer at _buf[1] by prefetches earlier on the stream (`deps`: the nodes that
+    carried them), so this is a zero-copy view — n * numel(w_shard) elements, flat."""
+    n = len(group)
+    if _is_fake(w_shard):
+        return w_shard.new_empty((n * w_shard.numel(),))
+    _require_cuda(w_shard, "gathered")
+    rt = get_runtime()
+    assert w_shard.data_ptr() == rt.heap_base + int(_buf[0]), "shard is not at its symmetric offset"
+    nbytes = w_shard.numel() * w_shard.element_size()
+    return SymmBuffer(rt, int(_buf[1]), n * nbytes).tensor(w_shard.dtype, (n * w_shard.numel(),))
+
+
 def ag_mm(x, w_shard, group, n_out, k_in, bias=None, *, _buf, _epoch=0):
     """all_gather(weight shard, dim 0) fused into the consuming GEMM (all_gather_end -> aten.mm /
     addmm of the sharded graph).  `w_shard`: this rank's rows [n_out/n, k_in] (flat or 2-D) living
@@ -557,4 +585,5 @@ def rs_finish(tokens, group, *, _bufs, _numels, _scale=1.0, _out_dtype=None, _ep
 COMM_FUNCS = [all_reduce_start, all_gather_start, reduce_scatter_start, all_to_all_start]
 COMM_SYNC_FUNCS = [all_reduce_end, all_gather_end, reduce_scatter_end, all_to_all_end]
 CUSTOM_FUNCS = COMM_FUNCS + COMM_SYNC_FUNCS + [scatter_wrapper, copy_wrapper]
-FUSED_FUNCS = [ag_mm, mm_rs, mm_rs_push, mm_push, rs_finish, symm_guard, epoch_barrier]
+FUSED_FUNCS = [ag_mm, mm_rs, mm_rs_push, mm_push, rs_finish, symm_guard, epoch_barrier, ag_prefetch,
+               gathered]

@@ -80,6 +80,9 @@ class Runtime:
         # a peer that stays away longer than this is fatal (the waiting kernel traps): same role as
         # the NCCL watchdog timeout of the reference's process groups
         self.set_option("spin_timeout_ms", int(os.environ.get("EDB_SPIN_TIMEOUT_MS", "120000")))
+        for opt in ("push_sync", "comm_ctas"):
+            if os.environ.get("EDB_" + opt.upper()) is not None:
+                self.set_option(opt, int(os.environ["EDB_" + opt.upper()]))
 
     # ---- bootstrap -------------------------------------------------------------------------
     def attach_peers(self, process_group=None):

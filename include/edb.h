@@ -231,6 +231,24 @@ int edb_ag_gemm_epoch_bf16(int gid, void* C, const void* A, const void* bias, ui
                            uint64_t b_full_off, int64_t M, int64_t N, int64_t K, int64_t lda,
                            int64_t ldc, void* stream);
 
+/* All-gather as a PREFETCH (the way the zero3 / auto-SPMD parameter gathers run in epoch mode).
+ * An item names a byte range that exists at the same symmetric offset on every member (a
+ * parameter shard, or part of one): for every member p the range [src_off, src_off + bytes) of
+ * p's heap is copied to the local heap at dst_off + p * dst_stride (dst_stride = bytes gives the
+ * dim-0 all-gather of all_gather_start, sharding.py:105-119).  Sources must be final since the
+ * last edb_epoch_barrier and stay untouched until the next one.
+ *   edb_ag_prefetch   : stand-alone launch (whole GPU; start of the step, before the first GEMM)
+ *   edb_gemm_pf_bf16  : edb_gemm_bf16 whose grid carries "comm_ctas" extra CTAs doing the copy
+ *                       while the others run the GEMM — the gathered operand belongs to a LATER
+ *                       kernel, so neither side waits for the other: the all-gather of layer i+1
+ *                       costs layer i a few SMs and no time (<= 4 items per launch). */
+int edb_ag_prefetch(int gid, int n_items, const uint64_t* src_offs, const uint64_t* dst_offs,
+                    const int64_t* bytes, const int64_t* dst_strides, void* stream);
+int edb_gemm_pf_bf16(void* C, const void* A, const void* B, const void* bias, int64_t M, int64_t N,
+                     int64_t K, int64_t lda, int64_t ldb, int64_t ldc, int a_kmajor, int b_kmajor,
+                     int gid, int n_items, const uint64_t* src_offs, const uint64_t* dst_offs,
+                     const int64_t* bytes, const int64_t* dst_strides, void* stream);
+
 /* GEMM whose result is reduce-scattered over its rows, push half: C = A.B (operand layouts as
  * edb_gemm_bf16, incl. cta_group::2 pairs and split-K); row block [p*M/n, (p+1)*M/n) is stored
  * straight into member p's receive slot [me] at symmetric `recv_off` (n slots of (M/n)*N*2 bytes

@@ -135,6 +135,17 @@ def epoch_barrier(x, group):
     return x
 
 
+def ag_prefetch(x, group, *, _items=None):
+    return x
+
+
+def gathered(w_shard, group, *deps, _buf=None):
+    """CPU stand-in of reshard.gathered: a real all-gather at every use."""
+    if _fake(w_shard):
+        return w_shard.new_empty((len(group) * w_shard.numel(),))
+    return all_gather_start(w_shard.reshape(-1), 0, group)
+
+
 def mm_push(a, b, group, *, _buf=None):
     """CPU stand-in of reshard.mm_push (epoch mode): the token carries the partial product."""
     if _fake(a):
@@ -227,7 +238,8 @@ class FakeSymmRuntime:
         return FakeSymmRuntime._Buf(off, nbytes)
 
 
-FUSED_FUNCS = [ag_mm, mm_rs, mm_rs_push, mm_push, rs_finish, symm_guard, epoch_barrier]
+FUSED_FUNCS = [ag_mm, mm_rs, mm_rs_push, mm_push, rs_finish, symm_guard, epoch_barrier, ag_prefetch,
+               gathered]
 COMM_FUNCS = [all_reduce_start, all_gather_start, reduce_scatter_start, all_to_all_start]
 COMM_SYNC_FUNCS = [all_reduce_end, all_gather_end, reduce_scatter_end, all_to_all_end]
 CUSTOM_FUNCS = COMM_FUNCS + COMM_SYNC_FUNCS + [scatter_wrapper, copy_wrapper]

@@ -416,6 +416,73 @@ def run_epoch(rank, world, group):
     return n_ok
 
 
+def run_prefetch(rank, world, group):
+    """All-gather as a prefetch: stand-alone (edb_ag_prefetch) and riding on a GEMM
+    (edb_gemm_pf_bf16) — gathered bytes bit-exact vs the oracle's all_gather of the same shards
+    (odd sizes, several items per launch, items that are sub-ranges of a shard), and the carrying
+    GEMM bit-identical to the same GEMM without passengers."""
+    from easydist_b200 import gemm
+    rt = runtime.get_runtime()
+    n_ok = 0
+    rng = np.random.RandomState(2024)
+    sizes = [16, 4096, 16384, 16400, 262144, 1048576 + 48, 6 * 1048576]
+    shards, fulls, data = [], [], []
+    for i, nbytes in enumerate(sizes):
+        sb = rt.alloc(nbytes, align=1024)
+        fb = rt.alloc(nbytes * world, align=1024)
+        allv = [np.random.RandomState(1000 * i + r).randint(0, 256, size=nbytes).astype(np.uint8)
+                for r in range(world)]
+        sb.tensor(torch.uint8, (nbytes,)).copy_(torch.from_numpy(allv[rank]))
+        shards.append(sb)
+        fulls.append(fb)
+        data.append(allv)
+    x = to_dev(np.zeros(1, dtype=np.float32), "float32")
+    reshard.epoch_barrier(x, group)  # every member's shards are in place
+
+    def wipe():
+        for fb, nbytes in zip(fulls, sizes):
+            fb.tensor(torch.uint8, (nbytes * world,)).fill_(0xEE)
+
+    def check_all(what):
+        k = 0
+        for fb, nbytes, allv in zip(fulls, sizes, data):
+            got = fb.tensor(torch.uint8, (nbytes * world,)).cpu().numpy()
+            want = O.all_gather([v for v in allv], 0)[rank]
+            assert np.array_equal(got, want), f"{what}: gathered bytes differ (shard {nbytes} B)"
+            k += 1
+        return k
+
+    # (1) stand-alone, all items in one call (the entry point chunks them by 4)
+    wipe()
+    items = [(sb.offset, fb.offset, nb, nb) for sb, fb, nb in zip(shards, fulls, sizes)]
+    reshard.ag_prefetch(x, group, _items=items)
+    torch.cuda.synchronize()
+    n_ok += check_all("ag_prefetch")
+    # (2) riding on GEMMs: items split into sub-ranges over several carriers
+    wipe()
+    split = []
+    for sb, fb, nb in zip(shards, fulls, sizes):
+        if nb >= 32768:
+            cut = (nb // 2) // 16384 * 16384
+            split += [(sb.offset, fb.offset, cut, nb), (sb.offset + cut, fb.offset + cut, nb - cut, nb)]
+        else:
+            split.append((sb.offset, fb.offset, nb, nb))
+    torch.manual_seed(7)
+    shapes = [(4096, 1024, 1024), (512, 256, 4096), (4096, 4096, 1024), (1024, 1024, 4096)]
+    for gi in range(0, len(split), 3):
+        M, N, K = shapes[(gi // 3) % len(shapes)]
+        a = torch.randn(M, K, device="cuda").bfloat16()
+        b = torch.randn(K, N, device="cuda").bfloat16()
+        ref = gemm.mm(a, b)
+        out = gemm.mm(a, b, _pf={"group": group, "items": split[gi:gi + 3]})
+        assert torch.equal(out, ref), f"carrying GEMM {(M, N, K)} differs from the plain one"
+        n_ok += 1
+    torch.cuda.synchronize()
+    n_ok += check_all("gemm_pf")
+    reshard.epoch_barrier(x, group)
+    return n_ok
+
+
 def run_train_parity(rank, world):
     """The benchmarked path end to end: zero3 + epoch-mode AG+GEMM / push GEMM + rs_finish +
     re-homed shards + bucketed small gradients + fused SGD, through easydist_compile (eager and
@@ -448,7 +515,8 @@ def run_train_parity(rank, world):
             losses.append(float(step(t.cuda(), y.cuda(), model, opt)))
         info = step.compiled_func.info
         if world > 1:
-            assert info["fused"]["ag_mm"] == 8 and info["fused"]["mm_rs"] == 8, info
+            # 8 Linear weights + token and position embeddings gathered by prefetch; 8 wgrad pushes
+            assert info["fused"]["ag_pf"] == 10 and info["fused"]["mm_rs"] == 8, info
             assert info["comm_nodes"].get("epoch_barrier") == 2, info
         sched = ([0, 0] if cuda_graph else [0]) + list(range(1, n_calls))
         steps = [batches[b] for b in sched]
@@ -698,6 +766,7 @@ def main():
     n += run_graph(rank, world, group, rows=4)
     n += run_fused(rank, world, group)
     n += run_epoch(rank, world, group)
+    n += run_prefetch(rank, world, group)
     n += run_auto_bundle(rank, world)
     n += run_train_parity(rank, world)
     if os.environ.get("EDB_TEST_EXPERIMENTAL") == "1":

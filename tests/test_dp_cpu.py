@@ -114,8 +114,7 @@ def _fusion_worker(rank, world, port, q, defer="0"):
     info["order"] = [n.target.__name__ for n in nodes if n.op == "call_function" and
                      n.target in (gloo_ops.epoch_barrier, gloo_ops.rs_finish, gloo_ops.mm_push,
                                   gloo_ops.ag_mm) or getattr(n.target, "__name__", "") == "sgd_momentum_"]
-    info["ag_epoch"] = [n.kwargs.get("_epoch", 0) for n in nodes
-                        if n.op == "call_function" and n.target is gloo_ops.ag_mm]
+    info["carried"] = sum(1 for n in nodes if "edb_pf" in n.meta)
     if rank == 0:
         q.put((ok, msg, info))
     dist.barrier()
@@ -140,7 +139,9 @@ def test_fusion_rewrite_on_cpu(defer):
     assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
     ok, msg, info = q.get(timeout=5)
     assert ok, msg
-    assert info["fused"] == {"ag_mm": 2, "mm_rs": 2}, info
+    want_fused = {"ag_mm": 0, "ag_pf": 2, "mm_rs": 2} if defer == "epoch" else \
+        {"ag_mm": 2, "ag_pf": 0, "mm_rs": 2}
+    assert info["fused"] == want_fused, info
     assert info["comm_nodes"].get("reduce_scatter_start", 0) == 0, info
     if defer == "epoch":
         # epoch protocol: flag-free fused kernels, exactly two barriers per step — one between the
@@ -148,7 +149,12 @@ def test_fusion_rewrite_on_cpu(defer):
         assert info["comm_nodes"].get("mm_push") == 2 and info["comm_nodes"].get("rs_finish") == 1, info
         assert info["comm_nodes"].get("epoch_barrier") == 2, info
         assert "symm_guard" not in info["comm_nodes"] and "mm_rs" not in info["comm_nodes"], info
-        assert info["ag_epoch"] == [1, 1], info
+        # parameter gathers are prefetches: fc1's (needed before the first GEMM) stand-alone at the
+        # top, fc2's riding on the fc1 GEMM up to that (tiny) GEMM's byte budget and the remainder
+        # stand-alone in front of the use; every use reads the gathered buffer
+        assert info["comm_nodes"].get("ag_prefetch") == 2 and "ag_mm" not in info["comm_nodes"], info
+        assert info["comm_nodes"].get("gathered", 0) >= 2, info
+        assert info["carried"] == 1, info
         order = info["order"]
         assert order.index("rs_finish") == order.index("epoch_barrier") + 1, order
         assert max(i for i, k in enumerate(order) if k == "mm_push") < order.index("epoch_barrier"), order
