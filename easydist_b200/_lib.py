@@ -79,10 +79,10 @@ SIGNATURES = {
     "edb_epoch_barrier": (c_int, [c_int, c_void_p]),
     "edb_ag_gemm_epoch_bf16": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_uint64, c_uint64,
                                        c_int64, c_int64, c_int64, c_int64, c_int64, c_void_p]),
-    "edb_ag_prefetch": (c_int, [c_int, c_int, c_void_p, c_void_p, _I64P, _I64P, c_void_p]),
+    "edb_ag_prefetch": (c_int, [c_int, c_int, c_void_p, c_void_p, _I64P, _I64P, _I64P, c_void_p]),
     "edb_gemm_pf_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64,
                                  c_int64, c_int64, c_int64, c_int, c_int, c_int, c_int, c_void_p,
-                                 c_void_p, _I64P, _I64P, c_void_p]),
+                                 c_void_p, _I64P, _I64P, _I64P, c_void_p]),
     "edb_gemm_push_bf16": (c_int, [c_int, c_uint64, c_void_p, c_void_p, c_int64, c_int64, c_int64,
                                    c_int64, c_int64, c_int, c_int, c_void_p]),
     "edb_rs_finish_local": (c_int, [c_int, c_int, c_void_p, c_void_p, _I64P, c_float, c_int,

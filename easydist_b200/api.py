@@ -62,7 +62,7 @@ def _flat_inputs(params, buffers, named_states, args, kwargs):
 
 
 def _finish(gm, params, buffers, named_states, args, kwargs, ops, native, io=None, ranks=None,
-            fuse=True, fuse_rt=None):
+            fuse=True, fuse_rt=None, my_index=None):
     """Local metas -> (fusions) -> static symmetric buffers -> GEMM dispatch."""
     flat = _flat_inputs(params, buffers, named_states, args, kwargs)
     lowering.propagate_local_meta(gm, flat)
@@ -83,7 +83,7 @@ def _finish(gm, params, buffers, named_states, args, kwargs, ops, native, io=Non
             from .runtime import get_runtime
             fuse_rt = get_runtime()
         rt = fuse_rt
-        rehomed, nf = lowering.fuse_collective_gemms(gm, io, rt, ranks, ops)
+        rehomed, nf = lowering.fuse_collective_gemms(gm, io, rt, ranks, ops, my_index=my_index)
         info["fused"] = nf
         # parameter shards read by peers must live at their symmetric offsets
         name_of = {ph.name: io.param_names[i] for i, ph in enumerate(io.param_ph)}
@@ -148,7 +148,7 @@ def _compile_dp(func, parallel_mode, tracing_mode, args, kwargs, *, ops=_default
                                                          my_index)
             named_states = pytree.tree_unflatten(flat_states, spec)
     info = _finish(gm, params, buffers, named_states, args, kwargs, ops, native, io=io,
-                   ranks=ranks, fuse=fuse, fuse_rt=fuse_rt)
+                   ranks=ranks, fuse=fuse, fuse_rt=fuse_rt, my_index=my_index)
     info.update(mode=mode, dp_size=n)
     if native and n > 1:
         # nobody enters the first step (peer waits have a fatal timeout) before everybody has

@@ -306,6 +306,7 @@ struct GemmParams {
 //                (aten.mm -> reduce_scatter_start in one kernel)
 enum { MODE_PLAIN = 0, MODE_AG = 1, MODE_RS = 2 };
 constexpr int kMaxPfItems = 4;
+constexpr int kPfSlots = 12, kPfDepth = 8;  // 16 KiB slots of the prefetch ring / loads in flight
 constexpr int F_TILECNT = 96;  // flag-block words [96,104): per-chunk completion counters
 
 struct FusedArgs {
@@ -344,6 +345,11 @@ struct FusedArgs {
   char* pf_local;
   uint64_t pf_src[kMaxPfItems], pf_dst[kMaxPfItems];
   int64_t pf_bytes[kMaxPfItems], pf_stride[kMaxPfItems];
+  // pf_sstride: member p's source is at pf_src + p * pf_sstride (0: the same offset everywhere).
+  // With pf_sstride == pf_stride and pf_src == pf_dst every member's shard LIVES in its slot of
+  // the gathered buffer: nothing to copy for the own range (pf_inplace), n-1 remote ranges only.
+  int64_t pf_sstride[kMaxPfItems];
+  int pf_inplace[kMaxPfItems];
 };
 constexpr int F_PUSHED = F_CHUNK + 8;  // [40..47] PUSHED[p]: peer p's deferred-RS tiles of op q landed
 
@@ -409,7 +415,7 @@ __device__ __forceinline__ void spin_wait_gpu(const uint64_t* flag, uint64_t tar
 // b % pf_ctas, so the CTAs stream neighbouring blocks and every range finishes at about the same
 // time.  No flags: the consumer is a later kernel on the stream.
 __device__ __forceinline__ void pf_role(const FusedArgs& fa, uint8_t* smem, int idx, int nctas) {
-  constexpr int S = 8, D = 5, SLOT = 16384;
+  constexpr int S = kPfSlots, D = kPfDepth, SLOT = 16384;
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + S * SLOT);
   if (threadIdx.x == 0) {
     for (int s = 0; s < S; ++s) mbar_init(&full[s], 1);
@@ -424,9 +430,10 @@ __device__ __forceinline__ void pf_role(const FusedArgs& fa, uint8_t* smem, int 
     // move to the next block owned by this CTA; returns false at the end
     while (c.it < fa.pf_items) {
       const int64_t nblk = (fa.pf_bytes[c.it] + SLOT - 1) / SLOT;
-      if (c.blk < nblk) return true;
-      c.blk -= nblk;  // keep the round-robin phase across ranges
-      if (++c.k == fa.pf_n) {
+      const int members = fa.pf_inplace[c.it] ? fa.pf_n - 1 : fa.pf_n;  // own range last / skipped
+      if (c.k < members && c.blk < nblk) return true;
+      if (c.k < members) c.blk -= nblk;  // keep the round-robin phase across ranges
+      if (++c.k >= members) {
         c.k = 0;
         ++c.it;
       }
@@ -445,7 +452,9 @@ __device__ __forceinline__ void pf_role(const FusedArgs& fa, uint8_t* smem, int 
       const int64_t left = fa.pf_bytes[ld.it] - off;
       const uint32_t bytes = (uint32_t)(left < SLOT ? left : SLOT);
       mbar_expect_tx(&full[slot], bytes);
-      bulk_load(smem + slot * SLOT, fa.pf_heap[p] + fa.pf_src[ld.it] + off, bytes, &full[slot]);
+      bulk_load(smem + slot * SLOT,
+                fa.pf_heap[p] + fa.pf_src[ld.it] + (int64_t)p * fa.pf_sstride[ld.it] + off, bytes,
+                &full[slot]);
       ++n_load;
       ++inflight;
       ld.blk += nctas;
@@ -1497,6 +1506,7 @@ struct PfSpec {
   const uint64_t* dst_offs;
   const int64_t* bytes;
   const int64_t* dst_strides;
+  const int64_t* src_strides;  // may be NULL (all 0)
 };
 
 static int fill_prefetch(FusedArgs* fa, const PfSpec* pf, int want_ctas) {
@@ -1521,11 +1531,17 @@ static int fill_prefetch(FusedArgs* fa, const PfSpec* pf, int want_ctas) {
         pf->dst_offs[i] < kUserOffset ||
         pf->dst_offs[i] + (uint64_t)st * (g.n - 1) + (uint64_t)b > r.heap_bytes)
       return set_error(EDB_E_INVALID, "prefetch item %d: symmetric range out of bounds", i);
+    const int64_t sst = pf->src_strides ? pf->src_strides[i] : 0;
+    if (sst < 0 || (sst & 15) ||
+        pf->src_offs[i] + (uint64_t)sst * (g.n - 1) + (uint64_t)b > r.heap_bytes)
+      return set_error(EDB_E_INVALID, "prefetch item %d: bad source stride", i);
     fa->pf_src[i] = pf->src_offs[i];
     fa->pf_dst[i] = pf->dst_offs[i];
     fa->pf_bytes[i] = b;
     fa->pf_stride[i] = st;
-    blocks += (b + 16383) / 16384 * g.n;
+    fa->pf_sstride[i] = sst;
+    fa->pf_inplace[i] = (sst == st && pf->src_offs[i] == pf->dst_offs[i]) ? 1 : 0;
+    blocks += (b + 16383) / 16384 * (fa->pf_inplace[i] ? g.n - 1 : g.n);
   }
   int ctas = want_ctas;
   if (blocks < ctas) ctas = (int)blocks;
@@ -1657,25 +1673,28 @@ int edb_gemm_bf16(void* C, const void* A, const void* B, const void* bias, int64
 int edb_gemm_pf_bf16(void* C, const void* A, const void* B, const void* bias, int64_t M, int64_t N,
                      int64_t K, int64_t lda, int64_t ldb, int64_t ldc, int a_kmajor, int b_kmajor,
                      int gid, int n_items, const uint64_t* src_offs, const uint64_t* dst_offs,
-                     const int64_t* bytes, const int64_t* dst_strides, void* stream) {
-  PfSpec pf = {gid, n_items, src_offs, dst_offs, bytes, dst_strides};
+                     const int64_t* bytes, const int64_t* dst_strides, const int64_t* src_strides,
+                     void* stream) {
+  PfSpec pf = {gid, n_items, src_offs, dst_offs, bytes, dst_strides, src_strides};
   return gemm_plain_impl(C, A, B, bias, M, N, K, lda, ldb, ldc, a_kmajor, b_kmajor, stream, nullptr,
                          n_items > 0 ? &pf : nullptr);
 }
 
 int edb_ag_prefetch(int gid, int n_items, const uint64_t* src_offs, const uint64_t* dst_offs,
-                    const int64_t* bytes, const int64_t* dst_strides, void* stream) {
+                    const int64_t* bytes, const int64_t* dst_strides, const int64_t* src_strides,
+                    void* stream) {
   if (n_items <= 0) return EDB_OK;
   Runtime& r = rt();
   static bool configured = false;
-  const int smem = 8 * 16384 + 1024 + 128;
+  const int smem = kPfSlots * 16384 + 1024 + 128;
   if (!configured) {
     EDB_CUDA(cudaFuncSetAttribute(k_ag_prefetch, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
   for (int done = 0; done < n_items; done += kMaxPfItems) {
     const int k = n_items - done < kMaxPfItems ? n_items - done : kMaxPfItems;
-    PfSpec pf = {gid, k, src_offs + done, dst_offs + done, bytes + done, dst_strides + done};
+    PfSpec pf = {gid, k, src_offs + done, dst_offs + done, bytes + done, dst_strides + done,
+                 src_strides ? src_strides + done : nullptr};
     FusedArgs fa;
     memset(&fa, 0, sizeof(fa));
     // nothing else needs the SMs: one CTA per SM (1 thread each drives a 5-deep 16 KiB ring)

@@ -151,10 +151,12 @@ def _pf_arrays(pf):
     import ctypes
     items = pf["items"]
     k = len(items)
+    # item = (src_off, dst_off, bytes, dst_stride[, src_stride])
     return (k, (ctypes.c_uint64 * k)(*[int(i[0]) for i in items]),
             (ctypes.c_uint64 * k)(*[int(i[1]) for i in items]),
             (ctypes.c_int64 * k)(*[int(i[2]) for i in items]),
-            (ctypes.c_int64 * k)(*[int(i[3]) for i in items]))
+            (ctypes.c_int64 * k)(*[int(i[3]) for i in items]),
+            (ctypes.c_int64 * k)(*[int(i[4]) if len(i) > 4 else 0 for i in items]))
 
 
 def prefetch_standalone(pf, device):
@@ -162,8 +164,8 @@ def prefetch_standalone(pf, device):
     from .runtime import get_runtime
     rt = get_runtime()
     gid = rt.group(pf["group"])
-    k, src, dst, nbytes, stride = _pf_arrays(pf)
-    check(rt.lib.edb_ag_prefetch(gid, k, src, dst, nbytes, stride, rt.stream()))
+    k, src, dst, nbytes, stride, sstride = _pf_arrays(pf)
+    check(rt.lib.edb_ag_prefetch(gid, k, src, dst, nbytes, stride, sstride, rt.stream()))
 
 
 def _launch(a, b, bias, side=0, pf=None):
@@ -185,11 +187,11 @@ def _launch(a, b, bias, side=0, pf=None):
             # the GEMM carries an all-gather prefetch for a later kernel (lowering.prefetch_param_gathers)
             from .runtime import get_runtime
             gid = get_runtime().group(pf["group"])
-            k, src, dst, nbytes, stride = _pf_arrays(pf)
+            k, src, dst, nbytes, stride, sstride = _pf_arrays(pf)
             check(lib.edb_gemm_pf_bf16(out.data_ptr(), ta.data_ptr(), tb.data_ptr(),
                                        bias.data_ptr() if bias is not None else None, M, N, K, lda,
                                        ldb, ldc, 1 if a_k else 0, 1 if b_k else 0, gid, k, src, dst,
-                                       nbytes, stride, _stream(a)))
+                                       nbytes, stride, sstride, _stream(a)))
         else:
             check(lib.edb_gemm_bf16(out.data_ptr(), ta.data_ptr(), tb.data_ptr(),
                                     bias.data_ptr() if bias is not None else None, M, N, K, lda, ldb,

@@ -924,7 +924,7 @@ def dispatch_compute(gm):
     return n
 
 
-def prefetch_param_gathers(gm, io, rt, ranks, ops=_default_ops):
+def prefetch_param_gathers(gm, io, rt, ranks, ops=_default_ops, my_index=None):
     """Epoch mode: every dim-0 all-gather of a parameter shard (zero3: compile_dp.py:136-150 puts
     one in front of each use) becomes a PREFETCH.
 
@@ -938,6 +938,10 @@ def prefetch_param_gathers(gm, io, rt, ranks, ops=_default_ops):
     Packing is earliest-first under a per-GEMM byte budget (its FLOPs at ~900 TFLOP/s times
     EDB_PF_GBPS, default 300 GB/s of NVLink pull); whatever is needed before the first GEMM
     (embeddings, first layer) goes into one stand-alone `ops.ag_prefetch` at the top of the graph.
+
+    Layout: with `my_index` given, a rank's shard LIVES in its own slot of the gathered buffer
+    (shard home = full + my_index * shard_bytes; the optimizer updates it there), so the own range
+    is never copied and only the n-1 remote ranges travel.
 
     Returns ({placeholder name: SymmBuffer home of the shard}, number of parameters handled)."""
     import os
@@ -964,8 +968,11 @@ def prefetch_param_gathers(gm, io, rt, ranks, ops=_default_ops):
     rehomed, bufs = {}, {}
     for ph in uses:
         nbytes = _nbytes(ph.meta["val"])
-        shard = rt.alloc(nbytes, align=1024)
         full = rt.alloc(nbytes * n, align=1024)
+        if my_index is None:
+            shard = rt.alloc(nbytes, align=1024)
+        else:
+            shard = full.sub(int(my_index) * nbytes, nbytes)
         rehomed[ph.name] = shard
         bufs[ph] = (shard, full, nbytes)
     first_use = {ph: min(order[a] for a, _ in lst) for ph, lst in uses.items()}
@@ -1004,7 +1011,9 @@ def prefetch_param_gathers(gm, io, rt, ranks, ops=_default_ops):
 
     def item(ph, done, take):
         shard, full, nbytes = bufs[ph]
-        return (shard.offset + done, full.offset + done, take, nbytes)
+        if my_index is None:
+            return (shard.offset + done, full.offset + done, take, nbytes, 0)
+        return (full.offset + done, full.offset + done, take, nbytes, nbytes)  # in place
 
     for nd, flops in carriers:
         budget = flops / 9e14 * gbps * 1e9 / max(1, n - 1) * 1.0  # bytes per member range
@@ -1049,7 +1058,7 @@ def prefetch_param_gathers(gm, io, rt, ranks, ops=_default_ops):
     return rehomed, len(uses)
 
 
-def fuse_collective_gemms(gm, io, rt, ranks, ops=_default_ops):
+def fuse_collective_gemms(gm, io, rt, ranks, ops=_default_ops, my_index=None):
     """Peephole fusion of reshard edges into the adjacent GEMM (B200 runtime only):
 
       all_gather(param shard) -> view -> t -> mm/addmm        ==>  ops.ag_mm   (AG + GEMM, one kernel)
@@ -1074,7 +1083,7 @@ def fuse_collective_gemms(gm, io, rt, ranks, ops=_default_ops):
     n_pf = 0
     if epoch and os.environ.get("EDB_AG_PREFETCH", "1") == "1" and hasattr(ops, "gathered"):
         # all parameter gathers as prefetches riding on earlier GEMMs (no AG left to fuse below)
-        rehomed, n_pf = prefetch_param_gathers(gm, io, rt, ranks, ops)
+        rehomed, n_pf = prefetch_param_gathers(gm, io, rt, ranks, ops, my_index=my_index)
         order = {nd: i for i, nd in enumerate(graph.nodes)}
 
     def val(nd):

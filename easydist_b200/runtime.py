@@ -49,6 +49,11 @@ class SymmBuffer:
         flat = self._rt.slab[self.offset:self.offset + nbytes]
         return flat.view(dtype).view(tuple(int(s) for s in shape))
 
+    def sub(self, delta, nbytes):
+        """The sub-range [delta, delta + nbytes) of this buffer as a buffer of its own."""
+        assert 0 <= delta and delta + nbytes <= self.nbytes
+        return SymmBuffer(self._rt, self.offset + int(delta), nbytes)
+
     @property
     def ptr(self):
         return self._rt.heap_base + self.offset

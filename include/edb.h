@@ -241,13 +241,20 @@ int edb_ag_gemm_epoch_bf16(int gid, void* C, const void* A, const void* bias, ui
  *   edb_gemm_pf_bf16  : edb_gemm_bf16 whose grid carries "comm_ctas" extra CTAs doing the copy
  *                       while the others run the GEMM — the gathered operand belongs to a LATER
  *                       kernel, so neither side waits for the other: the all-gather of layer i+1
- *                       costs layer i a few SMs and no time (<= 4 items per launch). */
+ *                       costs layer i a few SMs and no time (<= 4 items per launch).
+ *
+ * `src_strides` (may be NULL = all 0): member p's source range starts at src_off + p*src_stride.
+ * With src_stride == dst_stride and src_off == dst_off every member's shard lives IN PLACE in its
+ * own slot of the gathered buffer (the optimizer updates it there): the own range needs no copy
+ * and only the n-1 remote ranges move — the layout the zero3 lowering uses. */
 int edb_ag_prefetch(int gid, int n_items, const uint64_t* src_offs, const uint64_t* dst_offs,
-                    const int64_t* bytes, const int64_t* dst_strides, void* stream);
+                    const int64_t* bytes, const int64_t* dst_strides, const int64_t* src_strides,
+                    void* stream);
 int edb_gemm_pf_bf16(void* C, const void* A, const void* B, const void* bias, int64_t M, int64_t N,
                      int64_t K, int64_t lda, int64_t ldb, int64_t ldc, int a_kmajor, int b_kmajor,
                      int gid, int n_items, const uint64_t* src_offs, const uint64_t* dst_offs,
-                     const int64_t* bytes, const int64_t* dst_strides, void* stream);
+                     const int64_t* bytes, const int64_t* dst_strides, const int64_t* src_strides,
+                     void* stream);
 
 /* GEMM whose result is reduce-scattered over its rows, push half: C = A.B (operand layouts as
  * edb_gemm_bf16, incl. cta_group::2 pairs and split-K); row block [p*M/n, (p+1)*M/n) is stored

@@ -229,6 +229,9 @@ class FakeSymmRuntime:
         def tensor(self, dtype, shape):
             return torch.empty(shape, dtype=dtype)
 
+        def sub(self, delta, nbytes):
+            return FakeSymmRuntime._Buf(self.offset + delta, nbytes)
+
     def __init__(self):
         self._off = 1 << 20
 

@@ -480,6 +480,23 @@ def run_prefetch(rank, world, group):
     torch.cuda.synchronize()
     n_ok += check_all("gemm_pf")
     reshard.epoch_barrier(x, group)
+    # (3) in-place layout: every member's shard lives in its own slot of the gathered buffer
+    # (src_off == dst_off, src_stride == dst_stride): only the n-1 remote ranges are copied
+    for fb, nb, allv in zip(fulls, sizes, data):
+        t = fb.tensor(torch.uint8, (nb * world,))
+        t.fill_(0xEE)
+        t[rank * nb:(rank + 1) * nb].copy_(torch.from_numpy(allv[rank]))
+    reshard.epoch_barrier(x, group)
+    inpl = [(fb.offset, fb.offset, nb, nb, nb) for fb, nb in zip(fulls, sizes)]
+    reshard.ag_prefetch(x, group, _items=inpl[:3])
+    a = torch.randn(2048, 1024, device="cuda").bfloat16()
+    b = torch.randn(1024, 1024, device="cuda").bfloat16()
+    ref = gemm.mm(a, b)
+    out = gemm.mm(a, b, _pf={"group": group, "items": inpl[3:]})
+    assert torch.equal(out, ref), "carrying GEMM (in-place items) differs from the plain one"
+    torch.cuda.synchronize()
+    n_ok += check_all("in-place prefetch") + 1
+    reshard.epoch_barrier(x, group)
     return n_ok
 
 
