@@ -81,7 +81,7 @@ struct Runtime {
   int64_t ll_max_bytes = 128 * 1024;  // payload per rank up to which the LL protocol is used (0 = off)
   int64_t gemm_force_bn = 0;  // tuning aid: 128 / 256 overrides the tile-width heuristic
   int64_t gemm_splitk = 1;   // 1: split K over idle SMs when the tiles fill at most half of them
-  int64_t push_sync = 2;     // how push-GEMM CTAs retire (GemmParams::push_sync)
+  int64_t push_sync = 1;     // how push-GEMM CTAs retire (GemmParams::push_sync); 1 measured == 0
   int64_t gemm_cluster = 2;  // 2: pair CTAs in clusters and multicast the B tile; 1: off
 };
 
