@@ -325,6 +325,22 @@ def parity_leg(torch, dist, args, cfg, GPT2, step_fn, model, opt, state0, par_ho
                    f"{args.mode} step vs vanilla fp32 PyTorch on the same global batches: loss per "
                    "call, every parameter, every momentum buffer"}
     if world > 1:
+        # the reshard-kernel battery of tests/mgpu_worker.py (every collective / dtype / dim, P2P
+        # boxes, the epoch-protocol kernels and the all-gather prefetch) bit for bit against the
+        # oracle, so that multi-rank kernel parity is part of every N > 1 bench record
+        try:
+            from tests import mgpu_worker as W
+            group = list(range(world))
+            n_resh = W.run_cases(rank, world, group, tag="bench")
+            n_resh += W.run_p2p(rank, world, group)
+            n_resh += W.run_epoch(rank, world, group)
+            n_resh += W.run_prefetch(rank, world, group)
+            res["reshard_checks_bit_exact"] = n_resh
+            res["checks"] += n_resh
+        except AssertionError as e:
+            ok = False
+            res["ok"] = False
+            res["reshard_failure"] = str(e)[:300]
         flags = torch.tensor([0.0 if ok else 1.0, res["max_rel_err"], res["param_max_bf16_ulp"]],
                              device="cuda")
         dist.all_reduce(flags, op=dist.ReduceOp.MAX)

@@ -61,12 +61,25 @@ def _flat_inputs(params, buffers, named_states, args, kwargs):
     return pytree.tree_flatten((params, buffers, named_states, args, kwargs))[0]
 
 
+class _ParamIO:
+    """The slice of GraphIO the prefetch pass needs (auto path: placeholders by position)."""
+
+    def __init__(self, param_ph, param_names):
+        self.param_ph, self.param_names = list(param_ph), list(param_names)
+
+
 def _finish(gm, params, buffers, named_states, args, kwargs, ops, native, io=None, ranks=None,
-            fuse=True, fuse_rt=None, my_index=None):
+            fuse=True, fuse_rt=None, my_index=None, auto_io=None):
     """Local metas -> (fusions) -> static symmetric buffers -> GEMM dispatch."""
     flat = _flat_inputs(params, buffers, named_states, args, kwargs)
     lowering.propagate_local_meta(gm, flat)
     info = {}
+    if io is None and os.environ.get("EDB_LOCALIZE_OPT", "1" if native else "0") == "1":
+        # auto-SPMD plans: optimizer foreach ops on shards instead of on gathered tensors (changes
+        # the communication structure the reference's lowering produces, so the reference-structure
+        # tests run without it; the product path has it on)
+        info["localized_foreach"] = lowering.localize_foreach(gm, ops, my_rank=get_device_mesh().rank)
+        lowering.propagate_local_meta(gm, flat)
     if os.environ.get("EDB_BUCKET_COMM", "0") == "1":
         # opt-in: changes the communication structure the reference's lowering would produce
         info["bucketed"] = lowering.bucket_small_comm(gm, ops)
@@ -95,6 +108,23 @@ def _finish(gm, params, buffers, named_states, args, kwargs, ops, native, io=Non
             params[pname] = home
         lowering.propagate_local_meta(gm, _flat_inputs(params, buffers, named_states, args,
                                                        kwargs))
+    elif native and fuse and auto_io is not None and ranks is not None and len(ranks) > 1 and \
+            os.environ.get("EDB_EPOCH", "1") == "1" and os.environ.get("EDB_AG_PREFETCH", "1") == "1":
+        # auto-SPMD plan on a 1-D mesh: dim-0 gathers of parameter shards become prefetches that
+        # ride on the step's GEMMs, one gather per parameter per step (epoch protocol)
+        from .runtime import get_runtime
+        rt = get_runtime()
+        rehomed, n_pf = lowering.prefetch_param_gathers(gm, auto_io, rt, ranks, ops, my_index=my_index)
+        if rehomed:
+            lowering.insert_epoch_barriers(gm, ranks, ops)
+            name_of = dict(zip([ph.name for ph in auto_io.param_ph], auto_io.param_names))
+            for ph_name, buf in rehomed.items():
+                t = params[name_of[ph_name]]
+                home = buf.tensor(t.dtype, t.shape)
+                home.copy_(t)
+                params[name_of[ph_name]] = home
+            lowering.propagate_local_meta(gm, _flat_inputs(params, buffers, named_states, args, kwargs))
+        info["fused"] = {"ag_mm": 0, "ag_pf": n_pf, "mm_rs": 0}
     info["comm_nodes"] = lowering.count_nodes(gm, ops)
     info["reinplaced_updates"] = lowering.reinplace_optimizer_updates(gm)
     if native:
@@ -207,7 +237,12 @@ def _lower_auto(gm, plan, state_io_map, params, buffers, named_states, args, kwa
         return pytree.tree_unflatten(flat, spec_in)
 
     largs, lkwargs = input_transform(args, kwargs)
-    info = _finish(gm, params, buffers, named_states, largs, lkwargs, ops, native)
+    auto_io, ranks1d, my_index = None, None, None
+    if mesh.ndim == 1:
+        auto_io = _ParamIO(param_ph, list(params.keys()))
+        ranks1d, my_index = mesh.ranks_along(0), mesh.get_coordinate()[0]
+    info = _finish(gm, params, buffers, named_states, largs, lkwargs, ops, native, auto_io=auto_io,
+                   ranks=ranks1d, my_index=my_index)
     info.update(mode="auto", mesh=mesh.shape)
     if native:
         from .runtime import get_runtime, is_initialized

@@ -1176,7 +1176,11 @@ struct RsFinishDesc {
   RsFinishItem it[kRsMaxItems];
 };
 
-__global__ void __launch_bounds__(kRsFinishThreads)
+// NSRC > 0: group size known at compile time, so that exactly NSRC x U 16-byte loads are in flight
+// per thread (8 for every instantiation: the slots are read once, nothing is reused, the kernel
+// lives on memory-level parallelism); NSRC == 0: any group size, one vector at a time.
+template <int NSRC>
+__global__ void __launch_bounds__(kRsFinishThreads, 4)
     k_rs_finish(const __grid_constant__ RsFinishDesc d) {
   __shared__ uint64_t s_q;
   __shared__ unsigned long long s_need;
@@ -1187,22 +1191,24 @@ __global__ void __launch_bounds__(kRsFinishThreads)
   }
   __syncthreads();
   if (!d.local_only) {
-  // every source must have landed its tiles of the latest push among the items (flags are
-  // monotonic and a source's pushes complete in stream order, so the latest covers the earlier)
-  unsigned long long need = 0;
-  for (int i = threadIdx.x; i < d.n_items; i += blockDim.x) {
-    const unsigned long long e = ld_relaxed_gpu(d.it[i].state);
-    need = e > need ? e : need;
-  }
-  if (need) atomicMax(&s_need, need);
-  __syncthreads();
-  if ((int)threadIdx.x < d.f.n)
-    spin_wait_sys(d.f.local + F_PUSHED + threadIdx.x, s_need, d.f.timeout_ns, d.f.local + F_ERR);
-  __syncthreads();
+    // every source must have landed its tiles of the latest push among the items (flags are
+    // monotonic and a source's pushes complete in stream order, so the latest covers the earlier)
+    unsigned long long need = 0;
+    for (int i = threadIdx.x; i < d.n_items; i += blockDim.x) {
+      const unsigned long long e = ld_relaxed_gpu(d.it[i].state);
+      need = e > need ? e : need;
+    }
+    if (need) atomicMax(&s_need, need);
+    __syncthreads();
+    if ((int)threadIdx.x < d.f.n)
+      spin_wait_sys(d.f.local + F_PUSHED + threadIdx.x, s_need, d.f.timeout_ns, d.f.local + F_ERR);
+    __syncthreads();
   }
   const uint64_t q = s_q;
   const int total_units = d.first_unit[d.n_items];
-  const int n = d.f.n;
+  const int n = NSRC > 0 ? NSRC : d.f.n;
+  constexpr int MAXS = NSRC > 0 ? NSRC : kMaxGroup;
+  constexpr int U = NSRC > 0 ? (8 / NSRC > 0 ? 8 / NSRC : 1) : 1;
   for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
     int lo = 0, hi = d.n_items;
     while (hi - lo > 1) {
@@ -1210,21 +1216,22 @@ __global__ void __launch_bounds__(kRsFinishThreads)
       if (d.first_unit[mid] <= u) lo = mid;
       else hi = mid;
     }
-    const RsFinishItem& it = d.it[lo];
-    const int64_t nvec = it.chunk_bytes / 16;
+    const char* recv = d.it[lo].recv;
+    void* dst = d.it[lo].dst;
+    const int64_t chunk_bytes = d.it[lo].chunk_bytes;
+    const int64_t nvec = chunk_bytes / 16;
     const int64_t v0 = (int64_t)(u - d.first_unit[lo]) * kRsFinishChunkVecs;
     const int64_t v1 = v0 + kRsFinishChunkVecs < nvec ? v0 + kRsFinishChunkVecs : nvec;
-    constexpr int U = 2;
     for (int64_t i0 = v0 + threadIdx.x; i0 < v1; i0 += U * kRsFinishThreads) {
-      uint4 raw[U][kMaxGroup];
+      uint4 raw[U][MAXS];
 #pragma unroll
       for (int uu = 0; uu < U; ++uu) {
         const int64_t i = i0 + uu * kRsFinishThreads;
         if (i < v1) {
 #pragma unroll
-          for (int sidx = 0; sidx < kMaxGroup; ++sidx)
+          for (int sidx = 0; sidx < MAXS; ++sidx)
             if (sidx < n)
-              raw[uu][sidx] = *reinterpret_cast<const uint4*>(it.recv + (int64_t)sidx * it.chunk_bytes + i * 16);
+              raw[uu][sidx] = __ldcs(reinterpret_cast<const uint4*>(recv + (int64_t)sidx * chunk_bytes + i * 16));
         }
       }
 #pragma unroll
@@ -1233,7 +1240,7 @@ __global__ void __launch_bounds__(kRsFinishThreads)
         if (i >= v1) break;
         float acc[8];
 #pragma unroll
-        for (int sidx = 0; sidx < kMaxGroup; ++sidx) {
+        for (int sidx = 0; sidx < MAXS; ++sidx) {
           if (sidx < n) {
             const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw[uu][sidx]);
 #pragma unroll
@@ -1251,8 +1258,8 @@ __global__ void __launch_bounds__(kRsFinishThreads)
         }
 #pragma unroll
         for (int e = 0; e < 8; ++e) acc[e] *= d.scale;
-        if (d.out_dtype == EDB_F32) rs_store<float>(static_cast<float*>(it.dst), i, acc);
-        else rs_store<__nv_bfloat16>(static_cast<__nv_bfloat16*>(it.dst), i, acc);
+        if (d.out_dtype == EDB_F32) rs_store<float>(static_cast<float*>(dst), i, acc);
+        else rs_store<__nv_bfloat16>(static_cast<__nv_bfloat16*>(dst), i, acc);
       }
     }
   }
@@ -1263,7 +1270,6 @@ __global__ void __launch_bounds__(kRsFinishThreads)
   finish_op(d.f, q, &s_last, gridDim.x);
 }
 
-// out[r, c] = bf16( sum_s partial[s][r][c] (s ascending) + bias[c] ): the second half of a split-K GEMM
 // push mode: row r of C belongs to member r / rows_per and goes to base[owner] + (r % rows_per) * ldc
 struct PushDst {
   int n;
@@ -1904,7 +1910,12 @@ static int rs_finish_impl(int gid, int n_items, void* const* dsts, const uint64_
     }
     d.n_items = k;
     int grid = (int)(units < 4LL * r.sm_count ? units : 4LL * r.sm_count);
-    k_rs_finish<<<grid, kRsFinishThreads, 0, st>>>(d);
+    switch (n) {
+      case 2: k_rs_finish<2><<<grid, kRsFinishThreads, 0, st>>>(d); break;
+      case 4: k_rs_finish<4><<<grid, kRsFinishThreads, 0, st>>>(d); break;
+      case 8: k_rs_finish<8><<<grid, kRsFinishThreads, 0, st>>>(d); break;
+      default: k_rs_finish<0><<<grid, kRsFinishThreads, 0, st>>>(d); break;
+    }
     count_launch();
     rc = cuda_check(cudaGetLastError(), "k_rs_finish launch");
     if (rc) return rc;

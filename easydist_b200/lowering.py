@@ -646,6 +646,166 @@ def overlap_schedule(gm, io, ops=_default_ops, prefetch=2):
     return {"prefetched": len(gathers), "deferred": deferred}
 
 
+def _is_functional_foreach(target):
+    schema = getattr(target, "_schema", None)
+    return schema is not None and schema.name.startswith("aten::_foreach_") and \
+        not schema.name.endswith("_") and "norm" not in schema.name and \
+        schema.name not in ("aten::_foreach_max", "aten::_foreach_copy")
+
+
+def localize_foreach(gm, ops=_default_ops, my_rank=None):
+    """Elementwise foreach ops on SHARDS instead of on gathered tensors (auto-SPMD plans).
+
+    The reference only knows a *replicate* strategy for the optimizer's `_foreach_*` ops
+    (easydist/torch/preset_propagation.py:113-165) while parameters and optimizer states live
+    sharded, so its lowering all-gathers every parameter, gradient and state in front of each
+    foreach op and `scatter_wrapper`s + `copy_`s every result back (at mesh (8,)
+    the config-1 step carries ~300 all-gathers and 192 local scatters for nothing but this).  An
+    elementwise op commutes with sharding:
+
+        scatter(op(all_gather(a_i, d), all_gather(b_i, d), ...), n, d, idx)  ==  op(a_i, b_i, ...)
+
+    bit for bit.  For every list position whose result is only consumed by scatter_wrapper(n, d, idx)
+    the inputs are replaced by their shards along d: the source of an all-gather along d (nothing
+    moves), an all-to-all for an operand that is sharded along another dimension (1/n of the
+    all-gather's traffic), a local slice for a replicated operand.  Positions that do not fit stay
+    in a residual foreach node with the gathered inputs.  Returns the number of positions made
+    local."""
+    graph = gm.graph
+    n_local = 0
+    if my_rank is None:
+        import torch.distributed as dist
+        my_rank = dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
+
+    def ag_source(x):
+        """x == all_gather_end(all_gather_start(s, d, group)) -> (s, d, group) else None."""
+        if not (isinstance(x, Node) and x.op == "call_function" and x.target is ops.all_gather_end):
+            return None
+        st = x.args[0]
+        if not (isinstance(st, Node) and st.target is ops.all_gather_start):
+            return None
+        src, d, group = st.args[0], st.args[1], list(st.args[2])
+        if isinstance(src, Node) and src.op == "call_function" and src.target is ops.all_gather_end:
+            return None  # nested (N-D mesh) shardings are left alone
+        return src, d, group
+
+    for F in list(graph.nodes):
+        if F.op != "call_function" or not _is_functional_foreach(F.target):
+            continue
+        list_pos = [k for k, a in enumerate(F.args)
+                    if isinstance(a, (list, tuple)) and len(a) > 0 and all(isinstance(x, Node) for x in a)]
+        if not list_pos:
+            continue
+        L = len(F.args[list_pos[0]])
+        if any(len(F.args[k]) != L for k in list_pos):
+            continue
+        outs = {}
+        bad = False
+        for u in F.users:
+            if u.target is not operator.getitem or u.args[1] in outs:
+                bad = True
+                break
+            outs[u.args[1]] = u
+        if bad:
+            continue
+        local = {}  # position -> (n, d, idx, group or None)
+        for i in range(L):
+            gi = outs.get(i)
+            if gi is None or not gi.users:
+                continue
+            us = list(gi.users)
+            if not all(u.op == "call_function" and u.target is ops.scatter_wrapper and u.args[0] is gi
+                       and not any(w.op == "call_function" and w.target is ops.scatter_wrapper
+                                   for w in u.users) for u in us):
+                continue
+            sig = {(u.args[1], u.args[2], u.args[3]) for u in us}
+            if len(sig) != 1:
+                continue
+            n, d, idx = sig.pop()
+            group = None
+            ok = True
+            for k in list_pos:
+                src = ag_source(F.args[k][i])
+                if src is None:
+                    continue
+                _, _, g = src
+                if len(g) != n or my_rank not in g or g.index(my_rank) != idx or \
+                        (group is not None and g != group):
+                    ok = False
+                    break
+                group = g
+            if ok:
+                local[i] = (n, d, idx, group)
+        if not local:
+            continue
+        with graph.inserting_before(F):
+            new_lists = {k: [] for k in list_pos}
+            for i in sorted(local):
+                n, d, idx, group = local[i]
+                for k in list_pos:
+                    x = F.args[k][i]
+                    src = ag_source(x)
+                    xv = x.meta.get("val")
+                    dd = d + xv.dim() if (d < 0 and isinstance(xv, torch.Tensor)) else d
+                    if src is not None and (src[1] == d or src[1] == dd):
+                        new_lists[k].append(src[0])                       # already the shard
+                    elif src is not None:
+                        s_, sd, g = src                                   # sharded along another dim
+                        a2a = graph.call_function(ops.all_to_all_start, args=(s_, sd, d, n, idx, g))
+                        new_lists[k].append(graph.call_function(
+                            ops.all_to_all_end, args=(a2a, sd, d, n, idx, g)))
+                    else:                                                 # replicated: my slice
+                        new_lists[k].append(graph.call_function(ops.scatter_wrapper, args=(x, n, d, idx)))
+            idxs = sorted(local)
+
+            def sub_args(keep, lists):
+                out = []
+                for k, a in enumerate(F.args):
+                    if k in lists:
+                        out.append(lists[k])
+                    elif isinstance(a, (list, tuple)) and len(a) == L:
+                        out.append([a[i] for i in keep])                  # per-element scalars
+                    else:
+                        out.append(a)
+                return tuple(out)
+
+            F_loc = graph.call_function(F.target, args=sub_args(idxs, new_lists), kwargs=dict(F.kwargs))
+            rest = [i for i in range(L) if i not in local]
+            F_rest = None
+            if rest:
+                rest_lists = {k: [F.args[k][i] for i in rest] for k in list_pos}
+                F_rest = graph.call_function(F.target, args=sub_args(rest, rest_lists),
+                                             kwargs=dict(F.kwargs))
+        with graph.inserting_after(F_rest if F_rest is not None else F_loc):
+            for j, i in enumerate(idxs):
+                gi = outs[i]
+                new = graph.call_function(operator.getitem, args=(F_loc, j))
+                for u in list(gi.users):                                  # the scatter_wrappers
+                    new.meta = dict(u.meta)
+                    u.replace_all_uses_with(new)
+                    graph.erase_node(u)
+                graph.erase_node(gi)
+            for j, i in enumerate(rest):
+                gi = outs.get(i)
+                if gi is None:
+                    continue
+                new = graph.call_function(operator.getitem, args=(F_rest, j))
+                new.meta = dict(gi.meta)
+                gi.replace_all_uses_with(new)
+                graph.erase_node(gi)
+        graph.erase_node(F)
+        n_local += len(idxs)
+    if n_local:
+        # all-gathers that only fed the gathered form of those positions are dead now
+        for nd in reversed(list(graph.nodes)):
+            if nd.op == "call_function" and nd.target in (ops.all_gather_end, ops.all_gather_start) \
+                    and not nd.users:
+                graph.erase_node(nd)
+        graph.lint()
+        gm.recompile()
+    return n_local
+
+
 def propagate_local_meta(gm, flat_inputs):
     """Re-run shape propagation on the lowered graph with LOCAL placeholder values so that every
     node's meta['val'] is the per-rank tensor (the reference recomputes metas node by node with
@@ -951,18 +1111,27 @@ def prefetch_param_gathers(gm, io, rt, ranks, ops=_default_ops, my_index=None):
     order = {nd: i for i, nd in enumerate(graph.nodes)}
     uses = {}
     for ag_s in [x for x in graph.nodes if x.op == "call_function" and x.target is ops.all_gather_start]:
-        ph = ag_s.args[0]
+        ph, transposed = ag_s.args[0], False
+        if isinstance(ph, Node) and ph.op == "call_function" and ph.target == aten.t.default and \
+                isinstance(ph.args[0], Node) and ph.args[0].op == "placeholder":
+            # all_gather(t(W), 1) == t(all_gather(W, 0)): auto-SPMD plans gather the transposed
+            # weight of a Linear right in front of its GEMM
+            ph, transposed = ph.args[0], True
         if not (isinstance(ph, Node) and ph.op == "placeholder" and ph in io.param_ph):
-            continue
-        if ag_s.args[1] != 0 or list(ag_s.args[2]) != list(ranks) or ag_s.kwargs or len(ag_s.users) != 1:
-            continue
-        ag_e = next(iter(ag_s.users))
-        if ag_e.target is not ops.all_gather_end:
             continue
         val = ph.meta.get("val")
         if not isinstance(val, torch.Tensor) or (val.numel() * val.element_size()) % 16 or val.numel() == 0:
             continue
-        uses.setdefault(ph, []).append((ag_s, ag_e))
+        want_dim = 1 if transposed else 0
+        if transposed and val.dim() != 2:
+            continue
+        if ag_s.args[1] not in (want_dim, want_dim - val.dim()) or list(ag_s.args[2]) != list(ranks) \
+                or ag_s.kwargs or len(ag_s.users) != 1 or not val.is_contiguous():
+            continue
+        ag_e = next(iter(ag_s.users))
+        if ag_e.target is not ops.all_gather_end:
+            continue
+        uses.setdefault(ph, []).append((ag_s, ag_e, transposed))
     if not uses:
         return {}, 0
     rehomed, bufs = {}, {}
@@ -975,19 +1144,28 @@ def prefetch_param_gathers(gm, io, rt, ranks, ops=_default_ops, my_index=None):
             shard = full.sub(int(my_index) * nbytes, nbytes)
         rehomed[ph.name] = shard
         bufs[ph] = (shard, full, nbytes)
-    first_use = {ph: min(order[a] for a, _ in lst) for ph, lst in uses.items()}
     gathered_nodes = {}
     for ph, lst in uses.items():
         shard, full, nbytes = bufs[ph]
-        for ag_s, ag_e in lst:
+        pv = ph.meta["val"]
+        for ag_s, ag_e, transposed in lst:
             with graph.inserting_before(ag_s):
                 g = graph.call_function(ops.gathered, args=(ph, list(ranks)),
                                         kwargs={"_buf": (shard.offset, full.offset)})
-            g.meta = dict(ag_e.meta)
-            ag_e.replace_all_uses_with(g)
+                res = g
+                if pv.dim() > 1:  # flat concat of dim-0 shards == the dim-0 all-gather, reshaped
+                    res = graph.call_function(aten.view.default,
+                                              args=(g, [n * pv.shape[0]] + list(pv.shape[1:])))
+                if transposed:
+                    res = graph.call_function(aten.t.default, args=(res,))
+            res.meta = dict(ag_e.meta)
+            ag_e.replace_all_uses_with(res)
             graph.erase_node(ag_e)
             graph.erase_node(ag_s)
             gathered_nodes.setdefault(ph, []).append(g)
+    for nd in list(graph.nodes):  # t(W) nodes whose only reader was the all-gather
+        if nd.op == "call_function" and nd.target == aten.t.default and not nd.users:
+            graph.erase_node(nd)
     # ---- schedule ----------------------------------------------------------------------------
     order = {nd: i for i, nd in enumerate(graph.nodes)}
     first_use = {ph: min(order[g] for g in gathered_nodes[ph]) for ph in uses}
@@ -1056,6 +1234,44 @@ def prefetch_param_gathers(gm, io, rt, ranks, ops=_default_ops, my_index=None):
     graph.lint()
     gm.recompile()
     return rehomed, len(uses)
+
+
+def insert_epoch_barriers(gm, ranks, ops=_default_ops):
+    """The two rendezvous of an epoch-protocol step (see edb.h, edb_epoch_barrier):
+      * behind the LAST node that touches peer memory (all-gather prefetches read the peers'
+        parameter shards, push GEMMs write the peers' receive slots) unless a barrier already sits
+        behind it (the one in front of `rs_finish`): nobody may overwrite a shard that a slower
+        peer is still reading, and the optimizer — traced after the whole backward pass — is the
+        first to do so;
+      * at the very end: the updated shards are final and the receive slots free, the next step
+        may start."""
+    graph = gm.graph
+    order = {nd: i for i, nd in enumerate(graph.nodes)}
+    peer_touch = tuple(getattr(ops, k) for k in ("ag_mm", "mm_push", "ag_prefetch") if hasattr(ops, k))
+    fused_nodes = [nd for nd in graph.nodes if nd.op == "call_function"
+                   and (nd.target in peer_touch or "edb_pf" in nd.meta)]
+    if not fused_nodes:
+        return 0
+    n_new = 0
+    last_fused = max(fused_nodes, key=lambda nd: order[nd])
+    barriers = [nd for nd in graph.nodes if nd.op == "call_function"
+                and nd.target is ops.epoch_barrier]
+    if not any(order[b_] > order[last_fused] for b_ in barriers):
+        anchor = last_fused
+        while anchor.next.op == "call_function" and anchor.next.target is operator.getitem \
+                and anchor.next.args[0] is last_fused:
+            anchor = anchor.next
+        with graph.inserting_after(anchor):
+            graph.call_function(ops.epoch_barrier, args=(anchor, list(ranks)))
+        n_new += 1
+    out_node = next(nd for nd in graph.nodes if nd.op == "output")
+    some = next((nd for nd in reversed(list(graph.nodes)) if nd.op == "call_function"
+                 and isinstance(nd.meta.get("val"), torch.Tensor)), None)
+    if some is None:
+        some = next(nd for nd in graph.nodes if nd.op == "placeholder")
+    with graph.inserting_before(out_node):
+        graph.call_function(ops.epoch_barrier, args=(some, list(ranks)))
+    return n_new + 1
 
 
 def fuse_collective_gemms(gm, io, rt, ranks, ops=_default_ops, my_index=None):
@@ -1244,31 +1460,7 @@ def fuse_collective_gemms(gm, io, rt, ranks, ops=_default_ops, my_index=None):
 
     # peers read parameter shards in place: keep the optimizer from overwriting them too early
     if epoch and (rehomed or pushed):
-        order = {nd: i for i, nd in enumerate(graph.nodes)}
-        peer_touch = (ops.ag_mm, ops.mm_push) + ((ops.ag_prefetch,) if hasattr(ops, "ag_prefetch") else ())
-        fused_nodes = [nd for nd in graph.nodes if nd.op == "call_function"
-                       and (nd.target in peer_touch or "edb_pf" in nd.meta)]
-        last_fused = max(fused_nodes, key=lambda nd: order[nd])
-        barriers = [nd for nd in graph.nodes if nd.op == "call_function"
-                    and nd.target is ops.epoch_barrier]
-        if not any(order[b_] > order[last_fused] for b_ in barriers):
-            # no gradient push (hence no barrier in front of an rs_finish) behind the last peer read:
-            # the optimizer, which is traced after the whole backward pass, must still not touch
-            # shards that a slower peer is reading
-            anchor = last_fused
-            while anchor.next.op == "call_function" and anchor.next.target is operator.getitem \
-                    and anchor.next.args[0] is last_fused:
-                anchor = anchor.next
-            with graph.inserting_after(anchor):
-                graph.call_function(ops.epoch_barrier, args=(anchor, list(ranks)))
-        # behind the optimizer: new shards final, receive slots free => the next step may start
-        out_node = next(nd for nd in graph.nodes if nd.op == "output")
-        some = next((nd for nd in reversed(list(graph.nodes)) if nd.op == "call_function"
-                     and isinstance(nd.meta.get("val"), torch.Tensor)), None)
-        if some is None:
-            some = next(nd for nd in graph.nodes if nd.op == "placeholder")
-        with graph.inserting_before(out_node):
-            graph.call_function(ops.epoch_barrier, args=(some, list(ranks)))
+        insert_epoch_barriers(gm, ranks, ops)
     elif rehomed:
         region = optimizer_region(gm, io)
         if region:
