@@ -83,6 +83,9 @@ SIGNATURES = {
     "edb_gemm_pf_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64,
                                  c_int64, c_int64, c_int64, c_int, c_int, c_int, c_int, c_void_p,
                                  c_void_p, _I64P, _I64P, _I64P, c_void_p]),
+    "edb_gemm_epi_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int,
+                                  c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, c_int, c_int,
+                                  c_int, c_int, c_void_p, c_void_p, _I64P, _I64P, _I64P, c_void_p]),
     "edb_gemm_push_bf16": (c_int, [c_int, c_uint64, c_void_p, c_void_p, c_int64, c_int64, c_int64,
                                    c_int64, c_int64, c_int, c_int, c_void_p]),
     "edb_rs_finish_local": (c_int, [c_int, c_int, c_void_p, c_void_p, _I64P, c_float, c_int,
@@ -91,6 +94,9 @@ SIGNATURES = {
                                    c_int64, c_int64, c_float, c_int, c_void_p]),
     "edb_layer_norm_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                    c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_void_p]),
+    "edb_layer_norm_bwd_add": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                       c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64,
+                                       c_int, c_void_p]),
     "edb_layer_norm_bwd_workspace": (c_int, [c_int64, POINTER(c_size_t)]),
     "edb_colsum": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int, c_void_p]),
     "edb_colsum_workspace": (c_int, [c_int64, POINTER(c_size_t)]),

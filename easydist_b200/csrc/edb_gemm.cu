@@ -291,7 +291,30 @@ struct GemmParams {
   // 1 = completion only, 0 = only until the staging smem has been read (grid completion then
   // covers the stores, as it does for every ordinary TMA-store epilogue)
   int push_sync;
+  // fused elementwise epilogue with a second operand `aux` [M, N] bf16 (row stride ld_aux):
+  //   EPI_ADD      C = bf16(acc + bias + aux)                  (residual add behind a Linear)
+  //   EPI_GELU_BWD C = bf16(acc * gelu'(aux)), tanh approximation, ATen's formula in fp32
+  //                (aten.gelu_backward(grad = this GEMM, self = aux): the dgrad GEMM of the MLP's
+  //                second Linear produces d(pre-activation) directly)
+  const __nv_bfloat16* aux;
+  int64_t ld_aux;
+  int epi_op;
 };
+enum { EPI_NONE = 0, EPI_ADD = 1, EPI_GELU_BWD = 2 };
+
+__device__ __forceinline__ float gelu_tanh_grad(float x) {
+  // at::native GeluBackwardCUDAKernelImpl, approximate == 'tanh' (opmath = float)
+  const float kBeta = 0.7978845608028654f;  // sqrt(2) * (2/sqrt(pi)) * 0.5
+  const float kKappa = 0.044715f;
+  const float x_sq = x * x;
+  const float inner = kBeta * (x + kKappa * x_sq * x);
+  const float t = tanhf(inner);
+  const float left = 0.5f * x, right = 1.0f + t;
+  const float left_d = 0.5f * right;
+  const float tanh_d = 1.0f - t * t;
+  const float inner_d = kBeta * (1.0f + 3.0f * kKappa * x_sq);
+  return left_d + left * tanh_d * inner_d;
+}
 
 // Fusion modes of the GEMM kernel
 //   MODE_PLAIN : C = A.B
@@ -1073,6 +1096,35 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
             }
           }
         }
+        if (MODE == MODE_PLAIN && p.epi_op != EPI_NONE) {
+          const int64_t r = (int64_t)m_blk * BM + row_in_tile;
+          const int col0 = n_blk * BN + c0;
+          if (r < p.M) {
+            const __nv_bfloat16* arow = p.aux + r * p.ld_aux + col0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              if (col0 + 8 * j < p.N) {  // N % 8 == 0 whenever aux is passed
+                const uint4 araw = __ldg(reinterpret_cast<const uint4*>(arow + 8 * j));
+                const __nv_bfloat162* aa = reinterpret_cast<const __nv_bfloat162*>(&araw);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float2 f = __bfloat1622float2(aa[e]);
+                  float x0 = __uint_as_float(v[8 * j + 2 * e]), x1 = __uint_as_float(v[8 * j + 2 * e + 1]);
+                  if (p.epi_op == EPI_ADD) {
+                    x0 += f.x;
+                    x1 += f.y;
+                  } else {
+                    // ATen multiplies the bf16-rounded GEMM result: reproduce that rounding
+                    x0 = __bfloat162float(__float2bfloat16_rn(x0)) * gelu_tanh_grad(f.x);
+                    x1 = __bfloat162float(__float2bfloat16_rn(x1)) * gelu_tanh_grad(f.y);
+                  }
+                  v[8 * j + 2 * e] = __float_as_uint(x0);
+                  v[8 * j + 2 * e + 1] = __float_as_uint(x1);
+                }
+              }
+            }
+          }
+        }
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           uint4 o;
@@ -1506,6 +1558,13 @@ struct PushSpec {
 };
 
 // pf: NULL, or the all-gather prefetch that rides on this GEMM
+// epi: NULL, or the fused elementwise epilogue
+struct EpiSpec {
+  int op;
+  const void* aux;
+  int64_t ld_aux;
+};
+
 struct PfSpec {
   int gid, n_items;
   const uint64_t* src_offs;
@@ -1560,7 +1619,7 @@ static int fill_prefetch(FusedArgs* fa, const PfSpec* pf, int want_ctas) {
 static int gemm_plain_impl(void* C, const void* A, const void* B, const void* bias, int64_t M,
                            int64_t N, int64_t K, int64_t lda, int64_t ldb, int64_t ldc, int a_kmajor,
                            int b_kmajor, void* stream, const PushSpec* push,
-                           const PfSpec* pf = nullptr) {
+                           const PfSpec* pf = nullptr, const EpiSpec* epi = nullptr) {
   int rc = check_operands(A, B, C, bias, M, N, K, lda, ldb, ldc, "edb_gemm_bf16");
   if (rc) return rc;
   const int sms = sm_count_now();
@@ -1592,6 +1651,19 @@ static int gemm_plain_impl(void* C, const void* A, const void* B, const void* bi
   p.push_mtc = 1;
   p.m_rot = 0;
   p.push_sync = (int)rt().push_sync;
+  p.aux = nullptr;
+  p.ld_aux = 0;
+  p.epi_op = EPI_NONE;
+  if (epi && epi->op != EPI_NONE) {
+    if (epi->op != EPI_ADD && epi->op != EPI_GELU_BWD)
+      return set_error(EDB_E_INVALID, "edb_gemm_epi_bf16: unknown epilogue op %d", epi->op);
+    if ((N & 7) || ((uintptr_t)epi->aux & 15) || (epi->ld_aux & 7) || epi->ld_aux < N || !epi->aux)
+      return set_error(EDB_E_UNSUPPORTED,
+                       "edb_gemm_epi_bf16: aux needs N %% 8 == 0, 16-byte alignment, ld %% 8 == 0");
+    p.aux = static_cast<const __nv_bfloat16*>(epi->aux);
+    p.ld_aux = epi->ld_aux;
+    p.epi_op = epi->op;
+  }
   FusedArgs fa;
   memset(&fa, 0, sizeof(fa));
   CMaps cm;
@@ -1633,7 +1705,7 @@ static int gemm_plain_impl(void* C, const void* A, const void* B, const void* bi
   const int units = (cl == 2 ? ((p.m_tiles + 1) / 2) : p.m_tiles) * p.n_tiles;
   const int ctas = units * cl;
   const int k_blocks = (int)((K + BK - 1) / BK);
-  if (rt().gemm_splitk && 2 * ctas <= sms_gemm && k_blocks >= 16) {
+  if (rt().gemm_splitk && 2 * ctas <= sms_gemm && k_blocks >= 16 && p.epi_op == EPI_NONE) {
     int splits = sms_gemm / ctas;
     if (splits > k_blocks / 8) splits = k_blocks / 8;
     if (splits > 8) splits = 8;
@@ -1684,6 +1756,17 @@ int edb_gemm_pf_bf16(void* C, const void* A, const void* B, const void* bias, in
   PfSpec pf = {gid, n_items, src_offs, dst_offs, bytes, dst_strides, src_strides};
   return gemm_plain_impl(C, A, B, bias, M, N, K, lda, ldb, ldc, a_kmajor, b_kmajor, stream, nullptr,
                          n_items > 0 ? &pf : nullptr);
+}
+
+int edb_gemm_epi_bf16(void* C, const void* A, const void* B, const void* bias, const void* aux,
+                      int64_t ld_aux, int epi_op, int64_t M, int64_t N, int64_t K, int64_t lda,
+                      int64_t ldb, int64_t ldc, int a_kmajor, int b_kmajor, int gid, int n_items,
+                      const uint64_t* src_offs, const uint64_t* dst_offs, const int64_t* bytes,
+                      const int64_t* dst_strides, const int64_t* src_strides, void* stream) {
+  PfSpec pf = {gid, n_items, src_offs, dst_offs, bytes, dst_strides, src_strides};
+  EpiSpec epi = {epi_op, aux, ld_aux};
+  return gemm_plain_impl(C, A, B, bias, M, N, K, lda, ldb, ldc, a_kmajor, b_kmajor, stream, nullptr,
+                         n_items > 0 ? &pf : nullptr, &epi);
 }
 
 int edb_ag_prefetch(int gid, int n_items, const uint64_t* src_offs, const uint64_t* dst_offs,
@@ -1800,6 +1883,9 @@ static int ag_gemm_impl(int gid, void* C, const void* A, const void* bias, uint6
   p.push_mtc = 1;
   p.m_rot = 0;
   p.push_sync = 0;
+  p.aux = nullptr;
+  p.ld_aux = 0;
+  p.epi_op = EPI_NONE;
   const int sms = r.sm_count;
   int n_comm = (int)r.comm_ctas;
   if (n_comm < 1) n_comm = 1;
@@ -1981,6 +2067,9 @@ static int gemm_rs_impl(int gid, void* dst, uint64_t recv_off, uint64_t state_of
   p.push_mtc = 1;
   p.m_rot = 0;
   p.push_sync = 0;
+  p.aux = nullptr;
+  p.ld_aux = 0;
+  p.epi_op = EPI_NONE;
   fa.recv_base = recv;
   fa.chunk_bytes = (int64_t)chunk_bytes;
   fa.rs_dst = dst;

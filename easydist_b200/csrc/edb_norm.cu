@@ -86,7 +86,8 @@ template <typename T, int NV>
 __global__ void __launch_bounds__(kLnWarps * 32, (NV <= 4 ? 2 : 1))
     k_ln_bwd(T* __restrict__ dx, float* __restrict__ part, const T* __restrict__ dy,
              const T* __restrict__ x, const float* __restrict__ mean,
-             const float* __restrict__ rstd, const T* __restrict__ w, int64_t rows, int H) {
+             const float* __restrict__ rstd, const T* __restrict__ w, int64_t rows, int H,
+             const T* __restrict__ add_in) {
   constexpr int EPV = LnT<T>::EPV;
   extern __shared__ float ln_smem[];  // [kLnWarps][2][H]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -145,6 +146,14 @@ __global__ void __launch_bounds__(kLnWarps * 32, (NV <= 4 ? 2 : 1))
       mu = mean[row];
       rs = rstd[row];
     }
+    // fused gradient accumulation: dx = T(T(dx_ln) + add_in[row]) — the aten.add.Tensor that joins the
+    // LayerNorm branch with the residual branch in the backward pass (same two roundings as ATen)
+    uint4 ac[NV];
+    if (add_in != nullptr) {
+#pragma unroll
+      for (int i = 0; i < NV; ++i)
+        ac[i] = __ldg(reinterpret_cast<const uint4*>(add_in + row * H) + i * 32 + lane);
+    }
     float xh[NV][EPV], g[NV][EPV];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
@@ -170,6 +179,13 @@ __global__ void __launch_bounds__(kLnWarps * 32, (NV <= 4 ? 2 : 1))
       float o[EPV];
 #pragma unroll
       for (int e = 0; e < EPV; ++e) o[e] = rs * (g[i][e] - s1 - xh[i][e] * s2);
+      if (add_in != nullptr) {
+        float r1[EPV], av[EPV];
+        LnT<T>::unpack(LnT<T>::pack(o), r1);  // round to T first, like the separate kernels do
+        LnT<T>::unpack(ac[i], av);
+#pragma unroll
+        for (int e = 0; e < EPV; ++e) o[e] = r1[e] + av[e];
+      }
       dr[i * 32 + lane] = LnT<T>::pack(o);
     }
   }
@@ -321,7 +337,7 @@ static void ln_fwd_launch(void* y, void* mean, void* rstd, const void* x, const 
 template <typename T, int NV>
 static int ln_bwd_launch(void* dx, float* part, const void* dy, const void* x, const void* mean,
                          const void* rstd, const void* w, int64_t rows, int H, int grid,
-                         cudaStream_t st) {
+                         cudaStream_t st, const void* add_in) {
   auto kern = k_ln_bwd<T, NV>;
   const int smem = kLnWarps * 2 * H * (int)sizeof(float);
   static bool configured = false;
@@ -331,7 +347,7 @@ static int ln_bwd_launch(void* dx, float* part, const void* dy, const void* x, c
   }
   kern<<<grid, kLnWarps * 32, smem, st>>>((T*)dx, part, (const T*)dy, (const T*)x,
                                           (const float*)mean, (const float*)rstd, (const T*)w, rows,
-                                          H);
+                                          H, (const T*)add_in);
   return EDB_OK;
 }
 
@@ -424,7 +440,16 @@ int edb_layer_norm_fwd(void* y, void* mean, void* rstd, const void* x, const voi
 int edb_layer_norm_bwd(void* dx, void* dw, void* db, const void* dy, const void* x, const void* mean,
                        const void* rstd, const void* w, void* workspace, int64_t rows, int64_t H,
                        int dtype, void* stream) {
+  return edb_layer_norm_bwd_add(dx, dw, db, dy, x, mean, rstd, w, nullptr, workspace, rows, H, dtype,
+                                stream);
+}
+
+int edb_layer_norm_bwd_add(void* dx, void* dw, void* db, const void* dy, const void* x,
+                           const void* mean, const void* rstd, const void* w, const void* add_in,
+                           void* workspace, int64_t rows, int64_t H, int dtype, void* stream) {
   if (rows <= 0) return EDB_OK;
+  if ((uintptr_t)add_in & 15)
+    return set_error(EDB_E_UNSUPPORTED, "layer_norm_bwd: pointers must be 16-byte aligned");
   if (((uintptr_t)dx | (uintptr_t)dy | (uintptr_t)x | (uintptr_t)w | (uintptr_t)workspace) & 15)
     return set_error(EDB_E_UNSUPPORTED, "layer_norm_bwd: pointers must be 16-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
@@ -437,7 +462,7 @@ int edb_layer_norm_bwd(void* dx, void* dw, void* db, const void* dy, const void*
     if (!ln_shape_ok<__nv_bfloat16>(H))
       return set_error(EDB_E_UNSUPPORTED, "layer_norm_bwd: H=%lld not supported", (long long)H);
     const int nv = (int)(H / 256);
-    LN_DISPATCH_NV(nv, (rc = ln_bwd_launch<__nv_bfloat16, NV>(dx, part, dy, x, mean, rstd, w, rows, (int)H, grid, st)));
+    LN_DISPATCH_NV(nv, (rc = ln_bwd_launch<__nv_bfloat16, NV>(dx, part, dy, x, mean, rstd, w, rows, (int)H, grid, st, add_in)));
     if (rc) return rc;
     k_ln_bwd_finish<__nv_bfloat16><<<(int)((H + 31) / 32), 256, 0, st>>>(
         (__nv_bfloat16*)dw, (__nv_bfloat16*)db, part, grid, (int)H);
@@ -445,7 +470,7 @@ int edb_layer_norm_bwd(void* dx, void* dw, void* db, const void* dy, const void*
     if (!ln_shape_ok<float>(H))
       return set_error(EDB_E_UNSUPPORTED, "layer_norm_bwd: H=%lld not supported", (long long)H);
     const int nv = (int)(H / 128);
-    LN_DISPATCH_NV(nv, (rc = ln_bwd_launch<float, NV>(dx, part, dy, x, mean, rstd, w, rows, (int)H, grid, st)));
+    LN_DISPATCH_NV(nv, (rc = ln_bwd_launch<float, NV>(dx, part, dy, x, mean, rstd, w, rows, (int)H, grid, st, add_in)));
     if (rc) return rc;
     k_ln_bwd_finish<float><<<(int)((H + 31) / 32), 256, 0, st>>>((float*)dw, (float*)db, part, grid,
                                                                  (int)H);

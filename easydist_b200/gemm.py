@@ -29,11 +29,13 @@ _calls = []  # (M, N, K, a_kmajor, b_kmajor, a.stride(), b.stride()) of the nati
 
 def stats():
     return {"edb_gemm": _stats["edb_gemm"], "aten_mm": _stats["aten_mm"],
+            "edb_gemm_epi": _stats.get("edb_gemm_epi", 0),
             "padded_operands": _stats["padded_operands"], "unsupported": dict(_stats["unsupported"])}
 
 
 def reset_stats():
     _stats["edb_gemm"] = 0
+    _stats["edb_gemm_epi"] = 0
     _stats["aten_mm"] = 0
     _stats["padded_operands"] = 0
     _stats["unsupported"] = {}
@@ -168,7 +170,10 @@ def prefetch_standalone(pf, device):
     check(rt.lib.edb_ag_prefetch(gid, k, src, dst, nbytes, stride, sstride, rt.stream()))
 
 
-def _launch(a, b, bias, side=0, pf=None):
+EPI_ADD, EPI_GELU_BWD = 1, 2
+
+
+def _launch(a, b, bias, side=0, pf=None, epi=None):
     pa = _prepare(a, 1)
     pb = _prepare(b, 0)
     if pa is None or pb is None:
@@ -182,8 +187,27 @@ def _launch(a, b, bias, side=0, pf=None):
         return None
     lib = _lib.load()
     # operands were staged and the output allocated on the caller's stream; only the kernel forks
+    if epi is not None:
+        op, aux = epi
+        if N % 8 or aux.dtype != torch.bfloat16 or aux.shape != (M, N) or aux.stride(1) != 1 or \
+                aux.stride(0) % 8 or aux.data_ptr() % 16:
+            return None
     with _SideStream(side) as fork:
-        if pf:
+        if epi is not None:
+            import ctypes
+            if pf:
+                from .runtime import get_runtime
+                gid = get_runtime().group(pf["group"])
+                k, src, dst, nbytes, stride, sstride = _pf_arrays(pf)
+            else:
+                gid, k, src, dst, nbytes, stride, sstride = 0, 0, None, None, None, None, None
+            check(lib.edb_gemm_epi_bf16(out.data_ptr(), ta.data_ptr(), tb.data_ptr(),
+                                        bias.data_ptr() if bias is not None else None,
+                                        aux.data_ptr(), aux.stride(0), int(op), M, N, K, lda, ldb, ldc,
+                                        1 if a_k else 0, 1 if b_k else 0, gid, k, src, dst, nbytes,
+                                        stride, sstride, _stream(a)))
+            _stats["edb_gemm_epi"] = _stats.get("edb_gemm_epi", 0) + 1
+        elif pf:
             # the GEMM carries an all-gather prefetch for a later kernel (lowering.prefetch_param_gathers)
             from .runtime import get_runtime
             gid = get_runtime().group(pf["group"])
@@ -235,6 +259,34 @@ def mm(a, b, *, _side=0, _pf=None):
 
 def recorded_prefetches():
     return dict(_pf_calls)
+
+
+def mm_add(a, b, res, bias=None, *, _pf=None):
+    """res + (a @ b [+ bias]) in one kernel: the residual add behind a Linear fused into the GEMM
+    epilogue (aten.add.Tensor(res, aten.addmm(bias, a, b)) of the traced graph)."""
+    if isinstance(a, FakeTensor) or isinstance(b, FakeTensor) or a.is_meta:
+        y = torch.ops.aten.mm.default(a, b) if bias is None else torch.ops.aten.addmm.default(bias, a, b)
+        return torch.ops.aten.add.Tensor(res, y)
+    ok_bias = bias is None or (bias.dim() == 1 and bias.dtype == torch.bfloat16 and
+                               bias.shape[0] == b.shape[1])
+    if _eligible(a, b) and ok_bias and isinstance(res, torch.Tensor) and res.dim() == 2:
+        out = _launch(a, b, bias, 0, _pf, (EPI_ADD, res))
+        if out is not None:
+            return out
+    y = mm(a, b, _pf=_pf) if bias is None else addmm(bias, a, b, _pf=_pf)
+    return torch.ops.aten.add.Tensor(res, y)
+
+
+def mm_gelu_bwd(a, b, pre, *, _pf=None):
+    """aten.gelu_backward(a @ b, pre, approximate='tanh') in one kernel (GEMM epilogue)."""
+    if isinstance(a, FakeTensor) or isinstance(b, FakeTensor) or a.is_meta:
+        return torch.ops.aten.gelu_backward.default(torch.ops.aten.mm.default(a, b), pre,
+                                                    approximate="tanh")
+    if _eligible(a, b) and isinstance(pre, torch.Tensor) and pre.dim() == 2:
+        out = _launch(a, b, None, 0, _pf, (EPI_GELU_BWD, pre))
+        if out is not None:
+            return out
+    return torch.ops.aten.gelu_backward.default(mm(a, b, _pf=_pf), pre, approximate="tanh")
 
 
 def addmm(bias, a, b, *, _pf=None):

@@ -1038,6 +1038,134 @@ def parallel_wgrad_gemms(gm):
     return moved
 
 
+def fuse_gemm_epilogues(gm):
+    """Elementwise neighbours of the native GEMMs move into their epilogues (edb_gemm_epi_bf16):
+
+        add.Tensor(res, gemm.addmm(bias, a, b) | gemm.mm(a, b))   ==>  gemm.mm_add(a, b, res, bias)
+        gelu_backward(gemm.mm(a, b), pre, approximate='tanh')     ==>  gemm.mm_gelu_bwd(a, b, pre)
+
+    when the GEMM result has no other reader and the second operand is a bf16 matrix of the
+    result's shape (2-D, or a view of one: the traced Linear works on [tokens, features]).  The
+    reference runs these as separate ATen kernels (a14: op-by-op FX execution)."""
+    from . import gemm
+    graph = gm.graph
+    n = 0
+    bf16 = torch.bfloat16
+
+    def val(nd):
+        return nd.meta.get("val") if isinstance(nd, Node) else None
+
+    def gemm_behind(nd):
+        """nd == gemm.mm/addmm(...), or a shape-only view of it with a single reader chain."""
+        chain = []
+        while isinstance(nd, Node) and nd.op == "call_function" and \
+                nd.target in (aten.view.default, aten._unsafe_view.default) and len(nd.users) == 1:
+            chain.append(nd)
+            nd = nd.args[0]
+        if isinstance(nd, Node) and nd.op == "call_function" and nd.target in (gemm.mm, gemm.addmm) \
+                and len(nd.users) == 1 and not nd.kwargs.get("_side"):
+            return nd, chain
+        return None, chain
+
+    for node in list(graph.nodes):
+        if node.op != "call_function":
+            continue
+        if node.target == aten.add.Tensor and len(node.args) == 2 and not node.kwargs:
+            for gi, oi in ((1, 0), (0, 1)):
+                g, chain = gemm_behind(node.args[gi])
+                other = node.args[oi]
+                gv, ov, nv = val(g), val(other), val(node)
+                if g is None or not isinstance(other, Node) or gv is None or ov is None or nv is None:
+                    continue
+                if ov.dtype != bf16 or gv.dtype != bf16 or gv.shape[1] % 8 or \
+                        tuple(ov.shape) != tuple(nv.shape) or ov.numel() != gv.numel():
+                    continue
+                if not ov.is_contiguous():
+                    continue
+                order = {nd: i for i, nd in enumerate(graph.nodes)}
+                if order[other] > order[g]:
+                    continue  # the residual must exist when the GEMM runs
+                with graph.inserting_before(g):
+                    res2d = other if ov.dim() == 2 else graph.call_function(
+                        aten.view.default, args=(other, list(gv.shape)))
+                    if g.target is gemm.addmm:
+                        bias, a, b = g.args
+                    else:
+                        (a, b), bias = g.args, None
+                    fused = graph.call_function(gemm.mm_add, args=(a, b, res2d, bias),
+                                                kwargs={k: v for k, v in g.kwargs.items() if k == "_pf"})
+                    fused.meta = dict(g.meta)
+                    out = fused
+                    if nv.dim() != 2:
+                        out = graph.call_function(aten.view.default, args=(fused, list(nv.shape)))
+                        out.meta = dict(node.meta)
+                node.replace_all_uses_with(out)
+                graph.erase_node(node)
+                for c in chain:
+                    graph.erase_node(c)
+                graph.erase_node(g)
+                n += 1
+                break
+        elif node.target == aten.gelu_backward.default and node.kwargs.get("approximate") == "tanh":
+            g, chain = gemm_behind(node.args[0])
+            pre = node.args[1]
+            gv, pv, nv = val(g), val(pre), val(node)
+            if g is None or g.target is not gemm.mm or gv is None or pv is None or nv is None:
+                continue
+            if pv.dtype != bf16 or gv.dtype != bf16 or gv.shape[1] % 8 or pv.numel() != gv.numel() \
+                    or not pv.is_contiguous():
+                continue
+            order = {nd: i for i, nd in enumerate(graph.nodes)}
+            if order[pre] > order[g]:
+                continue
+            with graph.inserting_before(g):
+                pre2d = pre if pv.dim() == 2 else graph.call_function(
+                    aten.view.default, args=(pre, list(gv.shape)))
+                a, b = g.args
+                fused = graph.call_function(gemm.mm_gelu_bwd, args=(a, b, pre2d),
+                                            kwargs={k: v for k, v in g.kwargs.items() if k == "_pf"})
+                fused.meta = dict(g.meta)
+                out = fused
+                if nv.dim() != 2:
+                    out = graph.call_function(aten.view.default, args=(fused, list(nv.shape)))
+                    out.meta = dict(node.meta)
+            node.replace_all_uses_with(out)
+            graph.erase_node(node)
+            for c in chain:
+                graph.erase_node(c)
+            graph.erase_node(g)
+            n += 1
+    # gradient accumulation behind a LayerNorm backward: add(getitem(ln_bwd, 0), other) -> _add=other
+    from . import norm
+    order = {nd: i for i, nd in enumerate(graph.nodes)}
+    for node in list(graph.nodes):
+        if node.op != "call_function" or node.target != aten.add.Tensor or len(node.args) != 2 \
+                or node.kwargs:
+            continue
+        for gi, oi in ((0, 1), (1, 0)):
+            g, other = node.args[gi], node.args[oi]
+            if not (isinstance(g, Node) and g.op == "call_function" and g.target is operator.getitem
+                    and g.args[1] == 0 and len(g.users) == 1 and isinstance(other, Node)):
+                continue
+            ln = g.args[0]
+            if not (isinstance(ln, Node) and ln.target is norm.native_layer_norm_backward
+                    and "_add" not in ln.kwargs):
+                continue
+            lv, ov = val(g), val(other)
+            if lv is None or ov is None or tuple(lv.shape) != tuple(ov.shape) or lv.dtype != ov.dtype \
+                    or order[other] > order[ln]:
+                continue
+            ln.kwargs = dict(ln.kwargs, _add=other)
+            node.replace_all_uses_with(g)
+            graph.erase_node(node)
+            n += 1
+            break
+    if n:
+        graph.lint()
+        gm.recompile()
+    return n
+
+
 def dispatch_compute(gm):
     """Route bf16 `aten.mm` / `aten.addmm` nodes to the tcgen05 GEMM (sharded-op kernel dispatch)."""
     import os
@@ -1081,6 +1209,8 @@ def dispatch_compute(gm):
     gm.recompile()
     if os.environ.get("EDB_GEMM_SIDE", "0") == "1":
         n += parallel_wgrad_gemms(gm)
+    if os.environ.get("EDB_FUSE_EPILOGUE", "1") == "1":
+        n += fuse_gemm_epilogues(gm)
     return n
 
 

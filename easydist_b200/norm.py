@@ -70,14 +70,21 @@ def _workspace(H, device):
 
 
 def native_layer_norm_backward(grad_out, input, normalized_shape, mean, rstd, weight, bias,
-                               output_mask):
+                               output_mask, *, _add=None):
+    """`_add`: a tensor of input's shape added to dx inside the kernel (the gradient accumulation
+    `aten.add.Tensor(dx, residual_grad)` that follows in the traced backward pass)."""
     ok = (_supported(input, normalized_shape, weight) and grad_out.dtype == input.dtype
           and mean.dtype == torch.float32 and rstd.dtype == torch.float32 and output_mask[0])
+    if ok and _add is not None:
+        ok = _add.dtype == input.dtype and _add.shape == input.shape
     if not ok:
         if not isinstance(input, FakeTensor):
             _stats["aten_ln"] += 1
-        return aten.native_layer_norm_backward.default(grad_out, input, normalized_shape, mean, rstd,
-                                                       weight, bias, output_mask)
+        res = aten.native_layer_norm_backward.default(grad_out, input, normalized_shape, mean, rstd,
+                                                      weight, bias, output_mask)
+        if _add is not None:
+            res = (aten.add.Tensor(res[0], _add),) + tuple(res[1:])
+        return res
     x = input.contiguous()
     dy = grad_out.contiguous()
     H = int(normalized_shape[0])
@@ -87,11 +94,13 @@ def native_layer_norm_backward(grad_out, input, normalized_shape, mean, rstd, we
     db = torch.empty_like(weight) if output_mask[2] else None
     ws = _workspace(H, x.device)
     lib = _lib.load()
-    check(lib.edb_layer_norm_bwd(dx.data_ptr(), dw.data_ptr() if dw is not None else None,
-                                 db.data_ptr() if db is not None else None, dy.data_ptr(),
-                                 x.data_ptr(), mean.contiguous().data_ptr(),
-                                 rstd.contiguous().data_ptr(), weight.data_ptr(), ws.data_ptr(), rows,
-                                 H, _DT[x.dtype], _stream(x)))
+    add = _add.contiguous() if _add is not None else None
+    check(lib.edb_layer_norm_bwd_add(dx.data_ptr(), dw.data_ptr() if dw is not None else None,
+                                     db.data_ptr() if db is not None else None, dy.data_ptr(),
+                                     x.data_ptr(), mean.contiguous().data_ptr(),
+                                     rstd.contiguous().data_ptr(), weight.data_ptr(),
+                                     add.data_ptr() if add is not None else None, ws.data_ptr(), rows,
+                                     H, _DT[x.dtype], _stream(x)))
     _stats["edb_ln_bwd"] += 1
     return dx, dw, db
 

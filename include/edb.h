@@ -173,6 +173,19 @@ int edb_gemm_bf16(void* C, const void* A, const void* B, const void* bias, int64
                   int64_t K, int64_t lda, int64_t ldb, int64_t ldc, int a_kmajor, int b_kmajor,
                   int accumulate_into_c, void* stream);
 
+/* edb_gemm_bf16 with a fused elementwise epilogue over a second operand aux[M, N] (bf16, row
+ * stride ld_aux; N % 8 == 0) — "no separate elementwise kernel on the critical path":
+ *   epi_op 1 (add)      : C = bf16(A.B + bias + aux)        x + Linear(y): the residual adds of the
+ *                         transformer block (aten.add.Tensor behind aten.addmm in the traced graph)
+ *   epi_op 2 (gelu_bwd) : C = bf16(bf16(A.B) * gelu'(aux))  aten.gelu_backward(grad = A.B, self = aux,
+ *                         approximate = 'tanh') with ATen's fp32 formula
+ * Optionally carries an all-gather prefetch like edb_gemm_pf_bf16 (n_items may be 0). */
+int edb_gemm_epi_bf16(void* C, const void* A, const void* B, const void* bias, const void* aux,
+                      int64_t ld_aux, int epi_op, int64_t M, int64_t N, int64_t K, int64_t lda,
+                      int64_t ldb, int64_t ldc, int a_kmajor, int b_kmajor, int gid, int n_items,
+                      const uint64_t* src_offs, const uint64_t* dst_offs, const int64_t* bytes,
+                      const int64_t* dst_strides, const int64_t* src_strides, void* stream);
+
 /* all-gather fused into the consuming GEMM: B (weights [N,K], K-major) is sharded S(0) over the
  * group, shard (N/n rows) resident at symmetric offset `b_shard_off` on every rank.  The kernel's
  * copy CTAs pull the peer shards into the local gathered buffer `b_full_off` chunk by chunk while
@@ -286,6 +299,11 @@ int edb_layer_norm_fwd(void* y, void* mean, void* rstd, const void* x, const voi
 int edb_layer_norm_bwd(void* dx, void* dw, void* db, const void* dy, const void* x, const void* mean,
                        const void* rstd, const void* w, void* workspace, int64_t rows, int64_t H,
                        int dtype, void* stream);
+/* same with the gradient accumulation that follows in the graph fused in: dx = T(T(dx) + add_in)
+ * (aten.add.Tensor(native_layer_norm_backward(...)[0], residual_grad)); add_in: [rows, H] or NULL */
+int edb_layer_norm_bwd_add(void* dx, void* dw, void* db, const void* dy, const void* x,
+                           const void* mean, const void* rstd, const void* w, const void* add_in,
+                           void* workspace, int64_t rows, int64_t H, int dtype, void* stream);
 int edb_layer_norm_bwd_workspace(int64_t H, size_t* bytes_out);
 
 /* Column sums out[c] = sum_r x[r, c] of a [rows, cols] matrix with row stride `ld` (elements):

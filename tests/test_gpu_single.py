@@ -365,3 +365,66 @@ def test_gemm_split_k_agrees_with_unsplit(rt):
     assert torch.equal(ci, ci0)
     err = (cr.float() - cr0.float()).abs()
     assert bool((err <= cr0.float().abs() * 2 ** -7 + 1e-2).all())
+
+
+@pytest.mark.parametrize("with_bias", [False, True])
+def test_gemm_epilogue_residual_add(rt, with_bias):
+    """edb_gemm_epi_bf16 (add): res + (a @ b + bias) in one kernel vs a plain fp32 PyTorch
+    computation (one bf16 rounding of the exact sum: <= 1 bf16 ulp of the result's magnitude) and vs
+    the unfused GEMM-then-add (which rounds twice: <= 2 ulp apart)."""
+    from easydist_b200 import gemm
+    torch.manual_seed(3)
+    for (M, N, K) in [(4096, 1024, 1024), (512, 1024, 4096), (384, 264, 320)]:
+        a = torch.randn(M, K, device="cuda").bfloat16()
+        b = (torch.randn(K, N, device="cuda") * 0.05).bfloat16()
+        res = torch.randn(M, N, device="cuda").bfloat16()
+        bias = torch.randn(N, device="cuda").bfloat16() if with_bias else None
+        gemm.reset_stats()
+        out = gemm.mm_add(a, b, res, bias)
+        assert gemm.stats()["edb_gemm_epi"] == 1, gemm.stats()
+        ref = a.float() @ b.float() + res.float() + (bias.float() if with_bias else 0.0)
+        ulp = torch.exp2(torch.floor(torch.log2(ref.abs().clamp_min(1e-30))) - 7)
+        assert float(((out.float() - ref).abs() / ulp).max()) <= 1.0 + 2e-2, (M, N, K)
+        unfused = (gemm.addmm(bias, a, b) if with_bias else gemm.mm(a, b)) + res
+        assert float(((out.float() - unfused.float()).abs() / ulp).max()) <= 2.0
+
+
+def test_gemm_epilogue_gelu_backward(rt):
+    """edb_gemm_epi_bf16 (gelu_bwd): aten.gelu_backward(a @ b, pre, approximate='tanh') in the GEMM
+    epilogue vs the same formula in fp32 PyTorch on the fp32 product (tolerance: the bf16 rounding of
+    the GEMM result that ATen's operand order implies plus the final rounding = 2 bf16 ulp) and vs
+    ATen's kernel applied to this library's GEMM output (<= 1 ulp: same rounding points)."""
+    from easydist_b200 import gemm
+    torch.manual_seed(4)
+    for (M, N, K) in [(4096, 4096, 1024), (256, 512, 384)]:
+        a = torch.randn(M, K, device="cuda").bfloat16()
+        b = (torch.randn(K, N, device="cuda") * 0.05).bfloat16()
+        pre = (torch.randn(M, N, device="cuda") * 2).bfloat16()
+        gemm.reset_stats()
+        out = gemm.mm_gelu_bwd(a, b, pre)
+        assert gemm.stats()["edb_gemm_epi"] == 1, gemm.stats()
+        prod = a.float() @ b.float()
+        ref = torch.ops.aten.gelu_backward(prod, pre.float(), approximate="tanh")
+        scale = torch.exp2(torch.floor(torch.log2(ref.abs().clamp_min(1e-6))) - 7)
+        assert float(((out.float() - ref).abs() / scale).max()) <= 2.5, (M, N, K)
+        aten = torch.ops.aten.gelu_backward(gemm.mm(a, b), pre, approximate="tanh")
+        assert float(((out.float() - aten.float()).abs() / scale).max()) <= 1.0, (M, N, K)
+
+
+def test_layer_norm_backward_with_fused_accumulation(rt):
+    """edb_layer_norm_bwd_add: dx = bf16(bf16(dx_ln) + add) — bit-identical to the LayerNorm
+    backward kernel followed by aten.add (the same two roundings)."""
+    from easydist_b200 import norm
+    torch.manual_seed(5)
+    rows, H = 4096, 1024
+    x = torch.randn(rows, H, device="cuda").bfloat16()
+    dy = torch.randn(rows, H, device="cuda").bfloat16()
+    w = torch.randn(H, device="cuda").bfloat16()
+    b = torch.randn(H, device="cuda").bfloat16()
+    add = torch.randn(rows, H, device="cuda").bfloat16()
+    _, mean, rstd = norm.native_layer_norm(x, [H], w, b, 1e-5)
+    dx0, dw0, db0 = norm.native_layer_norm_backward(dy, x, [H], mean, rstd, w, b, [True, True, True])
+    dx1, dw1, db1 = norm.native_layer_norm_backward(dy, x, [H], mean, rstd, w, b, [True, True, True],
+                                                    _add=add)
+    assert torch.equal(dx1, dx0 + add)
+    assert torch.equal(dw1, dw0) and torch.equal(db1, db0)
