@@ -33,13 +33,23 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", rank))
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    runtime.init(rank, world, local, heap_bytes=8 << 30)
+    runtime.init(rank, world, local, heap_bytes=16 << 30)
     tag = args.mesh or str(world)
     mesh_shape = tuple(int(v) for v in tag.split("x"))
     set_device_mesh(np.arange(world).reshape(mesh_shape), [f"spmd{i}" for i in range(len(mesh_shape))],
                     rank=rank)
     golden = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
     bundle = gzip.open(os.path.join(golden, f"auto_gpt_c1_mesh{tag}.json.gz"), "rt").read()
+    # parity first (outside the timed region): outputs, every parameter and every momentum buffer
+    # vs vanilla PyTorch on the same batches (the reference's comparator, rtol 1e-4 / atol 1e-5)
+    from easydist_b200 import reshard
+    from tests.test_auto_bundle_cpu import run_c1_bundle
+    ok, msg, _ = run_c1_bundle(rank, world, reshard, True, "cuda", steps=3, tag=tag)
+    flag = torch.tensor([0.0 if ok else 1.0], device="cuda")
+    dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+    parity_ok = bool(flag.item() == 0.0)
+    if not ok:
+        print(f"[rank {rank}] parity failed: {msg}", flush=True)
     torch.manual_seed(42)
     model = EmbeddingGPT(4, 1024, 32).cuda()
     opt = torch.optim.SGD(model.parameters(), lr=1e-3, momentum=0.9, foreach=True)
@@ -75,6 +85,10 @@ def main():
                                                  f"{batch}x128, auto-SPMD plan of the reference solver",
                                      "mesh": list(mesh_shape), "cuda_graph": not args.no_cuda_graph,
                                      "bucket_comm": os.environ.get("EDB_BUCKET_COMM", "0")},
+                          "parity": {"ok": parity_ok, "what": "3 steps vs vanilla fp32 PyTorch: outputs, every "
+                                     "parameter, every momentum buffer (rtol 1e-4, atol 1e-5)"},
+                          "localized_foreach": compiled.info.get("localized_foreach"),
+                          "fused": compiled.info.get("fused"),
                           "comm_nodes": compiled.info["comm_nodes"]}), flush=True)
     dist.barrier()
     dist.destroy_process_group()
