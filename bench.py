@@ -400,6 +400,11 @@ def run_edb(args):
     launches_per_step = (rt.launch_count() - launches0) // passes
     gemm_calls_per_step = stats["edb_gemm"] // passes
     aten_mm_per_step = stats["aten_mm"] // passes
+    # the step's GEMM launch list, frozen now (the parity battery below issues GEMMs of its own)
+    step_calls = gemm.recorded_calls()[:gemm_calls_per_step]
+    fused_all = gemm.recorded_fused_calls()
+    step_fused = fused_all[:len(fused_all) // passes]
+    step_pf = {i: d for i, d in gemm.recorded_prefetches().items() if i < len(step_calls)}
 
     def barrier():
         if world > 1:
@@ -448,12 +453,10 @@ def run_edb(args):
     ms_per_step = ms_total / args.steps
     peaks = measured_peaks()
     # GEMM shapes of one step, recorded by the dispatcher during the eager warm-up
-    calls = gemm.recorded_calls()[:gemm_calls_per_step]
-    fused_all = gemm.recorded_fused_calls()
-    fused_calls = fused_all[:len(fused_all) // passes]
+    calls, fused_calls = step_calls, step_fused
     # every rank replays (the fused kernels talk to the peers); rank 0 reports
     barrier()
-    pf_map = {i: d for i, d in gemm.recorded_prefetches().items() if i < len(calls)}
+    pf_map = step_pf
     roof = gemm_roofline(torch, gemm, calls, peaks, sustained=False, fused_calls=fused_calls,
                          rank=rank, pf_map=pf_map)
     barrier()

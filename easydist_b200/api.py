@@ -61,6 +61,18 @@ def _flat_inputs(params, buffers, named_states, args, kwargs):
     return pytree.tree_flatten((params, buffers, named_states, args, kwargs))[0]
 
 
+def _single_group(gm, ops, ranks):
+    """True when every collective of the graph runs on the group `ranks`."""
+    want = list(ranks)
+    for nd in gm.graph.nodes:
+        if nd.op == "call_function" and nd.target in ops.COMM_FUNCS:
+            grp = nd.args[5] if nd.target is ops.all_to_all_start else \
+                (nd.args[3] if nd.target is ops.reduce_scatter_start else nd.args[2])
+            if list(grp) != want:
+                return False
+    return True
+
+
 class _ParamIO:
     """The slice of GraphIO the prefetch pass needs (auto path: placeholders by position)."""
 
@@ -129,7 +141,16 @@ def _finish(gm, params, buffers, named_states, args, kwargs, ops, native, io=Non
     info["reinplaced_updates"] = lowering.reinplace_optimizer_updates(gm)
     if native:
         from .runtime import get_runtime
-        info["symm_bytes"] = lowering.assign_static_buffers(gm, get_runtime(), ops)
+        # push-protocol collectives need ONE group for the end-of-step barrier: a 1-D mesh / the dp
+        # group.  (N-D meshes keep the flag protocol: a barrier per mesh dim would not cover the
+        # buffers of the other dims' collectives.)
+        push = ranks is not None and len(ranks) > 1 and os.environ.get("EDB_EPOCH", "1") == "1" \
+            and os.environ.get("EDB_PUSH_COLL", "1") == "1" and hasattr(ops, "epoch_barrier") \
+            and not overlap and _single_group(gm, ops, ranks)
+        info["symm_bytes"] = lowering.assign_static_buffers(gm, get_runtime(), ops, push=push)
+        if push and any(nd.kwargs.get("_push") for nd in gm.graph.nodes if nd.op == "call_function"):
+            lowering.ensure_end_barrier(gm, ranks, ops)
+            info["push_collectives"] = True
         info["gemm_nodes"] = lowering.dispatch_compute(gm)
     gm.graph.lint()
     gm.recompile()

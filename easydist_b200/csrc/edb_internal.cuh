@@ -54,6 +54,12 @@ enum FlagWord : int {
   F_AGDONE = 59,     // comm CTAs of the current launch that have finished
   F_AGCHUNK = 64,    // [64..71] local: peer shard c is in the gathered buffer (launch number)
   F_AGTILE = 72,     // [72..79] comm CTAs done with shard c
+  // push protocol of the stand-alone collectives (edb_*_push, epoch mode): every member writes its
+  // contribution straight into the consumers' static buffers and raises ONE one-way flag per peer
+  F_PUSHFLAG = 80,   // [80..87] PUSHED[p]: member p's data of push-op q has landed here (written by p)
+  F_PUSHSEQ = 88,    // push-ops completed locally
+  F_CNT_P = 89,      // last-block counters of the push kernels
+  F_CNT_P2 = 90,
 };
 
 struct Group {

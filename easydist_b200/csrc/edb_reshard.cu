@@ -138,6 +138,57 @@ __global__ void __launch_bounds__(kThreads) k_gather(const __grid_constant__ Gat
   finish_op(d.f, q, &s_last, gridDim.x);
 }
 
+// ---- push protocol (epoch mode) ---------------------------------------------------------------
+// The destination buffers are static per graph node and an edb_epoch_barrier separates two steps, so
+// nobody reads or writes them concurrently with the next step's push: no write-after-read guard, no
+// READY/DONE handshake — data first, then one flag per peer (system-scope release), and the
+// consumer polls its own memory.
+
+// All CTAs of the launch have written their share: the last one to arrive raises the flags.
+// Returns true in that CTA.
+__device__ __forceinline__ bool push_signal(const FlagCtx& f, uint64_t q, int* s_last,
+                                            unsigned n_ctas) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence_system();  // covers the CTA's stores into peer memory (see grid_signal)
+    const unsigned long long prev =
+        atomicAdd(reinterpret_cast<unsigned long long*>(f.local + F_CNT_P), 1ULL);
+    const int last = (prev == (unsigned long long)n_ctas - 1);
+    if (last) {
+      f.local[F_CNT_P] = 0;
+      __threadfence_system();
+    }
+    *s_last = last;
+  }
+  __syncthreads();
+  if (*s_last && (int)threadIdx.x < f.n && (int)threadIdx.x != f.me)
+    st_release_sys(f.peer[threadIdx.x] + F_PUSHFLAG + f.me, q);
+  return *s_last != 0;
+}
+
+__device__ __forceinline__ void push_wait(const FlagCtx& f, uint64_t q) {
+  if ((int)threadIdx.x < f.n && (int)threadIdx.x != f.me)
+    spin_wait_sys(f.local + F_PUSHFLAG + threadIdx.x, q, f.timeout_ns, f.local + F_ERR);
+  __syncthreads();
+}
+
+// all-gather / all-to-all / any box scatter as a push: every box writes into a member's buffer
+__global__ void __launch_bounds__(kThreads) k_push(const __grid_constant__ GatherDesc d) {
+  __shared__ uint64_t s_q;
+  __shared__ int s_last;
+  const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t nthr = (uint64_t)gridDim.x * blockDim.x;
+  if (threadIdx.x == 0) s_q = ld_relaxed_gpu(d.f.local + F_PUSHSEQ) + 1;
+  __syncthreads();
+  const uint64_t q = s_q;
+  for (int b = 0; b < d.n_boxes; ++b) copy_box(d.box[b], tid, nthr);
+  if (push_signal(d.f, q, &s_last, gridDim.x)) {
+    // only this CTA stays until every member's data is here; the others are done
+    push_wait(d.f, q);
+    if (threadIdx.x == 0) st_release_gpu(d.f.local + F_PUSHSEQ, q);
+  }
+}
+
 __global__ void __launch_bounds__(32) k_guard(const __grid_constant__ FlagCtx f) {
   __shared__ uint64_t s_q;
   begin_op(f, &s_q);
@@ -290,6 +341,7 @@ struct ReduceLaunch {
   ReduceDesc d;
   char* dst_b;  // optional second destination (two-shot: final dst of my own part)
   int vec;
+  int push;     // k_push_reduce: d.pull[] are pushes into the members' receive slots
 };
 
 template <typename In, typename Out, int OP>
@@ -319,6 +371,37 @@ __global__ void __launch_bounds__(kThreads, 3) k_reduce(const __grid_constant__ 
       }
     }
     finish_op(d.f, q, &s_last, gridDim.x);
+  }
+}
+
+// reduce-scatter / one-shot all-reduce as a push: my chunk for member p goes into p's receive slot
+// [me] (d.pull[] = the pushes, own slot included), then every CTA reduces its share of the n
+// local slots in rank order
+template <typename In, typename Out, int OP>
+__global__ void __launch_bounds__(kThreads, 3) k_push_reduce(const __grid_constant__ ReduceLaunch L) {
+  __shared__ uint64_t s_q;
+  __shared__ int s_last;
+  const ReduceDesc& d = L.d;
+  const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t nthr = (uint64_t)gridDim.x * blockDim.x;
+  if (threadIdx.x == 0) s_q = ld_relaxed_gpu(d.f.local + F_PUSHSEQ) + 1;
+  __syncthreads();
+  const uint64_t q = s_q;
+  for (int b = 0; b < d.n_pull; ++b) copy_box(d.pull[b], tid, nthr);
+  push_signal(d.f, q, &s_last, gridDim.x);
+  push_wait(d.f, q);
+  reduce_rows<In, Out, OP>(d, L.dst_b, tid, nthr, L.vec != 0);
+  // the op number advances when every CTA is through (they all read it at the start)
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned long long prev =
+        atomicAdd(reinterpret_cast<unsigned long long*>(d.f.local + F_CNT_P2), 1ULL);
+    if (prev == (unsigned long long)gridDim.x - 1) {
+      d.f.local[F_CNT_P2] = 0;
+      __threadfence();
+      st_release_gpu(d.f.local + F_PUSHSEQ, q);
+    }
   }
 }
 
@@ -474,12 +557,14 @@ static size_t box_bytes(const Box& b) {
   return (size_t)(b.inner * b.ext[0] * b.ext[1] * b.ext[2] * b.ext[3]);
 }
 
-static int launch_gather(const GatherDesc& d, bool flags, cudaStream_t st) {
+static int launch_gather(const GatherDesc& d, bool flags, cudaStream_t st, bool push = false) {
   size_t bytes = 0;
   for (int b = 0; b < d.n_boxes; ++b) bytes += box_bytes(d.box[b]);
   static const int occ_gather = occupancy_of(k_gather);
-  const int grid = grid_for_bytes(bytes, kThreads, flags ? occ_gather : 0);
-  if (flags) k_gather<<<grid, kThreads, 0, st>>>(d);
+  static const int occ_push = occupancy_of(k_push);
+  const int grid = grid_for_bytes(bytes, kThreads, push ? occ_push : (flags ? occ_gather : 0));
+  if (push) k_push<<<grid, kThreads, 0, st>>>(d);
+  else if (flags) k_gather<<<grid, kThreads, 0, st>>>(d);
   else k_local_copy<<<grid, kThreads, 0, st>>>(d);
   count_launch();
   return cuda_check(cudaGetLastError(), "reshard kernel launch");
@@ -487,6 +572,12 @@ static int launch_gather(const GatherDesc& d, bool flags, cudaStream_t st) {
 
 template <typename In, typename Out, int OP>
 static void launch_reduce_kernel(const ReduceLaunch& L, size_t bytes, cudaStream_t st) {
+  if (L.push) {
+    static const int occ_p = occupancy_of(k_push_reduce<In, Out, OP>);
+    const int grid = grid_for_bytes(bytes, kThreads, occ_p);
+    k_push_reduce<In, Out, OP><<<grid, kThreads, 0, st>>>(L);
+    return;
+  }
   static const int occ = occupancy_of(k_reduce<In, Out, OP>);
   const int grid = grid_for_bytes(bytes, kThreads, occ);
   k_reduce<In, Out, OP><<<grid, kThreads, 0, st>>>(L);
@@ -518,8 +609,10 @@ static int launch_reduce(ReduceLaunch& L, cudaStream_t st) {
   for (int k = 0; k < 4; ++k) obits |= (uintptr_t)d.dstr[k];
   const size_t oalign = obytes >= 16 ? 16 : obytes;
   L.vec = ((bits & 15) == 0 && (obits & (oalign - 1)) == 0) ? 1 : 0;
-  const size_t bytes = (size_t)(d.inner * d.ext[0] * d.ext[1] * d.ext[2] * d.ext[3]) * d.n_src +
-                       (d.has_in ? box_bytes(d.in) : 0);
+  size_t bytes = (size_t)(d.inner * d.ext[0] * d.ext[1] * d.ext[2] * d.ext[3]) * d.n_src +
+                 (d.has_in ? box_bytes(d.in) : 0);
+  if (L.push)
+    for (int b = 0; b < d.n_pull; ++b) bytes += box_bytes(d.pull[b]);
   const size_t grid = bytes;  // the launcher sizes the grid from the byte count + occupancy
   const int key = d.dtype * 16 + d.out_dtype;
   switch (key) {
@@ -940,6 +1033,202 @@ int edb_all_reduce(int gid, void* dst, uint64_t stage_off, uint64_t stage2_off, 
   }
   d.n_pull = np;
   return launch_reduce(L, (cudaStream_t)stream);
+}
+
+int edb_all_gather_push(int gid, uint64_t dst_off, const void* src, const int64_t* local_shape,
+                        int ndim, int dim, int elem_size, void* stream) {
+  GatherDesc d;
+  memset(&d, 0, sizeof(d));
+  int rc = fill_flagctx(&d.f, gid);
+  if (rc) return rc;
+  EDB_REQUIRE(ndim >= 1 && ndim <= 16 && dim >= 0 && dim < ndim, "edb_all_gather_push: bad dim %d/%d",
+              dim, ndim);
+  Runtime& r = rt();
+  const Group& g = r.groups[gid];
+  const int n = g.n, me = g.me;
+  if (n <= 1) return edb_all_gather(gid, dst_off, src, local_shape, ndim, dim, elem_size, stream);
+  int64_t outer = 1, rowb = elem_size;
+  for (int i = 0; i < dim; ++i) outer *= local_shape[i];
+  for (int i = dim; i < ndim; ++i) rowb *= local_shape[i];
+  const size_t total = (size_t)outer * rowb * n;
+  if (total == 0) return EDB_OK;
+  rc = check_symm(dst_off, total, "edb_all_gather_push");
+  if (rc) return rc;
+  const int64_t ext[2] = {outer, rowb};
+  const int64_t s_src[2] = {rowb, 1}, s_out[2] = {rowb * n, 1};
+  int nb = 0;
+  for (int k = 0; k < n; ++k) {  // own buffer first, then the peers starting with the next one
+    const int p = (me + k) % n;
+    char* out_p = r.peer_heap[g.ranks[p]] + dst_off;
+    if (p == me && out_p + (int64_t)me * rowb == static_cast<const char*>(src) && outer == 1)
+      continue;  // in-place gather: my part already sits in my buffer
+    rc = make_box(&d.box[nb], src, s_src, out_p + (int64_t)me * rowb, s_out, ext, 2, 1, -1);
+    if (rc) return rc;
+    ++nb;
+  }
+  d.n_in = 0;
+  d.n_boxes = nb;
+  return launch_gather(d, true, (cudaStream_t)stream, true);
+}
+
+int edb_all_to_all_push(int gid, uint64_t dst_off, const void* src, const int64_t* local_shape,
+                        int ndim, int gather_dim, int scatter_dim, int elem_size, void* stream) {
+  GatherDesc d;
+  memset(&d, 0, sizeof(d));
+  int rc = fill_flagctx(&d.f, gid);
+  if (rc) return rc;
+  EDB_REQUIRE(ndim >= 1 && ndim <= 16 && gather_dim >= 0 && gather_dim < ndim && scatter_dim >= 0 &&
+                  scatter_dim < ndim && gather_dim != scatter_dim && src != nullptr,
+              "edb_all_to_all_push: bad dims g=%d s=%d ndim=%d", gather_dim, scatter_dim, ndim);
+  Runtime& r = rt();
+  const Group& g = r.groups[gid];
+  const int n = g.n, me = g.me;
+  EDB_REQUIRE(local_shape[scatter_dim] % n == 0,
+              "edb_all_to_all_push: scatter dim size %lld not divisible by group size %d",
+              (long long)local_shape[scatter_dim], n);
+  const int64_t total = numel_of(local_shape, ndim) * elem_size;
+  if (total == 0) return EDB_OK;
+  rc = check_symm(dst_off, (size_t)total, "edb_all_to_all_push");
+  if (rc) return rc;
+  int64_t oshape[16], ext[16], sstr[16], dstr[16];
+  for (int i = 0; i < ndim; ++i) oshape[i] = ext[i] = local_shape[i];
+  const int64_t cs = local_shape[scatter_dim] / n;
+  oshape[gather_dim] = local_shape[gather_dim] * n;
+  oshape[scatter_dim] = cs;
+  ext[scatter_dim] = cs;
+  contiguous_strides(local_shape, ndim, elem_size, sstr);
+  contiguous_strides(oshape, ndim, elem_size, dstr);
+  int nb = 0;
+  for (int k = 0; k < n; ++k) {
+    const int p = (me + k) % n;
+    // chunk p of my tensor along scatter_dim lands at index `me` along gather_dim of p's result
+    rc = make_box(&d.box[nb++], static_cast<const char*>(src) + (int64_t)p * cs * sstr[scatter_dim],
+                  sstr,
+                  r.peer_heap[g.ranks[p]] + dst_off +
+                      (int64_t)me * local_shape[gather_dim] * dstr[gather_dim],
+                  dstr, ext, ndim, elem_size, -1);
+    if (rc) return rc;
+  }
+  d.n_in = 0;
+  d.n_boxes = nb;
+  return launch_gather(d, true, (cudaStream_t)stream, true);
+}
+
+// shared by reduce_scatter_push and the one-shot all_reduce_push: `pieces` = n (reduce-scatter: my
+// tensor is cut into n chunks along dim, chunk p goes to member p) or 1 (all-reduce: everybody gets
+// my whole tensor); slot s of the local receive buffer holds member s's contribution
+static int push_reduce_impl(int gid, void* dst, uint64_t recv_off, const void* src, int64_t outer,
+                            int64_t chunk_b, bool scatter, int dtype, int redop, float scale,
+                            int out_dtype, const char* who, cudaStream_t st) {
+  ReduceLaunch L;
+  memset(&L, 0, sizeof(L));
+  ReduceDesc& d = L.d;
+  int rc = fill_flagctx(&d.f, gid);
+  if (rc) return rc;
+  Runtime& r = rt();
+  const Group& g = r.groups[gid];
+  const int n = g.n, me = g.me;
+  const int64_t slot_b = outer * chunk_b;  // bytes of one member's contribution to one receiver
+  rc = check_symm(recv_off, (size_t)slot_b * n, who);
+  if (rc) return rc;
+  EDB_REQUIRE(outer < 0xffffffffll, "%s: too many rows", who);
+  const int64_t ext[2] = {outer, chunk_b};
+  const int64_t s_src[2] = {scatter ? chunk_b * n : chunk_b, 1}, s_slot[2] = {chunk_b, 1};
+  for (int k = 0; k < n; ++k) {
+    const int p = (me + 1 + k) % n;  // peers first, own slot last
+    const char* sp = static_cast<const char*>(src) + (scatter ? (int64_t)p * chunk_b : 0);
+    rc = make_box(&d.pull[k], sp, s_src, r.peer_heap[g.ranks[p]] + recv_off + (int64_t)me * slot_b,
+                  s_slot, ext, 2, 1, -1);
+    if (rc) return rc;
+  }
+  d.n_pull = n;
+  for (int s = 0; s < n; ++s) d.src[s] = r.heap + recv_off + (int64_t)s * slot_b;
+  d.n_src = n;
+  d.dst = static_cast<char*>(dst);
+  d.inner = slot_b;  // the slots are contiguous: one long row
+  for (int k = 0; k < 4; ++k) {
+    d.ext[k] = 1;
+    d.sstr[k] = 0;
+    d.dstr[k] = 0;
+  }
+  d.dtype = dtype;
+  d.out_dtype = out_dtype;
+  d.redop = redop;
+  d.scale = scale;
+  L.push = 1;
+  return launch_reduce(L, st);
+}
+
+int edb_reduce_scatter_push(int gid, void* dst, uint64_t recv_off, const void* src,
+                            const int64_t* shape, int ndim, int dim, int dtype, int redop,
+                            float post_scale, int out_dtype, void* stream) {
+  Runtime& r = rt();
+  if (!r.inited) return set_error(EDB_E_STATE, "runtime not initialised (call edb_init)");
+  if (gid < 0 || gid >= r.ngroups) return set_error(EDB_E_INVALID, "bad group id %d", gid);
+  const int n = r.groups[gid].n;
+  if (n <= 1 || src == nullptr)
+    return edb_reduce_scatter(gid, dst, recv_off, src, shape, ndim, dim, dtype, redop, post_scale,
+                              out_dtype, stream);
+  EDB_REQUIRE(ndim >= 1 && ndim <= 16 && dim >= 0 && dim < ndim, "edb_reduce_scatter_push: bad dim");
+  EDB_REQUIRE(shape[dim] % n == 0,
+              "edb_reduce_scatter_push: input dimension %d (%lld) must be a multiple of group_size %d",
+              dim, (long long)shape[dim], n);
+  const size_t es = dtype_size(dtype);
+  EDB_REQUIRE(es && dtype_size(out_dtype), "edb_reduce_scatter_push: bad dtype");
+  EDB_REQUIRE(!(redop == EDB_AVG && (dtype == EDB_I32 || dtype == EDB_I64)),
+              "edb_reduce_scatter_push: avg on integer dtype");
+  int64_t outer = 1, inner_el = 1;
+  for (int i = 0; i < dim; ++i) outer *= shape[i];
+  for (int i = dim + 1; i < ndim; ++i) inner_el *= shape[i];
+  const int64_t chunk_b = shape[dim] / n * inner_el * (int64_t)es;
+  if (outer * chunk_b == 0) return EDB_OK;
+  if (out_dtype == dtype) {
+    const float sc = post_scale * (redop == EDB_AVG ? 1.0f / (float)n : 1.0f);
+    const int ll = ll_try(gid, /*LL_REDUCE_SCATTER*/ 2, dst, src, outer * chunk_b * n, outer, chunk_b,
+                          dtype, redop, sc, (cudaStream_t)stream);
+    if (ll >= 0) return ll;
+  }
+  return push_reduce_impl(gid, dst, recv_off, src, outer, chunk_b, true, dtype, redop,
+                          post_scale * (redop == EDB_AVG ? 1.0f / (float)n : 1.0f), out_dtype,
+                          "edb_reduce_scatter_push", (cudaStream_t)stream);
+}
+
+int edb_all_reduce_push(int gid, uint64_t out_off, uint64_t recv_off, const void* src, int64_t numel,
+                        int dtype, int redop, void* stream) {
+  Runtime& r = rt();
+  if (!r.inited) return set_error(EDB_E_STATE, "runtime not initialised (call edb_init)");
+  if (gid < 0 || gid >= r.ngroups) return set_error(EDB_E_INVALID, "bad group id %d", gid);
+  const Group& g = r.groups[gid];
+  const int n = g.n, me = g.me;
+  const size_t es = dtype_size(dtype);
+  EDB_REQUIRE(es && src != nullptr, "edb_all_reduce_push: bad dtype %d / src", dtype);
+  EDB_REQUIRE(!(redop == EDB_AVG && (dtype == EDB_I32 || dtype == EDB_I64)),
+              "edb_all_reduce_push: avg on integer dtype");
+  const int64_t total = numel * (int64_t)es;
+  if (total == 0) return EDB_OK;
+  int rc = check_symm(out_off, (size_t)total, "edb_all_reduce_push");
+  if (rc) return rc;
+  char* out = r.heap + out_off;
+  if (n <= 1) return edb_copy(out, src, (size_t)total, stream);
+  const float scale = redop == EDB_AVG ? 1.0f / (float)n : 1.0f;
+  {
+    const int ll = ll_try(gid, /*LL_ALL_REDUCE*/ 0, out, src, total, 1, total, dtype, redop, scale,
+                          (cudaStream_t)stream);
+    if (ll >= 0) return ll;
+  }
+  const int64_t per = 16 / (int64_t)es * n;
+  const bool two_shot = total > r.allreduce_oneshot_bytes && numel % per == 0;
+  if (!two_shot)  // everybody receives everybody's tensor (receive buffer: n * total bytes)
+    return push_reduce_impl(gid, out, recv_off, src, 1, total, false, dtype, redop, scale, dtype,
+                            "edb_all_reduce_push", (cudaStream_t)stream);
+  // two-shot: reduce-scatter push (my reduced chunk lands in place, at out + me*chunk), then an
+  // in-place all-gather push of the chunks
+  const int64_t chunk_b = total / n;
+  rc = push_reduce_impl(gid, out + (int64_t)me * chunk_b, recv_off, src, 1, chunk_b, true, dtype,
+                        redop, scale, dtype, "edb_all_reduce_push", (cudaStream_t)stream);
+  if (rc) return rc;
+  const int64_t shp[1] = {chunk_b};
+  return edb_all_gather_push(gid, out_off, out + (int64_t)me * chunk_b, shp, 1, 0, 1, stream);
 }
 
 int edb_epoch_barrier(int gid, void* stream) {

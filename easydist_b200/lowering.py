@@ -822,20 +822,31 @@ def _nbytes(val):
     return val.numel() * val.element_size()
 
 
-def assign_static_buffers(gm, rt, ops=_default_ops):
+def assign_static_buffers(gm, rt, ops=_default_ops, push=False):
     """Give every communication node fixed symmetric-heap buffers (`_buf` kwarg) sized from the
     local metas: no allocation, no address change on the comm path => CUDA-graph capturable and
-    zero-copy outputs.  Returns the number of bytes reserved."""
+    zero-copy outputs.  Returns the number of bytes reserved.
+
+    push=True (the graph ends with an epoch barrier, see insert_epoch_barriers): the nodes are
+    marked `_push=1` — with buffers dedicated to a node and a group barrier between two steps the
+    collectives need no handshake (edb_*_push in edb.h): data straight into the consumers' buffers
+    plus one flag per peer."""
     total = 0
     oneshot = rt.get_option("allreduce_oneshot_bytes")
     for node in gm.graph.nodes:
         if node.op != "call_function" or node.target not in ops.COMM_FUNCS:
             continue
         x = node.args[0].meta["val"]
+        lane = bool(node.kwargs.get("_lane"))
         if node.target is ops.all_gather_start:
             need = [_nbytes(node.meta["val"])]
         elif node.target is ops.all_reduce_start:
-            need = [_nbytes(x)] * (2 if _nbytes(x) > oneshot else 1)
+            if push and not lane:
+                grp = node.args[2]
+                need = list(ops.all_reduce_push_sizes(_nbytes(x), x.numel(), x.element_size(),
+                                                      len(grp), oneshot))
+            else:
+                need = [_nbytes(x)] * (2 if _nbytes(x) > oneshot else 1)
         else:
             need = [_nbytes(x)]
         if need[0] == 0:
@@ -844,6 +855,8 @@ def assign_static_buffers(gm, rt, ops=_default_ops):
         total += sum(need)
         kw = dict(node.kwargs)
         kw["_buf"] = (bufs[0].offset, need[0]) + tuple(b.offset for b in bufs[1:])
+        if push and not lane:
+            kw["_push"] = 1
         node.kwargs = kw
     gm.recompile()
     return total
@@ -1394,14 +1407,24 @@ def insert_epoch_barriers(gm, ranks, ops=_default_ops):
         with graph.inserting_after(anchor):
             graph.call_function(ops.epoch_barrier, args=(anchor, list(ranks)))
         n_new += 1
+    return n_new + ensure_end_barrier(gm, ranks, ops)
+
+
+def ensure_end_barrier(gm, ranks, ops=_default_ops):
+    """One epoch barrier as the last node of the step (idempotent)."""
+    graph = gm.graph
     out_node = next(nd for nd in graph.nodes if nd.op == "output")
+    prev = out_node.prev
+    if prev.op == "call_function" and prev.target is ops.epoch_barrier:
+        return 0
     some = next((nd for nd in reversed(list(graph.nodes)) if nd.op == "call_function"
                  and isinstance(nd.meta.get("val"), torch.Tensor)), None)
     if some is None:
         some = next(nd for nd in graph.nodes if nd.op == "placeholder")
     with graph.inserting_before(out_node):
         graph.call_function(ops.epoch_barrier, args=(some, list(ranks)))
-    return n_new + 1
+    gm.recompile()
+    return 1
 
 
 def fuse_collective_gemms(gm, io, rt, ranks, ops=_default_ops, my_index=None):

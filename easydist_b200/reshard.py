@@ -137,14 +137,29 @@ def _buffers(rt, _buf, sizes):
 # ---- all_reduce -------------------------------------------------------------------------------------
 
 
+def all_reduce_push_sizes(nbytes, numel, elem_size, n, oneshot_bytes):
+    """(receive bytes, result bytes) of edb_all_reduce_push — same rule as the C side."""
+    two_shot = nbytes > oneshot_bytes and numel % (16 // elem_size * n) == 0
+    return (nbytes if two_shot else n * nbytes), nbytes
+
+
 def all_reduce_start(self: torch.Tensor, reduceOp: str, group: List[int], tag: str = "", *,
-                     _buf=None, _lane=0):
-    """P(op) -> R. Reference: sharding.py:94-98 (c10d_functional.all_reduce)."""
+                     _buf=None, _lane=0, _push=0):
+    """P(op) -> R. Reference: sharding.py:94-98 (c10d_functional.all_reduce).
+    `_push=1` (set by lowering.assign_static_buffers for graphs that end with an epoch barrier):
+    the push protocol, _buf = (receive offset, size, result offset); the result is a view of the
+    static symmetric result buffer."""
     if _is_fake(self):
         return torch.empty_like(self, memory_format=torch.contiguous_format)
     _require_cuda(self, "all_reduce_start")
     rt, gid, n, _ = _group(group, _lane)
     x = self.contiguous()
+    if _push and _buf is not None and n > 1 and x.numel() > 0:
+        recv_off, out_off = int(_buf[0]), int(_buf[2])
+        check(rt.lib.edb_all_reduce_push(gid, out_off, recv_off, x.data_ptr(), x.numel(),
+                                         _dtype_code(x, "all_reduce_start"),
+                                         _redop(reduceOp, "all_reduce_start"), rt.stream()))
+        return SymmBuffer(rt, out_off, x.numel() * x.element_size()).tensor(x.dtype, x.shape)
     out = torch.empty_like(x)
     nbytes = x.numel() * x.element_size()
     if nbytes == 0:
@@ -175,7 +190,7 @@ def all_reduce_end(self: torch.Tensor, reduceOp: str, group: List[int], tag: str
 
 
 def all_gather_start(self: torch.Tensor, gather_dim: int, group: List[int], tag: str = "", *,
-                     _buf=None, _lane=0):
+                     _buf=None, _lane=0, _push=0):
     """S(gather_dim) -> R. Reference: sharding.py:105-111 gathers along dim 0 and leaves the
     chunk+cat to all_gather_end (:114-119); here the result is already laid out along
     `gather_dim`."""
@@ -195,8 +210,9 @@ def all_gather_start(self: torch.Tensor, gather_dim: int, group: List[int], tag:
     (buf,), static = _buffers(rt, _buf, [nbytes])
     # the lane needs a buffer of its own until *_end: only with static buffers
     with _Lane(_lane and n > 1 and static) as lane:
-        check(rt.lib.edb_all_gather(gid, buf.offset, x.data_ptr(), i64_array(x.shape), ndim, dim,
-                                    x.element_size(), rt.stream()))
+        fn = rt.lib.edb_all_gather_push if (_push and static and not _lane) else rt.lib.edb_all_gather
+        check(fn(gid, buf.offset, x.data_ptr(), i64_array(x.shape), ndim, dim, x.element_size(),
+                 rt.stream()))
         out = buf.tensor(x.dtype, out_shape)
         out = out if static else out.clone()
     return lane.tag(out, x)
@@ -258,7 +274,7 @@ def copy_wrapper(self, other):
 
 def reduce_scatter_start(self: torch.Tensor, reduceOp: str, scatter_dim: int, group: List[int],
                          tag: str = "", *, _buf=None, _scale: float = 1.0, _out_dtype=None,
-                         _lane=0):
+                         _lane=0, _push=0):
     """P(op) -> S(scatter_dim). Reference: sharding.py:130-144 (pre-permute copy for dim != 0 and
     reduce_scatter_tensor). `_scale`/`_out_dtype` fuse the gradient scale / cast into the kernel."""
     n = len(group)
@@ -283,11 +299,12 @@ def reduce_scatter_start(self: torch.Tensor, reduceOp: str, scatter_dim: int, gr
         (buf,), static = _buffers(rt, _buf, [nbytes])
         stage = buf.offset
     with _Lane(_lane and n > 1 and static) as lane:
-        check(rt.lib.edb_reduce_scatter(gid, out.data_ptr(), stage, x.data_ptr(),
-                                        i64_array(x.shape), ndim, dim,
-                                        _dtype_code(x, "reduce_scatter_start"),
-                                        _redop(reduceOp, "reduce_scatter_start"), float(_scale),
-                                        _TORCH_DTYPE_CODE[out_dtype], rt.stream()))
+        fn = rt.lib.edb_reduce_scatter_push if (_push and static and not _lane) \
+            else rt.lib.edb_reduce_scatter
+        check(fn(gid, out.data_ptr(), stage, x.data_ptr(),
+                 i64_array(x.shape), ndim, dim, _dtype_code(x, "reduce_scatter_start"),
+                 _redop(reduceOp, "reduce_scatter_start"), float(_scale),
+                 _TORCH_DTYPE_CODE[out_dtype], rt.stream()))
     return lane.tag(out, x)
 
 
@@ -302,7 +319,7 @@ def reduce_scatter_end(self: torch.Tensor, reduceOp: str, scatter_dim: int, grou
 
 
 def all_to_all_start(tensor, gather_dim, scatter_dim, num_chunks, indice, ranks, tag: str = "", *,
-                     _buf=None):
+                     _buf=None, _push=0):
     """S(gather_dim) -> S(scatter_dim). Reference: sharding.py:155-163 (all-gather + local chunk,
     n x over-communication); here a true all-to-all: each rank pulls only its slice."""
     n = len(ranks)
@@ -320,8 +337,13 @@ def all_to_all_start(tensor, gather_dim, scatter_dim, num_chunks, indice, ranks,
     rt, gid, n, me = _group(ranks)
     assert me == indice, f"all_to_all: indice {indice} is not this rank's coordinate {me}"
     x = tensor.contiguous()
-    out = x.new_empty(out_shape)
     nbytes = x.numel() * x.element_size()
+    if _push and _buf is not None and n > 1 and nbytes > 0:
+        # push protocol: every member writes its pieces straight into the static result buffers
+        check(rt.lib.edb_all_to_all_push(gid, int(_buf[0]), x.data_ptr(), i64_array(x.shape), ndim,
+                                         g, s, x.element_size(), rt.stream()))
+        return SymmBuffer(rt, int(_buf[0]), nbytes).tensor(x.dtype, out_shape)
+    out = x.new_empty(out_shape)
     if nbytes == 0:
         return out
     stage = 0

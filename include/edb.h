@@ -244,6 +244,30 @@ int edb_ag_gemm_epoch_bf16(int gid, void* C, const void* A, const void* bias, ui
                            uint64_t b_full_off, int64_t M, int64_t N, int64_t K, int64_t lda,
                            int64_t ldc, void* stream);
 
+/* The stand-alone collectives as PUSHES (epoch mode; what the compiled graphs use for every reshard
+ * edge with static buffers).  Preconditions: the destination / receive buffers named by the
+ * symmetric offsets are dedicated to this graph node, and an edb_epoch_barrier separates the last
+ * reader of the previous step from this call (the compiled step ends with one).  Then no
+ * write-after-read guard and no READY/DONE handshake is needed: every member stores its contribution
+ * straight into the consumers' buffers over NVLink and raises one flag per peer; the consumer polls
+ * its own memory.  Results are identical to the flag-protocol entry points above (same rank-order
+ * fp32 accumulation).  <= "ll_max_bytes" the low-latency packet path is taken as before.
+ *   all_gather_push    : dst_off = the gathered result on every member (as edb_all_gather)
+ *   all_to_all_push    : dst_off = the RESULT (symmetric, contiguous, shape of edb_all_to_all's dst)
+ *   reduce_scatter_push: recv_off = n receive slots (total input bytes); dst = local result
+ *   all_reduce_push    : out_off = the result on every member; recv_off = n * bytes (one-shot: bytes
+ *                        <= "allreduce_oneshot_bytes" or numel not divisible) else bytes (two-shot:
+ *                        reduce-scatter push + in-place all-gather push) */
+int edb_all_gather_push(int gid, uint64_t dst_off, const void* src, const int64_t* local_shape,
+                        int ndim, int dim, int elem_size, void* stream);
+int edb_all_to_all_push(int gid, uint64_t dst_off, const void* src, const int64_t* local_shape,
+                        int ndim, int gather_dim, int scatter_dim, int elem_size, void* stream);
+int edb_reduce_scatter_push(int gid, void* dst, uint64_t recv_off, const void* src,
+                            const int64_t* shape, int ndim, int dim, int dtype, int redop,
+                            float post_scale, int out_dtype, void* stream);
+int edb_all_reduce_push(int gid, uint64_t out_off, uint64_t recv_off, const void* src, int64_t numel,
+                        int dtype, int redop, void* stream);
+
 /* All-gather as a PREFETCH (the way the zero3 / auto-SPMD parameter gathers run in epoch mode).
  * An item names a byte range that exists at the same symmetric offset on every member (a
  * parameter shard, or part of one): for every member p the range [src_off, src_off + bytes) of
