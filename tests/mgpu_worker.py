@@ -112,6 +112,124 @@ def run_cases(rank, world, group, tag=""):
     return n_ok
 
 
+def run_push_cases(rank, world, group):
+    """The push-protocol collectives (edb_*_push: static per-node buffers, one flag per peer, an
+    epoch barrier between reuses of a buffer) bit for bit against the oracle: every op, the LL
+    threshold switched off for half of the passes so that the push kernels themselves run on the
+    small shapes too, random rank skew, buffers reused after a barrier (as a compiled step does)."""
+    rt = runtime.get_runtime()
+    n_ok = 0
+    oneshot = rt.get_option("allreduce_oneshot_bytes")
+    ll_saved = rt.get_option("ll_max_bytes")
+    x0 = to_dev(np.zeros(1, dtype=np.float32), "float32")
+    ag_cases = [((3, 4), 0), ((3, 4), 1), ((2, 3, 5), 2), ((7,), 0), ((64, 1024), 0), ((64, 1024), 1),
+                ((5, 33), 1), ((2, 16, 128, 32), 2), ((512, 2048), 0)]
+    a2a_cases = [((2, 4 * world), 0, 1), ((2 * world, 3), 1, 0), ((2, 3, 2 * world), 0, 2),
+                 ((2, 128, 16 * world), 0, 2), ((2 * world, 16, 8 * world), 2, 0),
+                 ((64 * world, 1024), 1, 0)]
+    red_cases = [((2 * world, 3), 0), ((3, 2 * world), 1), ((2, 3, world), 2), ((64 * world, 256), 0),
+                 ((16, 8 * world, 32), 1), ((512 * world, 1024), 0)]
+    ar_cases = [(5, 3), (), (1024,), (300, 1000), (1 << 20,), (world * 1024 * 512,)]
+    for pas in range(4):
+        rt.set_option("ll_max_bytes", ll_saved if pas % 2 == 0 else 0)
+        mark = rt.mark()
+        if rank % 2 == pas % 2:
+            torch.cuda._sleep(2_000_000)  # skew: half of the ranks arrive late
+        for dtype in ("float32", "bfloat16", "int64"):
+            es = torch.empty((), dtype=TORCH_DT[dtype]).element_size()
+            for shape, dim in ag_cases:
+                key = f"pag{pas}_{shape}_{dim}_{dtype}"
+                xs = inputs_for(key, shape, dtype, world)
+                nb = int(np.prod(shape)) * es * world
+                buf = rt.alloc(nb)
+                got = reshard.all_gather_start(to_dev(xs[rank], dtype), dim, group,
+                                               _buf=(buf.offset, nb), _push=1)
+                check_equal(got, O.all_gather(xs, dim)[rank], key)
+                n_ok += 1
+            for shape, g, s_ in a2a_cases:
+                key = f"pa2a{pas}_{shape}_{g}_{s_}_{dtype}"
+                xs = inputs_for(key, shape, dtype, world)
+                nb = int(np.prod(shape)) * es
+                buf = rt.alloc(nb)
+                got = reshard.all_to_all_start(to_dev(xs[rank], dtype), g, s_, world, rank, group,
+                                               _buf=(buf.offset, nb), _push=1)
+                check_equal(got, O.all_to_all(xs, g, s_)[rank], key)
+                n_ok += 1
+        for dtype in ("float32", "bfloat16", "int32", "float64"):
+            es = torch.empty((), dtype=TORCH_DT[dtype]).element_size()
+            ops_ = ("sum", "max") + (() if dtype.startswith("int") else ("avg",))
+            for op in ops_:
+                for shape, dim in red_cases:
+                    key = f"prs{pas}_{shape}_{dim}_{dtype}_{op}"
+                    xs = inputs_for(key, shape, dtype, world)
+                    if op == "avg":
+                        xs = [x * world for x in xs]
+                    nb = int(np.prod(shape)) * es
+                    buf = rt.alloc(nb)
+                    got = reshard.reduce_scatter_start(to_dev(xs[rank], dtype), op, dim, group,
+                                                       _buf=(buf.offset, nb), _push=1)
+                    check_equal(got, O.reduce_scatter(xs, op, dim)[rank], key)
+                    n_ok += 1
+                for shape in ar_cases:
+                    key = f"par{pas}_{shape}_{dtype}_{op}"
+                    xs = inputs_for(key, shape, dtype, world)
+                    if op == "avg":
+                        xs = [x * world for x in xs]
+                    numel = int(np.prod(shape)) if shape else 1
+                    rb, ob = reshard.all_reduce_push_sizes(numel * es, numel, es, world, oneshot)
+                    recv, outb = rt.alloc(rb), rt.alloc(ob)
+                    got = reshard.all_reduce_start(to_dev(xs[rank], dtype), op, group,
+                                                   _buf=(recv.offset, rb, outb.offset), _push=1)
+                    check_equal(got, O.all_reduce(xs, op)[rank], key)
+                    n_ok += 1
+        # fused scale + cast
+        xs = inputs_for(f"prs_cast{pas}", (8 * world, 64), "bfloat16", world)
+        nb = 8 * world * 64 * 2
+        buf = rt.alloc(nb)
+        got = reshard.reduce_scatter_start(to_dev(xs[rank], "bfloat16"), "sum", 0, group, _scale=0.5,
+                                           _out_dtype=torch.float32, _buf=(buf.offset, nb), _push=1)
+        check_equal(got, O.reduce_scatter([x.astype(np.float32) for x in xs], "sum", 0)[rank] * 0.5,
+                    "push rs_cast")
+        n_ok += 1
+        # the buffers are reused by the next pass: the barrier a compiled step ends with
+        torch.cuda.synchronize()
+        reshard.epoch_barrier(x0, group)
+        rt.reset(mark)
+    rt.set_option("ll_max_bytes", ll_saved)
+    # CUDA-graph replay of a push sequence with changing inputs
+    mark = rt.mark()
+    xin = torch.zeros(64 * world, 256, device="cuda")
+    nb = xin.numel() * 4
+    b1, b2, b3, b4 = rt.alloc(nb * world), rt.alloc(nb), rt.alloc(nb * world), rt.alloc(nb)
+
+    def seq():
+        a = reshard.all_gather_start(xin, 0, group, _buf=(b1.offset, nb * world), _push=1)
+        r_ = reshard.reduce_scatter_start(xin, "sum", 0, group, _buf=(b2.offset, nb), _push=1)
+        ar = reshard.all_reduce_start(xin, "sum", group, _buf=(b3.offset, nb * world, b4.offset), _push=1)
+        reshard.epoch_barrier(xin, group)
+        return a, r_, ar
+
+    for _ in range(2):
+        seq()
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        outs = seq()
+    for it in range(4):
+        xs = inputs_for(f"pgraph{it}", (64 * world, 256), "float32", world)
+        xin.copy_(to_dev(xs[rank], "float32"))
+        graph.replay()
+        torch.cuda.synchronize()
+        check_equal(outs[0], O.all_gather(xs, 0)[rank], f"push graph ag {it}")
+        check_equal(outs[1], O.reduce_scatter(xs, "sum", 0)[rank], f"push graph rs {it}")
+        check_equal(outs[2], O.all_reduce(xs, "sum")[rank], f"push graph ar {it}")
+        n_ok += 3
+    reshard.epoch_barrier(x0, group)
+    rt.reset(mark)
+    rt.health()
+    return n_ok
+
+
 def run_p2p(rank, world, group):
     """Partition P2P redistribution vs the oracle's restatement of sharding.py:336-474."""
     n_ok = 0
@@ -784,19 +902,38 @@ def main():
     n += run_fused(rank, world, group)
     n += run_epoch(rank, world, group)
     n += run_prefetch(rank, world, group)
+    n += run_push_cases(rank, world, group)
     n += run_auto_bundle(rank, world)
     n += run_train_parity(rank, world)
     if os.environ.get("EDB_TEST_EXPERIMENTAL") == "1":
         n += run_lane(rank, world, group)
-        if world in (2, 4, 8):
-            # SURVEY.md config 1 with the reference solver's plans, on real GPUs (fp32)
-            from tests.test_auto_bundle_cpu import run_c1_bundle
-            for tag in [str(world)] + (["2x2"] if world == 4 else []):
-                ok, msg, hist = run_c1_bundle(rank, world, reshard, True, "cuda", tag=tag)
-                assert ok, f"config-1 bundle mesh {tag} on GPUs: {msg}"
-                if rank == 0:
-                    print(f"AUTO_BUNDLE_C1_OK mesh={tag} {hist}", flush=True)
-                n += 1
+    if world in (2, 4, 8) and os.environ.get("EDB_SKIP_C1") != "1":
+        # SURVEY.md config 1 (the reference's examples/torch/gpt_train.py model, fp32) in AUTO-SPMD
+        # mode with the plans the reference's solver produced, on real GPUs: outputs, every parameter
+        # and every momentum buffer vs vanilla (rtol 1e-4 / atol 1e-5) — with the product's lowering
+        # (optimizer on shards, parameter gathers as prefetches, push collectives) and, for the 1-D
+        # mesh, also with the reference's communication structure (EDB_LOCALIZE_OPT=0 etc.)
+        from tests.test_auto_bundle_cpu import run_c1_bundle
+        variants = [(str(world), {})]
+        variants.append((str(world), {"EDB_LOCALIZE_OPT": "0", "EDB_AG_PREFETCH": "0",
+                                      "EDB_PUSH_COLL": "0"}))
+        if world == 4:
+            variants.append(("2x2", {}))
+        for tag, env in variants:
+            saved = {k: os.environ.get(k) for k in env}
+            os.environ.update(env)
+            try:
+                ok, msg, hist = run_c1_bundle(rank, world, reshard, True, "cuda", steps=3, tag=tag)
+            finally:
+                for k, v in saved.items():
+                    if v is None:
+                        os.environ.pop(k, None)
+                    else:
+                        os.environ[k] = v
+            assert ok, f"config-1 bundle mesh {tag} on GPUs ({env}): {msg}"
+            if rank == 0:
+                print(f"AUTO_BUNDLE_C1_OK mesh={tag} env={env} {hist}", flush=True)
+            n += 1
     if world >= 4 and world % 2 == 0:
         # 2-D mesh: groups along each mesh dim (ranks in mesh-coordinate order)
         mesh = np.arange(world).reshape(2, world // 2)
