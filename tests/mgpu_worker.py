@@ -876,9 +876,129 @@ def bench(rank, world, group):
     return res
 
 
+def _ref_wrappers(world, rank, group_pg=None):
+    """The reference's own communication wrappers restated over NCCL (easydist/torch/passes/
+    sharding.py:94-163): all-gather along dim 0 + chunk/cat for other dims, pre-permute copy +
+    reduce_scatter_tensor, all-to-all as all-gather + local chunk (its TODO), blocking each."""
+    def ag(x, dim):
+        x = x.contiguous()
+        out = torch.empty((x.shape[0] * world,) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
+        dist.all_gather_into_tensor(out, x)
+        if dim != 0:
+            out = torch.cat(torch.chunk(out, world, dim=0), dim=dim)
+        return out
+
+    def rs(x, dim):
+        if dim != 0:
+            x = torch.cat(torch.chunk(x, world, dim=dim))
+        out = torch.empty((x.shape[0] // world,) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
+        dist.reduce_scatter_tensor(out, x.contiguous())
+        return out
+
+    def ar(x):
+        y = x.clone()
+        dist.all_reduce(y)
+        return y
+
+    def a2a(x, g, s_):
+        return torch.chunk(ag(x, g), world, s_)[rank].contiguous()
+
+    return ag, rs, ar, a2a
+
+
+def bench2(rank, world, group, sizes=None, dtypes=("bfloat16", "float32")):
+    """Reshard microbench, BASELINE.json config 5 / SURVEY.md §8(d): all-gather, reduce-scatter(sum),
+    all-reduce, all-to-all; total bytes 1 KB ... 1 GB (x4); bf16 and fp32; dims {0, last}; three
+    arms on the same GPUs — this library (push protocol with static buffers + an epoch barrier per
+    replayed batch of 10 ops, as in a compiled step), raw NCCL, and the reference's wrappers over
+    NCCL.  Bus bandwidth in the nccl-tests convention; CUDA-graph replay timing, max over ranks."""
+    rt = runtime.get_runtime()
+    timeit = _graph_timer(world)
+    r_ag, r_rs, r_ar, r_a2a = _ref_wrappers(world, rank)
+    sizes = sizes or [1 << k for k in range(10, 31, 2)]
+    oneshot = rt.get_option("allreduce_oneshot_bytes")
+    f = (world - 1) / world
+    for dtype in dtypes:
+        tdt = TORCH_DT[dtype]
+        es = torch.empty((), dtype=tdt).element_size()
+        for dim_kind in ("0", "last"):
+            for nbytes in sizes:
+                if nbytes * (world + 3) > rt.heap_bytes // 2:
+                    break
+                cols = 1024 if nbytes // es >= 1024 * world * world else world
+                rows = nbytes // es // cols
+                if rows < world or rows % world:
+                    rows = max(world, rows // world * world)
+                full_shape = (rows, cols)
+                numel = rows * cols
+                nb = numel * es
+                dim = 0 if dim_kind == "0" else 1
+                if full_shape[dim] % world:
+                    continue
+                shard_shape = list(full_shape)
+                shard_shape[dim] //= world
+                mark = rt.mark()
+                shard = torch.randn(shard_shape, device="cuda").to(tdt)
+                full = torch.randn(full_shape, device="cuda").to(tdt)
+                # static buffers may only be reused after a group barrier.  Up to 16 MiB ten buffer
+                # sets rotate and ONE barrier follows every tenth call (a compiled step has two
+                # barriers for hundreds of edges); above that a single set + a barrier per call
+                # (a few us against milliseconds)
+                K = 10 if nb <= (16 << 20) else 1
+                rb, ob = reshard.all_reduce_push_sizes(nb, numel, es, world, oneshot)
+                sets = [(rt.alloc(nb), rt.alloc(nb), rt.alloc(rb), rt.alloc(ob), rt.alloc(nb))
+                        for _ in range(K)]
+                row = {"dtype": dtype, "dim": dim_kind, "bytes": nb}
+
+                def edb(fn):
+                    cnt = [0]
+
+                    def run():
+                        i = cnt[0] % K
+                        cnt[0] += 1
+                        fn(sets[i])
+                        if i == K - 1:
+                            reshard.epoch_barrier(shard, group)
+                    return run
+                t = timeit(edb(lambda b_: reshard.all_gather_start(shard, dim, group, _buf=(b_[0].offset, nb), _push=1)))
+                row["ag_edb_us"], row["ag_edb_GBs"] = t * 1e3, nb * f / t / 1e6
+                t = timeit(lambda: dist.all_gather_into_tensor(torch.empty(numel, dtype=tdt, device="cuda"), shard.view(-1)))
+                row["ag_nccl_us"] = t * 1e3
+                t = timeit(lambda: r_ag(shard, dim))
+                row["ag_ref_us"] = t * 1e3
+                t = timeit(edb(lambda b_: reshard.reduce_scatter_start(full, "sum", dim, group, _buf=(b_[1].offset, nb), _push=1)))
+                row["rs_edb_us"], row["rs_edb_GBs"] = t * 1e3, nb * f / t / 1e6
+                t = timeit(lambda: dist.reduce_scatter_tensor(torch.empty(numel // world, dtype=tdt, device="cuda"), full.view(-1)))
+                row["rs_nccl_us"] = t * 1e3
+                t = timeit(lambda: r_rs(full, dim))
+                row["rs_ref_us"] = t * 1e3
+                if dim_kind == "0":
+                    t = timeit(edb(lambda b_: reshard.all_reduce_start(full, "sum", group, _buf=(b_[2].offset, rb, b_[3].offset), _push=1)))
+                    row["ar_edb_us"], row["ar_edb_GBs"] = t * 1e3, 2 * nb * f / t / 1e6
+                    t = timeit(lambda: r_ar(full))
+                    row["ar_nccl_us"] = t * 1e3
+                other = 1 - dim
+                if shard_shape[other] % world == 0:
+                    t = timeit(edb(lambda b_: reshard.all_to_all_start(shard, dim, other, world, rank, group, _buf=(b_[4].offset, nb // world), _push=1)))
+                    row["a2a_edb_us"], row["a2a_edb_GBs"] = t * 1e3, nb / world * f / t / 1e6
+                    t = timeit(lambda: r_a2a(shard, dim, other))
+                    row["a2a_ref_us"] = t * 1e3
+                torch.cuda.synchronize()
+                reshard.epoch_barrier(shard, group)
+                rt.reset(mark)
+                if rank == 0:
+                    print("BENCH2 " + " ".join(f"{k}={v:.1f}" if isinstance(v, float) else f"{k}={v}"
+                                               for k, v in row.items()), flush=True)
+    # the barrier itself (its cost is inside every *_edb_us above)
+    t = timeit(lambda: reshard.epoch_barrier(shard, group))
+    if rank == 0:
+        print(f"BENCH2 epoch_barrier_us={t * 1e3:.2f}", flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--bench", action="store_true")
+    ap.add_argument("--bench2", action="store_true", help="only the reshard microbench (config 5)")
     ap.add_argument("--bench-fused", action="store_true", help="only the fused-kernel microbench")
     ap.add_argument("--heap-gb", type=float, default=8.0)
     ap.add_argument("--ll-bytes", type=int, default=-1,
@@ -894,6 +1014,11 @@ def main():
     if args.ll_bytes >= 0:
         rt.set_option("ll_max_bytes", args.ll_bytes)
     group = list(range(world))
+    if args.bench2:
+        bench2(rank, world, group)
+        dist.barrier()
+        dist.destroy_process_group()
+        return
     n = run_cases(rank, world, group)
     n += run_cases(rank, world, group, tag="b")  # second pass: epochs keep counting
     n += run_p2p(rank, world, group)
