@@ -1054,6 +1054,11 @@ int edb_all_gather_push(int gid, uint64_t dst_off, const void* src, const int64_
   if (total == 0) return EDB_OK;
   rc = check_symm(dst_off, total, "edb_all_gather_push");
   if (rc) return rc;
+  {
+    const int ll = ll_try(gid, /*LL_ALL_GATHER*/ 1, r.heap + dst_off, src, outer * rowb, outer, rowb, 0,
+                          0, 1.0f, (cudaStream_t)stream);
+    if (ll >= 0) return ll;
+  }
   const int64_t ext[2] = {outer, rowb};
   const int64_t s_src[2] = {rowb, 1}, s_out[2] = {rowb * n, 1};
   int nb = 0;
@@ -1217,7 +1222,10 @@ int edb_all_reduce_push(int gid, uint64_t out_off, uint64_t recv_off, const void
     if (ll >= 0) return ll;
   }
   const int64_t per = 16 / (int64_t)es * n;
-  const bool two_shot = total > r.allreduce_oneshot_bytes && numel % per == 0;
+  // one-shot moves (n-1) x the tensor per rank, two-shot 2(n-1)/n x in two launches: with two
+  // members the volumes are equal, so the single launch wins up to much larger tensors
+  const int64_t thr = r.allreduce_oneshot_bytes * (n == 2 ? 8 : 1);
+  const bool two_shot = total > thr && numel % per == 0;
   if (!two_shot)  // everybody receives everybody's tensor (receive buffer: n * total bytes)
     return push_reduce_impl(gid, out, recv_off, src, 1, total, false, dtype, redop, scale, dtype,
                             "edb_all_reduce_push", (cudaStream_t)stream);

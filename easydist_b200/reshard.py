@@ -139,7 +139,7 @@ def _buffers(rt, _buf, sizes):
 
 def all_reduce_push_sizes(nbytes, numel, elem_size, n, oneshot_bytes):
     """(receive bytes, result bytes) of edb_all_reduce_push — same rule as the C side."""
-    two_shot = nbytes > oneshot_bytes and numel % (16 // elem_size * n) == 0
+    two_shot = nbytes > oneshot_bytes * (8 if n == 2 else 1) and numel % (16 // elem_size * n) == 0
     return (nbytes if two_shot else n * nbytes), nbytes
 
 
