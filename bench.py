@@ -32,7 +32,10 @@ def parse_args():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--impl", default="edb", choices=["edb", "reference"])
+    ap.add_argument("--impl", default="edb", choices=["edb", "reference", "torch-nccl"],
+                    help="edb: this backend; reference: the reference's CPU path (oracle port); "
+                         "torch-nccl: stock eager PyTorch + DDP/NCCL + cuBLAS on the same GPUs (what "
+                         "the reference's lowering runs on: SURVEY.md 8(d) 'the real competitor')")
     ap.add_argument("--model", default="gpt2-medium")
     ap.add_argument("--mode", default="zero3", choices=["ddp", "zero2", "zero3"])
     ap.add_argument("--batch-per-gpu", type=int, default=8)
@@ -369,8 +372,16 @@ def run_edb(args):
     import dataclasses
     rt = runtime.init(rank, world, local, heap_bytes=int(args.heap_gb * (1 << 30)))
     set_device_mesh(list(range(world)), ["dp"], rank=rank)
-    cfg = dataclasses.replace(GPT2_CONFIGS[args.model], attn=args.attn,
-                              block_size=max(args.seq, GPT2_CONFIGS[args.model].block_size))
+    if args.model.startswith("llama"):
+        # BASELINE.json config 4: Llama-2 (RMSNorm / rotary / SwiGLU, untied head); "-lN" = N layers
+        from easydist_b200.workloads import LLAMA_CONFIGS, Llama
+        base, _, nl = args.model.partition("-l")
+        cfg = dataclasses.replace(LLAMA_CONFIGS["llama2-7b"], block_size=max(args.seq, 2048),
+                                  **({"n_layer": int(nl)} if nl else {}))
+        GPT2 = Llama
+    else:
+        cfg = dataclasses.replace(GPT2_CONFIGS[args.model], attn=args.attn,
+                                  block_size=max(args.seq, GPT2_CONFIGS[args.model].block_size))
     torch.manual_seed(0)
     model = GPT2(cfg).to(device="cuda", dtype=torch.bfloat16)
     opt = torch.optim.SGD(model.parameters(), lr=1e-3, momentum=0.9, foreach=True)
@@ -461,7 +472,11 @@ def run_edb(args):
     roof = gemm_roofline(torch, gemm, calls, peaks, sustained=False, fused_calls=fused_calls,
                          rank=rank, pf_map=pf_map)
     barrier()
-    step_flops = train_flops_per_step(cfg, B, S)
+    if args.model.startswith("llama"):
+        p_mm = sum(p.numel() for n_, p in model.named_parameters() if p.dim() == 2 and "tok" not in n_)
+        step_flops = 6 * p_mm * B * S + 12 * cfg.n_layer * cfg.n_embd * S * B * S
+    else:
+        step_flops = train_flops_per_step(cfg, B, S)
     line = {
         "metric": "train_step_throughput", "value": value, "unit": "samples/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_per_step,
@@ -499,9 +514,72 @@ def run_edb(args):
         raise SystemExit("parity leg failed: " + json.dumps(parity))
 
 
+def run_torch_nccl(args):
+    """GPU baseline on the same box: the same model / batches / optimizer in stock eager PyTorch
+    (bf16, cuBLAS GEMMs, cuDNN attention, ATen elementwise) with DistributedDataParallel over NCCL
+    for N > 1 — none of this repository's kernels, graph passes or runtime."""
+    import dataclasses
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from easydist_b200.workloads import GPT2, GPT2_CONFIGS, synthetic_tokens
+    cfg = dataclasses.replace(GPT2_CONFIGS[args.model], attn=args.attn,
+                              block_size=max(args.seq, GPT2_CONFIGS[args.model].block_size))
+    torch.manual_seed(0)
+    model = GPT2(cfg).to(device="cuda", dtype=torch.bfloat16)
+    net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local]) if world > 1 else model
+    opt = torch.optim.SGD(model.parameters(), lr=1e-3, momentum=0.9, foreach=True)
+    B, S = args.batch_per_gpu, args.seq
+    dev = [tuple(t.cuda() for t in synthetic_tokens(cfg, B, S, seed=1000 * b + rank)) for b in range(4)]
+
+    def step(i):
+        t, y = dev[i % 4]
+        loss = net(t, y)
+        loss.backward()
+        opt.step()
+        opt.zero_grad(True)
+        return loss
+
+    for i in range(max(3, args.warmup)):
+        step(i)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        loss = step(i)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        value = B * world * args.steps / (ms.item() / 1e3)
+        cfgd = workload_config(args, world)
+        cfgd["parallelism"] = f"DistributedDataParallel dp{world}" if world > 1 else "single GPU"
+        cfgd["cuda_graph"] = False
+        print(json.dumps({"impl": "torch-nccl", "metric": "train_step_throughput", "value": value,
+                          "unit": "samples/s", "n_gpus": world, "steps": args.steps,
+                          "warmup": max(3, args.warmup), "ms_per_step": ms.item() / args.steps,
+                          "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                          "dtype": "bf16", "data": "synthetic", "config": cfgd,
+                          "loss": float(loss)}), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     args = parse_args()
-    if args.impl == "reference":
+    if args.impl == "torch-nccl":
+        run_torch_nccl(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_edb(args)
