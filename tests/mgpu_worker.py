@@ -999,6 +999,8 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--bench", action="store_true")
     ap.add_argument("--bench2", action="store_true", help="only the reshard microbench (config 5)")
+    ap.add_argument("--bench2-quick", action="store_true",
+                    help="bf16 only, 1 KiB ... 256 MiB (x16 steps): the affordable form at 8 GPUs")
     ap.add_argument("--bench-fused", action="store_true", help="only the fused-kernel microbench")
     ap.add_argument("--heap-gb", type=float, default=8.0)
     ap.add_argument("--ll-bytes", type=int, default=-1,
@@ -1014,8 +1016,12 @@ def main():
     if args.ll_bytes >= 0:
         rt.set_option("ll_max_bytes", args.ll_bytes)
     group = list(range(world))
-    if args.bench2:
-        bench2(rank, world, group)
+    if args.bench2 or args.bench2_quick:
+        if args.bench2_quick:
+            bench2(rank, world, group, sizes=[1 << k for k in range(10, 29, 4)] + [1 << 28],
+                   dtypes=("bfloat16",))
+        else:
+            bench2(rank, world, group)
         dist.barrier()
         dist.destroy_process_group()
         return
