@@ -308,13 +308,20 @@ __device__ __forceinline__ float gelu_tanh_grad(float x) {
   const float kKappa = 0.044715f;
   const float x_sq = x * x;
   const float inner = kBeta * (x + kKappa * x_sq * x);
-  // tanh.approx (one MUFU op, |rel err| ~ 2^-11): 16.7 M evaluations per MLP dgrad GEMM sit on the
-  // epilogue warps, tanhf would take longer than the main loop; the result is rounded to bf16 (2^-8)
-  float t;
-  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(inner));
+  // tanh and sech^2 from ONE exponential: e = exp(-2|u|) (ex2.approx, rel. error 2^-22),
+  // tanh = sign(u)(1-e)/(1+e), 1 - tanh^2 = 4e/(1+e)^2.  (tanh.approx.f32 is one MUFU op cheaper but
+  // its 2^-11 error is absolute near saturation: 1 - t*t then loses everything for |x| > 3 and the
+  // gradient of a saturated unit came out as ~3 % of dy instead of ~0.  tanhf costs more than the
+  // main loop: 16.7 M evaluations per MLP dgrad GEMM sit on the four epilogue warps.)
+  const float au = fabsf(inner);
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-2.885390081777927f * au));  // 2 / ln 2
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+  const float t = copysignf((1.0f - e) * r, inner);
+  const float tanh_d = 4.0f * e * r * r;
   const float left = 0.5f * x, right = 1.0f + t;
   const float left_d = 0.5f * right;
-  const float tanh_d = 1.0f - t * t;
   const float inner_d = kBeta * (1.0f + 3.0f * kKappa * x_sq);
   return left_d + left * tanh_d * inner_d;
 }

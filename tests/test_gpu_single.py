@@ -391,7 +391,11 @@ def test_gemm_epilogue_residual_add(rt, with_bias):
         # <= 1 ulp for the single rounding, + the accumulator's own error (relative to the product)
         assert float(((out.float() - ref).abs() / ulp).max()) <= 1.5, (M, N, K)
         unfused = (gemm.addmm(bias, a, b) if with_bias else gemm.mm(a, b)) + res
-        assert float(((out.float() - unfused.float()).abs() / ulp).max()) <= 2.0
+        # the unfused path rounds (product + bias) to bf16 before the add: its error scales with that
+        # intermediate's magnitude, not with the (possibly cancelled) result's
+        pb = prod + (bias.float() if with_bias else 0.0)
+        ulp2 = torch.exp2(torch.floor(torch.log2(torch.maximum(mag, pb.abs()))) - 7)
+        assert float(((out.float() - unfused.float()).abs() / ulp2).max()) <= 2.0
 
 
 def test_gemm_epilogue_gelu_backward(rt):
@@ -416,8 +420,13 @@ def test_gemm_epilogue_gelu_backward(rt):
         scale = torch.exp2(torch.floor(torch.log2(mag)) - 7)
         assert float(((out.float() - ref).abs() / scale).max()) <= 2.5, (M, N, K)
         aten = torch.ops.aten.gelu_backward(gemm.mm(a, b), pre, approximate="tanh")
-        # vs ATen's kernel on this library's GEMM output: same rounding points; tanh.approx (2^-11)
-        assert float(((out.float() - aten.float()).abs() / scale).max()) <= 1.5, (M, N, K)
+        # vs ATen's kernel on this library's GEMM output: same rounding points (ex2/rcp.approx vs tanhf)
+        assert float(((out.float() - aten.float()).abs() / scale).max()) <= 1.0, (M, N, K)
+        # saturated units (|pre| > 5): the gradient must vanish like ATen's, not like 1 - t*t of an
+        # approximate tanh
+        sat = pre.float().abs() > 5
+        if bool(sat.any()):
+            assert float((out.float() - aten.float()).abs()[sat].max()) <= 1e-3
 
 
 def test_layer_norm_backward_with_fused_accumulation(rt):

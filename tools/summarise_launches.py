@@ -1,7 +1,9 @@
 """Per-kernel totals of an `ncu --metrics gpu__time_duration.sum --csv` launch list.
 
-usage: python tools/summarise_launches.py gpurun_out/final_launches.csv [last_n_launches] > profiles/...csv
-With last_n_launches the summary covers only the tail of the list (= the final, timed step).
+usage: python tools/summarise_launches.py gpurun_out/final_launches.csv [last_n_launches | step:K] > profiles/...csv
+With last_n_launches the summary covers only the tail of the list; with `step:K` (e.g. step:-3) it
+covers exactly one train step: the launches between the K-th and (K+1)-th optimizer kernel
+(`k_sgd_momentum`) of the run — bench.py's tail is the roofline replay, not a step.
 """
 import csv
 import sys
@@ -10,13 +12,18 @@ from collections import defaultdict
 
 def main():
     path = sys.argv[1]
-    last = int(sys.argv[2]) if len(sys.argv) > 2 else 0
+    arg = sys.argv[2] if len(sys.argv) > 2 else "0"
+    step = int(arg.split(":")[1]) if arg.startswith("step:") else None
+    last = 0 if step is not None else int(arg)
     rows = []
     with open(path, newline="") as f:
         lines = [l for l in f if l.startswith('"')]
     for r in csv.DictReader(lines):
         if r.get("Metric Name") == "gpu__time_duration.sum":
             rows.append((r["Kernel Name"], float(r["Metric Value"].replace(",", "")) / 1e3))
+    if step is not None:
+        marks = [i for i, (k, _) in enumerate(rows) if "k_sgd_momentum" in k]
+        rows = rows[marks[step] + 1:marks[step + 1] + 1]
     if last:
         rows = rows[-last:]
     tot = defaultdict(float)
