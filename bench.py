@@ -47,6 +47,9 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-seqs", type=int, default=2)
     ap.add_argument("--heap-gb", type=float, default=12.0)
+    ap.add_argument("--no-roofline", action="store_true",
+                    help="skip the GEMM launch-list replay (multi-billion-parameter models: the replay "
+                         "allocates fresh operands for every launch)")
     ap.add_argument("--no-parity", action="store_true",
                     help="skip the pre-timing parity leg (compiled N-GPU steps vs vanilla fp32)")
     return ap.parse_args()
@@ -383,7 +386,12 @@ def run_edb(args):
         cfg = dataclasses.replace(GPT2_CONFIGS[args.model], attn=args.attn,
                                   block_size=max(args.seq, GPT2_CONFIGS[args.model].block_size))
     torch.manual_seed(0)
-    model = GPT2(cfg).to(device="cuda", dtype=torch.bfloat16)
+    if args.model.startswith("llama"):
+        with torch.device("cuda"):  # 7 B fp32 parameters per rank must not be built in host memory
+            model = GPT2(cfg)
+        model = model.to(torch.bfloat16)
+    else:
+        model = GPT2(cfg).to(device="cuda", dtype=torch.bfloat16)
     opt = torch.optim.SGD(model.parameters(), lr=1e-3, momentum=0.9, foreach=True)
     B, S = args.batch_per_gpu, args.seq
     n_batches = 4
@@ -392,7 +400,7 @@ def run_edb(args):
     dev = [(t.cuda(), y.cuda()) for t, y in host]
     step_fn = easydist_compile(gpt2_train_step, parallel_mode=args.mode, tracing_mode="fake",
                                cuda_graph=not args.no_cuda_graph, fuse=not args.no_fuse)
-    state0 = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    state0 = None if args.no_parity else {k: v.detach().clone() for k, v in model.state_dict().items()}
     # parity batches: one per (step, rank); every rank can rebuild all of them for the reference
     n_par = 3
     par_host = [[synthetic_tokens(cfg, B, S, seed=7000 + 1000 * b + r) for r in range(world)]
@@ -469,8 +477,8 @@ def run_edb(args):
     # every rank replays (the fused kernels talk to the peers); rank 0 reports
     barrier()
     pf_map = step_pf
-    roof = gemm_roofline(torch, gemm, calls, peaks, sustained=False, fused_calls=fused_calls,
-                         rank=rank, pf_map=pf_map)
+    roof = None if args.no_roofline else gemm_roofline(torch, gemm, calls, peaks, sustained=False,
+                                                       fused_calls=fused_calls, rank=rank, pf_map=pf_map)
     barrier()
     if args.model.startswith("llama"):
         p_mm = sum(p.numel() for n_, p in model.named_parameters() if p.dim() == 2 and "tok" not in n_)
