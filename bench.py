@@ -341,7 +341,7 @@ def parity_leg(torch, dist, args, cfg, GPT2, step_fn, model, opt, state0, par_ho
             n_resh += W.run_p2p(rank, world, group)
             n_resh += W.run_epoch(rank, world, group)
             n_resh += W.run_prefetch(rank, world, group)
-            n_resh += W.run_push_cases(rank, world, group)
+            n_resh += W.run_push_cases(rank, world, group, passes=2, big=False)
             res["reshard_checks_bit_exact"] = n_resh
             res["checks"] += n_resh
         except AssertionError as e:

@@ -257,10 +257,14 @@ def legalize_views(gm, mesh, shard_env):
     hard part 1; its meta propagation only works under torch 2.11 with the reshape retry of
     oracle/refcompat).  Dry-run the lowered graph on fake LOCAL placeholders and retarget exactly
     the view nodes that fail to `aten.reshape` (same values, copies when it must).  Returns the
-    number of nodes changed; never raises (an op the dry run cannot execute just ends it)."""
+    number of nodes changed.  A dry run that cannot complete is an ERROR (views behind the failing
+    node would stay unchecked and an illegal one would only surface at run time, on one rank);
+    `EDB_LEGALIZE_BEST_EFFORT=1` restores the old log-and-continue behaviour."""
+    import os
     from torch._subclasses.fake_tensor import FakeTensorMode
     changed = 0
     env = {}
+    cur = None
     try:
         with FakeTensorMode(allow_non_fake_inputs=True):
             for node in gm.graph.nodes:
@@ -276,6 +280,7 @@ def legalize_views(gm, mesh, shard_env):
                     else:
                         env[node] = val
                 elif node.op == "call_function":
+                    cur = node
                     args, kwargs = pytree.tree_map_only(Node, lambda n: env[n],
                                                         (node.args, node.kwargs))
                     try:
@@ -290,9 +295,15 @@ def legalize_views(gm, mesh, shard_env):
                     break
                 else:
                     return changed
-    except Exception as e:  # noqa: BLE001 — best effort: the graph itself is left as lowered
-        import logging
-        logging.getLogger(__name__).warning("legalize_views stopped early: %r", e)
+    except Exception as e:  # noqa: BLE001
+        if os.environ.get("EDB_LEGALIZE_BEST_EFFORT", "0") == "1":
+            import logging
+            logging.getLogger(__name__).warning("legalize_views stopped early: %r", e)
+            return changed
+        raise RuntimeError(
+            f"legalize_views: the dry run of the lowered graph failed at node "
+            f"{cur.name if cur is not None else '?'} ({getattr(cur, 'target', None)}): {e!r}; views "
+            "behind it are unchecked (EDB_LEGALIZE_BEST_EFFORT=1 to continue anyway)") from e
     return changed
 
 

@@ -116,6 +116,14 @@ class Runtime:
         import torch.distributed as dist
         if dist.is_available() and dist.is_initialized():
             torch.cuda.synchronize(self.device)
+            # the symmetric heap is only symmetric if every rank made the same allocations: compare
+            # the bump pointers (uneven shards / a rank-dependent branch would otherwise make peers
+            # read and write each other's buffers at the wrong offsets, silently)
+            marks = [None] * self.world
+            dist.all_gather_object(marks, (self.rank, self.mark()), group=getattr(self, "_pg", None))
+            if len({m for _, m in marks}) != 1:
+                raise _lib.EdbError(_lib.EDB_E_STATE,
+                                    f"symmetric heap diverged across ranks after compilation: {marks}")
             dist.barrier(group=getattr(self, "_pg", None))
 
     def group(self, ranks, slot=None, lane=0):

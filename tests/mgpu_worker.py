@@ -112,7 +112,7 @@ def run_cases(rank, world, group, tag=""):
     return n_ok
 
 
-def run_push_cases(rank, world, group):
+def run_push_cases(rank, world, group, passes=4, big=True):
     """The push-protocol collectives (edb_*_push: static per-node buffers, one flag per peer, an
     epoch barrier between reuses of a buffer) bit for bit against the oracle: every op, the LL
     threshold switched off for half of the passes so that the push kernels themselves run on the
@@ -130,7 +130,12 @@ def run_push_cases(rank, world, group):
     red_cases = [((2 * world, 3), 0), ((3, 2 * world), 1), ((2, 3, world), 2), ((64 * world, 256), 0),
                  ((16, 8 * world, 32), 1), ((512 * world, 1024), 0)]
     ar_cases = [(5, 3), (), (1024,), (300, 1000), (1 << 20,), (world * 1024 * 512,)]
-    for pas in range(4):
+    if not big:
+        # bench.py's pre-timing battery: the host-side oracle work of the world-scaled shapes
+        # (numpy over `world` ranks' inputs) would take minutes at 8 GPUs
+        ag_cases, a2a_cases = ag_cases[:-1], a2a_cases[:-1]
+        red_cases, ar_cases = red_cases[:-1], ar_cases[:-2] + [(256 * 1024,)]
+    for pas in range(passes):
         rt.set_option("ll_max_bytes", ll_saved if pas % 2 == 0 else 0)
         mark = rt.mark()
         if rank % 2 == pas % 2:
