@@ -471,4 +471,45 @@ def register(reference_api=None, reference_compile_auto=None, **compile_kwargs):
                                            ops=compile_kwargs.get("ops", _default_ops))
 
     reference_compile_auto.sharding_transform = sharding_transform
+
+    # ---- Hook C: the reference's front end, this backend's lowering AND executor ---------------
+    class _PlanCaptured(Exception):
+        pass
+
+    def auto_entry(original_func, parallel_mode, tracing_mode, args, kwargs):
+        """parallel_mode="b200_auto": run the reference's own `_compile_auto` (tracing, sharding
+        annotation, MetaIR, AutoFlow ILP on rank 0, plan broadcast — compile_auto.py:456-546) and
+        stop it exactly where it would lower (`sharding_transform`, :569): the traced graph and the
+        solver's plan are captured and handed to this backend, which lowers them
+        (`lowering.sharding_transform` + the product passes), pre-shards the state locally and
+        returns ITS `EDCompiledFunc` — so the reference's per-step `distribute_tensor` of every input
+        (compile_auto.py:737-745), its op-by-op executor and its NCCL lowering are all out of the
+        loop, while `@easydist_compile` and the solver stay the reference's.  Graphs with
+        `aten.embedding` need the reference's `fix_embedding(recover=True)` post-pass and are not
+        covered."""
+        from easydist.torch.device_mesh import get_device_mesh as ref_mesh
+        from . import graph_io
+        from .device_mesh import set_device_mesh
+        set_device_mesh(ref_mesh("spmd"), rank=torch.distributed.get_rank())
+        captured = {}
+        saved = reference_compile_auto.sharding_transform
+
+        def capture(fx_module, opt_strategy, state_io_map):
+            captured["bundle"] = graph_io.dump_bundle(
+                fx_module, opt_strategy, [(a.name, b.name) for a, b in state_io_map.items()])
+            raise _PlanCaptured()
+
+        reference_compile_auto.sharding_transform = capture
+        try:
+            reference_compile_auto._compile_auto(original_func, tracing_mode, None, "b200_auto", args,
+                                                 kwargs)
+            raise RuntimeError("b200_auto: the reference's _compile_auto returned without lowering")
+        except _PlanCaptured:
+            pass
+        finally:
+            reference_compile_auto.sharding_transform = saved
+        kw = {k: v for k, v in compile_kwargs.items() if k in ("ops", "native", "planner")}
+        return compile_from_bundle(captured["bundle"], args, kwargs, **kw)
+
+    reference_api.register_parallel_method("b200_auto", auto_entry)
     return reference_api

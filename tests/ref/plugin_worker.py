@@ -53,7 +53,7 @@ def main():
     from easydist_b200 import api
     from tests import gloo_ops
     api.register(ops=gloo_ops, native=False)
-    if mode == "auto":
+    if mode in ("auto", "b200_auto"):
         # Hook B: register() also rebinds compile_auto.sharding_transform; the reference's auto
         # path (annotation, solver, executor) then runs on this backend's lowering
         import numpy as np
@@ -71,7 +71,7 @@ def main():
     ok, msgs = True, []
     sl = slice(rank * 4, (rank + 1) * 4)
     for b in batches:
-        if mode == "auto":   # SPMD: every rank passes the global batch and gets the global loss
+        if mode in ("auto", "b200_auto"):   # SPMD: every rank passes the global batch, gets the global loss
             loss = step(b, model, opt).detach().clone()
             want = train_step(b, vmodel, vopt).detach()
         else:
@@ -86,7 +86,7 @@ def main():
     for name, p_ref in vmodel.named_parameters():
         p = cf.named_parameters()[name]
         p = p.to_local() if hasattr(p, "to_local") else p
-        if mode == "auto" and p.shape != p_ref.shape:
+        if mode in ("auto", "b200_auto") and p.shape != p_ref.shape:
             continue  # placement is the solver's choice; outputs / losses are the comparator here
         if p.shape != p_ref.shape:
             parts = [torch.empty_like(p) for _ in range(world)]

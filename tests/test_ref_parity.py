@@ -33,13 +33,16 @@ def test_dropin_lowering_equals_reference_lowering(mesh, nproc, port, planner, m
     assert "same_plan_equal=True" in line, line
 
 
-@pytest.mark.parametrize("mode,port", [("b200_ddp", 29796), ("b200_zero3", 29797), ("auto", 29798)])
+@pytest.mark.parametrize("mode,port", [("b200_ddp", 29796), ("b200_zero3", 29797), ("auto", 29798),
+                                       ("b200_auto", 29799)])
 def test_plugin_hook_through_the_reference_decorator(mode, port):
     """Hook A of INTEGRATION.md: `easydist_b200.api.register()` adds the modes to the reference's
     registry (`register_parallel_method`, api.py:39-50); the REFERENCE's own `easydist_compile`
     decorator and CompiledFuncWrapper then drive this backend's compiled object (`.graph`,
     `.run_with_graph`, state accessors); "auto" = Hook B, the `sharding_transform` name rebound by
-    the same call — tests/ref/plugin_worker.py."""
+    the same call; "b200_auto" = Hook C: the reference's tracing + annotation + ILP produce the plan,
+    this backend lowers AND executes it (its own EDCompiledFunc, no per-step distribute_tensor) —
+    tests/ref/plugin_worker.py."""
     if not os.path.isdir("/root/reference/easydist"):
         pytest.skip("reference not present (GPU box)")
     env = dict(os.environ, OMP_NUM_THREADS="1", EDB_PLUGIN_MODE=mode)
@@ -49,3 +52,6 @@ def test_plugin_hook_through_the_reference_decorator(mode, port):
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=280, cwd=ROOT, env=env)
     line = next((l for l in r.stdout.splitlines() if l.startswith("PLUGIN_PARITY")), "")
     assert r.returncode == 0 and "ok=True" in line, r.stdout[-2000:] + r.stderr[-3000:]
+    if mode.startswith("b200_"):
+        # the object the reference's wrapper drives is THIS backend's executor
+        assert "compiled=easydist_b200.compile.EDCompiledFunc" in line, line
