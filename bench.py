@@ -37,7 +37,10 @@ def parse_args():
                          "torch-nccl: stock eager PyTorch + DDP/NCCL + cuBLAS on the same GPUs (what "
                          "the reference's lowering runs on: SURVEY.md 8(d) 'the real competitor')")
     ap.add_argument("--model", default="gpt2-medium")
-    ap.add_argument("--mode", default="zero3", choices=["ddp", "zero2", "zero3"])
+    ap.add_argument("--mode", default="zero3", choices=["ddp", "zero2", "zero3", "auto"],
+                    help="auto: BASELINE.json config 1 (the reference's GPT example, fp32) in auto-SPMD "
+                         "mode with the plan the reference's solver recorded for this mesh "
+                         "(tools/bench_c1_auto.py; needs 2, 4 or 8 GPUs)")
     ap.add_argument("--batch-per-gpu", type=int, default=8)
     ap.add_argument("--seq", type=int, default=512)
     ap.add_argument("--attn", default="sdpa", choices=["sdpa", "unfused"])
@@ -585,6 +588,11 @@ def run_torch_nccl(args):
 
 def main():
     args = parse_args()
+    if args.mode == "auto" and args.impl == "edb":
+        from tools import bench_c1_auto
+        bench_c1_auto.run(argparse.Namespace(mesh="", steps=args.steps, warmup=max(3, args.warmup),
+                                             no_cuda_graph=args.no_cuda_graph))
+        return
     if args.impl == "torch-nccl":
         run_torch_nccl(args)
     elif args.impl == "reference":

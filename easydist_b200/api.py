@@ -96,6 +96,14 @@ def _finish(gm, params, buffers, named_states, args, kwargs, ops, native, io=Non
         # opt-in: changes the communication structure the reference's lowering would produce
         info["bucketed"] = lowering.bucket_small_comm(gm, ops)
         lowering.propagate_local_meta(gm, flat)
+    experimental = [k for k in ("EDB_OVERLAP", "EDB_RS_LANE", "EDB_GEMM_SIDE", "EDB_DEFER_RS")
+                    if os.environ.get(k, "0") == "1"]
+    if experimental and native:
+        # round-1 advisor finding: kernels whose CTAs wait on other CTAs assume the whole grid is
+        # co-resident, which a second stream breaks; these switches stay opt-in experiments
+        logger.warning("experimental switches %s: kernels on a second stream share the SMs with "
+                       "grids sized for an idle GPU (not co-residency safe); not part of the measured "
+                       "configuration", experimental)
     overlap = os.environ.get("EDB_OVERLAP", "0") == "1" and io is not None and ranks is not None \
         and len(ranks) > 1
     if overlap:

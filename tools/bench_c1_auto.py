@@ -28,7 +28,11 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--no-cuda-graph", action="store_true")
-    args = ap.parse_args()
+    run(ap.parse_args())
+
+
+def run(args):
+    """Also the body of `bench.py --mode auto` (args: mesh, steps, warmup, no_cuda_graph)."""
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     local = int(os.environ.get("LOCAL_RANK", rank))
     torch.cuda.set_device(local)
@@ -80,7 +84,9 @@ def main():
     if rank == 0:
         ms = t.item()
         print(json.dumps({"metric": "train_step_throughput", "value": batch / ms * 1e3, "unit": "samples/s",
-                          "n_gpus": world, "ms_per_step": ms, "dtype": "f32",
+                          "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                          "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
+                          "vs_baseline": None, "data": "synthetic", "dtype": "f32",
                           "config": {"workload": "config 1: GPT depth 4 dim 1024 heads 32, batch "
                                                  f"{batch}x128, auto-SPMD plan of the reference solver",
                                      "mesh": list(mesh_shape), "cuda_graph": not args.no_cuda_graph,
