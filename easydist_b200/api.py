@@ -328,6 +328,30 @@ def compile_from_bundle(bundle_text, args, kwargs, *, ops=_default_ops, native=T
                        native=native, planner=planner, mesh=mesh)
 
 
+LAST_AUTO_SOURCE = [None]  # "solved" | "cache": where the last b200_auto compilation got its plan
+
+
+def _plan_cache_key(args, kwargs, mesh):
+    """Stable across processes (unlike input_signature, which names modules by id): tensor shapes
+    and dtypes, the printed architecture of every module, class + hyper-parameters of every
+    optimizer, scalars, and the mesh shape."""
+    import hashlib
+    leaves, spec = pytree.tree_flatten((args, kwargs))
+    parts = [repr(spec), repr(tuple(mesh.shape))]
+    for x in leaves:
+        if isinstance(x, torch.Tensor):
+            parts.append(f"T{tuple(x.shape)}:{x.dtype}")
+        elif isinstance(x, torch.nn.Module):
+            parts.append(repr(x) + "|" + ",".join(f"{n}{tuple(p.shape)}{p.dtype}"
+                                                  for n, p in x.named_parameters()))
+        elif isinstance(x, torch.optim.Optimizer):
+            parts.append(type(x).__qualname__ + repr([{k: v for k, v in g.items() if k != "params"}
+                                                      for g in x.param_groups]))
+        else:
+            parts.append(repr(x))
+    return hashlib.sha256("|".join(parts).encode("utf-8")).hexdigest()[:32]
+
+
 def input_signature(args, kwargs):
     """Key of a compiled graph: shapes and dtypes of the tensor inputs, repr of everything else
     (scalars; modules and optimizers by identity) — the information the reference's
@@ -498,7 +522,26 @@ def register(reference_api=None, reference_compile_auto=None, **compile_kwargs):
         from easydist.torch.device_mesh import get_device_mesh as ref_mesh
         from . import graph_io
         from .device_mesh import set_device_mesh
-        set_device_mesh(ref_mesh("spmd"), rank=torch.distributed.get_rank())
+        mesh = set_device_mesh(ref_mesh("spmd"), rank=torch.distributed.get_rank())
+        kw = {k: v for k, v in compile_kwargs.items() if k in ("ops", "native", "planner")}
+        # plan cache (the reference caches the solver's output per input signature,
+        # compile_auto.py:97-106,181-184): here the whole captured bundle — traced graph + plan — is
+        # cached, so a hit skips tracing, annotation, the ILP and the RPC plan broadcast.  Rank 0
+        # decides and ships the text, so the cache directory need not be shared.
+        cache_dir = os.environ.get("EDB_PLAN_CACHE_DIR", "")
+        cache_file = None
+        if cache_dir:
+            cache_file = os.path.join(cache_dir, f"b200_auto_{_plan_cache_key(args, kwargs, mesh)}.json.gz")
+            import gzip
+            box = [None]
+            if torch.distributed.get_rank() == 0 and os.path.exists(cache_file):
+                with gzip.open(cache_file, "rt") as f:
+                    box[0] = f.read()
+            if torch.distributed.get_world_size() > 1:
+                torch.distributed.broadcast_object_list(box, src=0)
+            if box[0] is not None:
+                LAST_AUTO_SOURCE[0] = "cache"
+                return compile_from_bundle(box[0], args, kwargs, **kw)
         captured = {}
         saved = reference_compile_auto.sharding_transform
 
@@ -516,7 +559,14 @@ def register(reference_api=None, reference_compile_auto=None, **compile_kwargs):
             pass
         finally:
             reference_compile_auto.sharding_transform = saved
-        kw = {k: v for k, v in compile_kwargs.items() if k in ("ops", "native", "planner")}
+        LAST_AUTO_SOURCE[0] = "solved"
+        if cache_file is not None and torch.distributed.get_rank() == 0:
+            import gzip
+            os.makedirs(cache_dir, exist_ok=True)
+            tmp = cache_file + f".tmp{os.getpid()}"
+            with gzip.open(tmp, "wt") as f:
+                f.write(captured["bundle"])
+            os.replace(tmp, cache_file)
         return compile_from_bundle(captured["bundle"], args, kwargs, **kw)
 
     reference_api.register_parallel_method("b200_auto", auto_entry)

@@ -95,9 +95,39 @@ def main():
         if not torch.allclose(p, p_ref.detach(), rtol=1e-4, atol=1e-5):
             ok = False
             msgs.append(f"param {name} differs by {(p - p_ref).abs().max()}")
+    source = None
+    if mode == "b200_auto" and os.environ.get("EDB_PLAN_CACHE_DIR"):
+        # second compilation of the same step in this job: the plan must come from the cache (no
+        # tracing / annotation / ILP by the reference) and train identically
+        source = [api.LAST_AUTO_SOURCE[0]]
+        import easydist.torch.compile_auto as ref_auto
+        calls = {"n": 0}
+        orig = ref_auto._compile_auto
+
+        def counting(*a, **k):
+            calls["n"] += 1
+            return orig(*a, **k)
+
+        ref_auto._compile_auto = counting
+        model2 = copy.deepcopy(model0)
+        opt2 = torch.optim.SGD(model2.parameters(), lr=0.1, momentum=0.9, foreach=True)
+        step2 = easydist_compile(train_step, mode, "fake", cuda_graph=False)
+        vmodel2 = copy.deepcopy(model0)
+        vopt2 = torch.optim.SGD(vmodel2.parameters(), lr=0.1, momentum=0.9, foreach=True)
+        for b in batches:
+            loss = step2(b, model2, opt2).detach().clone()
+            want = train_step(b, vmodel2, vopt2).detach()
+            if not torch.allclose(loss, want, rtol=1e-4, atol=1e-5):
+                ok = False
+                msgs.append(f"cached plan: loss {loss} vs {want}")
+        source.append(api.LAST_AUTO_SOURCE[0])
+        if calls["n"] != 0 or source != ["solved", "cache"]:
+            ok = False
+            msgs.append(f"plan cache not used: reference compiles={calls['n']} sources={source}")
     if rank == 0:
         print(f"PLUGIN_PARITY ok={ok} mode={mode} wrapper={type(step).__module__}.{type(step).__name__} "
-              f"compiled={type(cf).__module__}.{type(cf).__name__} {msgs}", flush=True)
+              f"compiled={type(cf).__module__}.{type(cf).__name__} plan_source={source} {msgs}",
+              flush=True)
     dist.barrier()
     dist.destroy_process_group()
 

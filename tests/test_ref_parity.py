@@ -46,6 +46,9 @@ def test_plugin_hook_through_the_reference_decorator(mode, port):
     if not os.path.isdir("/root/reference/easydist"):
         pytest.skip("reference not present (GPU box)")
     env = dict(os.environ, OMP_NUM_THREADS="1", EDB_PLUGIN_MODE=mode)
+    if mode == "b200_auto":
+        import tempfile
+        env["EDB_PLAN_CACHE_DIR"] = tempfile.mkdtemp(prefix="edb_plan_cache_")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
            "--master-addr", "127.0.0.1", "--master-port", str(port),
            os.path.join(ROOT, "tests", "ref", "plugin_worker.py")]
@@ -55,3 +58,6 @@ def test_plugin_hook_through_the_reference_decorator(mode, port):
     if mode.startswith("b200_"):
         # the object the reference's wrapper drives is THIS backend's executor
         assert "compiled=easydist_b200.compile.EDCompiledFunc" in line, line
+    if mode == "b200_auto":
+        # ... and a second compilation took graph + plan from the plan cache
+        assert "plan_source=['solved', 'cache']" in line, line
