@@ -48,7 +48,7 @@ def train_step(x, y, model, opt):
     return loss
 
 
-def _worker(rank, world, port, mode, q):
+def _worker(rank, world, port, mode, q, arch="tiny"):
     os.environ["OMP_NUM_THREADS"] = "1"
     torch.set_num_threads(1)
     dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
@@ -57,13 +57,21 @@ def _worker(rank, world, port, mode, q):
     from tests import gloo_ops
     set_device_mesh(list(range(world)), ["dp"], rank=rank)
     torch.manual_seed(0)
-    model, ref = TinyResNet(), TinyResNet()
+    if arch == "resnet50":
+        # the real thing (torchvision's ResNet-50: 53 convolutions, 53 BatchNorms, 161 parameters,
+        # 159 buffers) at CPU-sized inputs
+        import torchvision
+        model, ref = torchvision.models.resnet50(num_classes=10), torchvision.models.resnet50(num_classes=10)
+        res, lr, steps = 32, 0.01, 2
+    else:
+        model, ref = TinyResNet(), TinyResNet()
+        res, lr, steps = 16, 0.1, 3
     ref.load_state_dict(model.state_dict())
-    opt = torch.optim.SGD(model.parameters(), lr=0.1, momentum=0.9, foreach=True)
-    ropt = torch.optim.SGD(ref.parameters(), lr=0.1, momentum=0.9, foreach=True)
+    opt = torch.optim.SGD(model.parameters(), lr=lr, momentum=0.9, foreach=True)
+    ropt = torch.optim.SGD(ref.parameters(), lr=lr, momentum=0.9, foreach=True)
     g = torch.Generator().manual_seed(3)
-    xs = [torch.randn(world * 4, 3, 16, 16, generator=g) for _ in range(3)]
-    ys = [torch.randint(0, 10, (world * 4,), generator=g) for _ in range(3)]
+    xs = [torch.randn(world * 4, 3, res, res, generator=g) for _ in range(steps)]
+    ys = [torch.randint(0, 10, (world * 4,), generator=g) for _ in range(steps)]
     sl = slice(rank * 4, (rank + 1) * 4)
     compiled = api._compile_dp(train_step, mode, "fake", (xs[0][sl], ys[0][sl], model, opt), {},
                                ops=gloo_ops, native=False)
@@ -115,3 +123,23 @@ def test_conv_batchnorm_network_matches_per_rank_eager(mode, port):
         assert hist.get("all_reduce_start", 0) == 11, hist
     else:
         assert hist.get("reduce_scatter_start", 0) + hist.get("all_reduce_start", 0) >= 1, hist
+
+
+def test_torchvision_resnet50_ddp_matches_per_rank_eager():
+    """BASELINE.json config 3's model itself (torchvision ResNet-50) through the ddp mode on gloo,
+    world 2, 32x32 inputs: traced with its 159 BatchNorm buffers as graph state, 161 gradient
+    all-reduces, losses / every parameter / every buffer equal per-rank eager training with averaged
+    gradients (rtol 1e-4, atol 1e-5).  On GPUs its convolutions and BatchNorms stay ATen/cuDNN kernels
+    (no native convolution path: DESIGN.md section 7); what runs natively there is the collectives."""
+    pytest.importorskip("torchvision")
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, 29904, "ddp", q, "resnet50")) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(500)
+    assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
+    ok, msg, hist = q.get(timeout=5)
+    assert ok, msg
+    assert hist.get("all_reduce_start", 0) == 161, hist
