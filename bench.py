@@ -507,6 +507,26 @@ def run_edb(args):
     }
     if parity is not None:
         line["parity"] = parity
+    if world > 1 and not args.no_parity:
+        # the other half of BASELINE.json's metric: reshard bus bandwidth (nccl-tests convention)
+        # against NVLink-5 peak, 64 MiB bf16, push-protocol kernels vs NCCL on the same GPUs
+        # (tests/mgpu_worker.py bench2: CUDA-graph timed, max over ranks; outside the timed region)
+        try:
+            from tests import mgpu_worker as W
+            rows = W.bench2(rank, world, list(range(world)), sizes=[1 << 26], dtypes=("bfloat16",),
+                            quiet=True)
+            r0 = next(r for r in rows if r["dim"] == "0")
+            nb, f = r0["bytes"], (world - 1) / world
+            line["reshard_bus"] = {
+                "bytes": nb, "dtype": "bf16", "unit": "GB/s", "nvlink_peak": 900.0,
+                "all_gather": r0["ag_edb_GBs"], "reduce_scatter": r0["rs_edb_GBs"],
+                "all_reduce": r0.get("ar_edb_GBs"), "all_to_all": r0.get("a2a_edb_GBs"),
+                "nccl_all_gather": nb * f / r0["ag_nccl_us"] / 1e3,
+                "nccl_reduce_scatter": nb * f / r0["rs_nccl_us"] / 1e3,
+                "nccl_all_reduce": 2 * nb * f / r0["ar_nccl_us"] / 1e3 if "ar_nccl_us" in r0 else None,
+                "frac_of_nvlink_peak": r0["ag_edb_GBs"] / 900.0}
+        except Exception as e:  # the microbench must never sink the throughput line
+            line["reshard_bus"] = {"error": repr(e)[:200]}
     if roof:
         roof["share_of_step"] = roof["gemm_ms_per_step"] / ms_per_step
         line["roofline"] = roof

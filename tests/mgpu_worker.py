@@ -911,7 +911,7 @@ def _ref_wrappers(world, rank, group_pg=None):
     return ag, rs, ar, a2a
 
 
-def bench2(rank, world, group, sizes=None, dtypes=("bfloat16", "float32")):
+def bench2(rank, world, group, sizes=None, dtypes=("bfloat16", "float32"), quiet=False):
     """Reshard microbench, BASELINE.json config 5 / SURVEY.md §8(d): all-gather, reduce-scatter(sum),
     all-reduce, all-to-all; total bytes 1 KB ... 1 GB (x4); bf16 and fp32; dims {0, last}; three
     arms on the same GPUs — this library (push protocol with static buffers + an epoch barrier per
@@ -923,6 +923,7 @@ def bench2(rank, world, group, sizes=None, dtypes=("bfloat16", "float32")):
     sizes = sizes or [1 << k for k in range(10, 31, 2)]
     oneshot = rt.get_option("allreduce_oneshot_bytes")
     f = (world - 1) / world
+    rows_out = []
     for dtype in dtypes:
         tdt = TORCH_DT[dtype]
         es = torch.empty((), dtype=tdt).element_size()
@@ -991,13 +992,15 @@ def bench2(rank, world, group, sizes=None, dtypes=("bfloat16", "float32")):
                 torch.cuda.synchronize()
                 reshard.epoch_barrier(shard, group)
                 rt.reset(mark)
-                if rank == 0:
+                rows_out.append(row)
+                if rank == 0 and not quiet:
                     print("BENCH2 " + " ".join(f"{k}={v:.1f}" if isinstance(v, float) else f"{k}={v}"
                                                for k, v in row.items()), flush=True)
     # the barrier itself (its cost is inside every *_edb_us above)
     t = timeit(lambda: reshard.epoch_barrier(shard, group))
-    if rank == 0:
+    if rank == 0 and not quiet:
         print(f"BENCH2 epoch_barrier_us={t * 1e3:.2f}", flush=True)
+    return rows_out
 
 
 def main():
