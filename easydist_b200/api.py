@@ -499,8 +499,14 @@ def register(reference_api=None, reference_compile_auto=None, **compile_kwargs):
         from easydist.torch.device_mesh import get_device_mesh as ref_mesh
         from .device_mesh import set_device_mesh
         mesh = set_device_mesh(ref_mesh("spmd"), rank=torch.distributed.get_rank())
-        return lowering.sharding_transform(fx_module, opt_strategy, state_io_map, mesh=mesh,
-                                           ops=compile_kwargs.get("ops", _default_ops))
+        ops_ = compile_kwargs.get("ops", _default_ops)
+        gm = lowering.sharding_transform(fx_module, opt_strategy, state_io_map, mesh=mesh, ops=ops_)
+        if os.environ.get("EDB_LOCALIZE_OPT", "0") == "1":
+            # opt-in under Hook B (it changes the communication structure the reference's own
+            # lowering would produce): the optimizer's foreach ops on shards; the rewritten graph
+            # still only uses the ten reshard callables, so the reference's executor runs it as is
+            lowering.localize_foreach(gm, ops_, my_rank=mesh.rank)
+        return gm
 
     reference_compile_auto.sharding_transform = sharding_transform
 

@@ -34,7 +34,7 @@ def test_dropin_lowering_equals_reference_lowering(mesh, nproc, port, planner, m
 
 
 @pytest.mark.parametrize("mode,port", [("b200_ddp", 29796), ("b200_zero3", 29797), ("auto", 29798),
-                                       ("b200_auto", 29799)])
+                                       ("b200_auto", 29799), ("auto+localize", 29800)])
 def test_plugin_hook_through_the_reference_decorator(mode, port):
     """Hook A of INTEGRATION.md: `easydist_b200.api.register()` adds the modes to the reference's
     registry (`register_parallel_method`, api.py:39-50); the REFERENCE's own `easydist_compile`
@@ -46,6 +46,9 @@ def test_plugin_hook_through_the_reference_decorator(mode, port):
     if not os.path.isdir("/root/reference/easydist"):
         pytest.skip("reference not present (GPU box)")
     env = dict(os.environ, OMP_NUM_THREADS="1", EDB_PLUGIN_MODE=mode)
+    if mode == "auto+localize":
+        # Hook B with the optimizer localized: the REFERENCE's executor runs the rewritten graph
+        env.update(EDB_PLUGIN_MODE="auto", EDB_LOCALIZE_OPT="1")
     if mode == "b200_auto":
         import tempfile
         env["EDB_PLAN_CACHE_DIR"] = tempfile.mkdtemp(prefix="edb_plan_cache_")
