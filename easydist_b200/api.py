@@ -100,10 +100,16 @@ def _finish(gm, params, buffers, named_states, args, kwargs, ops, native, io=Non
                     if os.environ.get(k, "0") == "1"]
     if experimental and native:
         # round-1 advisor finding: kernels whose CTAs wait on other CTAs assume the whole grid is
-        # co-resident, which a second stream breaks; these switches stay opt-in experiments
-        logger.warning("experimental switches %s: kernels on a second stream share the SMs with "
-                       "grids sized for an idle GPU (not co-residency safe); not part of the measured "
-                       "configuration", experimental)
+        # co-resident, which a second stream breaks (resident CTAs would wait on CTAs that cannot be
+        # scheduled until the fatal timeout fires).  Gated until the spinning kernels are launched
+        # cooperatively / sized from the SMs actually free.
+        if os.environ.get("EDB_ALLOW_EXPERIMENTAL", "0") != "1":
+            raise RuntimeError(
+                f"{experimental}: experimental multi-stream switches are gated on GPUs (kernels that "
+                "spin on peer / sibling CTAs are sized for an idle GPU and are not co-residency safe "
+                "next to a second stream); set EDB_ALLOW_EXPERIMENTAL=1 to try them anyway")
+        logger.warning("experimental switches %s enabled (EDB_ALLOW_EXPERIMENTAL=1): not "
+                       "co-residency safe, not part of the measured configuration", experimental)
     overlap = os.environ.get("EDB_OVERLAP", "0") == "1" and io is not None and ranks is not None \
         and len(ranks) > 1
     if overlap:
