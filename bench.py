@@ -81,7 +81,7 @@ class ClockSampler:
              "clocks_event_reasons.sw_power_cap")
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "200",
+                ["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100",
                  "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL,
                 text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
@@ -460,11 +460,15 @@ def run_edb(args):
     if not args.no_parity:
         parity = parity_leg(torch, dist, args, cfg, GPT2, step_fn, model, opt, state0, par_host,
                             float(loss), rank, world)
-    for _ in range(max(3, args.warmup)):
-        step_fn(dev[0][0], dev[0][1], model, opt)
+    # clocks / throttle reasons are sampled from the warm-up steps on (the same workload): the timed
+    # region alone lasts only ~0.3 s, one or two nvidia-smi samples
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+        time.sleep(0.3)  # nvidia-smi needs a moment to start reporting
+    for _ in range(max(3, args.warmup)):
+        step_fn(dev[0][0], dev[0][1], model, opt)
+    torch.cuda.synchronize()
     ms_total, loss_v = timed(args.steps, e2e=False)
     clocks = sampler.stop() if rank == 0 else None
     ms_e2e, _ = timed(args.steps, e2e=True)
