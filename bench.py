@@ -464,8 +464,7 @@ def run_edb(args):
     # region alone lasts only ~0.3 s, one or two nvidia-smi samples
     sampler = ClockSampler(local)
     if rank == 0:
-        sampler.start()
-        time.sleep(0.3)  # nvidia-smi needs a moment to start reporting
+        sampler.start()  # its first sample arrives ~0.1 s later: the GPU is already under load
     for _ in range(max(3, args.warmup)):
         step_fn(dev[0][0], dev[0][1], model, opt)
     torch.cuda.synchronize()
