@@ -8,6 +8,8 @@ import torch
 import torch.distributed as dist
 from torch._subclasses.fake_tensor import FakeTensor
 
+from easydist_b200.reshard import all_reduce_push_sizes  # noqa: E402,F401  (pure host arithmetic)
+
 _GROUPS = {}
 
 
@@ -234,6 +236,9 @@ class FakeSymmRuntime:
 
     def __init__(self):
         self._off = 1 << 20
+
+    def get_option(self, name):
+        return {"allreduce_oneshot_bytes": 512 * 1024}[name]
 
     def alloc(self, nbytes, align=256):
         off = (self._off + align - 1) // align * align

@@ -107,3 +107,51 @@ def test_every_shard_byte_is_prefetched_once_before_its_first_use(gbps, my_index
                        and nd.target == torch.ops.aten.copy_.default and nd.args[0] in io.param_ph)
     assert max([last_peer] + pushes) < barriers[0] < first_update
     assert nodes[barriers[1]].next.op == "output"
+
+
+def test_static_buffers_mark_push_collectives_and_the_step_ends_with_a_barrier(monkeypatch):
+    """lowering.assign_static_buffers(push=True): every remaining collective node of the zero3 graph
+    gets dedicated symmetric buffers and `_push=1`; an all-reduce's receive buffer follows the
+    one-shot / two-shot rule of edb_all_reduce_push; ensure_end_barrier is idempotent."""
+    monkeypatch.setenv("EDB_EPOCH", "1")
+    from easydist_b200 import lowering
+    from easydist_b200.api import _flat_inputs
+    from easydist_b200.compile import GraphIO, trace_train_step
+    from tests import gloo_ops
+    torch.manual_seed(0)
+    model = Deep(layers=2).bfloat16()
+    opt = make_opt("sgd", model.parameters())
+    x = torch.randn(64, 256).bfloat16()
+    params, buffers, named_states, gm, module, o = trace_train_step(train_step, (x, model, opt), {},
+                                                                   "fake")
+    io = GraphIO(gm, params, buffers, named_states)
+    ranks, n = [0, 1], 2
+    _, shard_info = lowering.transform_fsdp(gm, io, ranks, 0, True, gloo_ops, bucket_numel=2048)
+    with torch.no_grad():
+        params = {k: v.detach() for k, v in params.items()}
+        for ph, name in zip(io.param_ph, io.param_names):
+            if ph.name in shard_info:
+                params[name] = torch.chunk(params[name].flatten(), n)[0].contiguous()
+        flat_states, spec = torch.utils._pytree.tree_flatten(named_states)
+        for i, ph in enumerate(io.state_ph):
+            if ph.name in shard_info and isinstance(flat_states[i], torch.Tensor):
+                flat_states[i] = torch.chunk(flat_states[i].detach().flatten(), n)[0].contiguous()
+        named_states = torch.utils._pytree.tree_unflatten(flat_states, spec)
+        lowering.propagate_local_meta(gm, [t.detach() if isinstance(t, torch.Tensor) else t for t in
+                                           _flat_inputs(params, buffers, named_states, (x, model, opt), {})])
+    rt = gloo_ops.FakeSymmRuntime()
+    total = lowering.assign_static_buffers(gm, rt, gloo_ops, push=True)
+    assert total > 0
+    comm = [nd for nd in gm.graph.nodes if nd.op == "call_function" and nd.target in gloo_ops.COMM_FUNCS]
+    assert comm and all(nd.kwargs.get("_push") == 1 and "_buf" in nd.kwargs for nd in comm)
+    for nd in comm:
+        if nd.target is gloo_ops.all_reduce_start:
+            xv = nd.args[0].meta["val"]
+            nb = xv.numel() * xv.element_size()
+            rb, ob = gloo_ops.all_reduce_push_sizes(nb, xv.numel(), xv.element_size(), n, 512 * 1024)
+            assert nd.kwargs["_buf"][1] == rb and len(nd.kwargs["_buf"]) == 3
+            assert rb == (n * nb if nb <= 8 * 512 * 1024 else nb) and ob == nb
+    assert lowering.ensure_end_barrier(gm, ranks, gloo_ops) == 1
+    assert lowering.ensure_end_barrier(gm, ranks, gloo_ops) == 0
+    out = next(nd for nd in gm.graph.nodes if nd.op == "output")
+    assert out.prev.target is gloo_ops.epoch_barrier
