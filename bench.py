@@ -505,7 +505,7 @@ def run_edb(args):
         "gpu_launches_per_step": launches_per_step,
         "dispatch": {"edb_gemm_per_step": gemm_calls_per_step, "aten_mm_per_step": aten_mm_per_step,
                      "comm_nodes": info.get("comm_nodes"), "fused": info.get("fused"),
-                     "symm_bytes": info.get("symm_bytes")},
+                     "symm_bytes": info.get("symm_bytes"), "epoch_check": info.get("epoch_check")},
         "clocks": clocks, "loss": loss_v, "compile_s": compile_s,
     }
     if parity is not None:

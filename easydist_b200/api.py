@@ -166,6 +166,19 @@ def _finish(gm, params, buffers, named_states, args, kwargs, ops, native, io=Non
             lowering.ensure_end_barrier(gm, ranks, ops)
             info["push_collectives"] = True
         info["gemm_nodes"] = lowering.dispatch_compute(gm)
+        if ranks is not None and len(ranks) > 1 and (push or info.get("fused")):
+            # static race check of the lowered graph against the epoch-protocol contract (diagnostic:
+            # problems are logged and reported in `info`; EDB_VERIFY_STRICT=1 makes them fatal)
+            try:
+                rep = lowering.verify_epoch_protocol(gm, ops, len(ranks))
+            except Exception as e:  # noqa: BLE001 — the checker must never break a compilation
+                rep = {"ok": None, "problems": [f"checker failed: {e!r}"]}
+            info["epoch_check"] = {"ok": rep["ok"], "problems": rep["problems"][:5],
+                                   "ranges": rep.get("ranges"), "items": rep.get("items")}
+            if rep["problems"]:
+                logger.error("epoch-protocol check: %s", rep["problems"][:5])
+                if os.environ.get("EDB_VERIFY_STRICT", "0") == "1":
+                    raise RuntimeError(f"epoch-protocol check failed: {rep['problems'][:5]}")
     gm.graph.lint()
     gm.recompile()
     return info

@@ -1638,6 +1638,157 @@ def fuse_collective_gemms(gm, io, rt, ranks, ops=_default_ops, my_index=None):
     return rehomed, {"ag_mm": n_ag, "ag_pf": n_pf, "mm_rs": n_rs}
 
 
+def verify_epoch_protocol(gm, ops, n):
+    """Static race check of a lowered graph against the contract of the epoch protocol (edb.h,
+    DESIGN.md §3.1) — the B200-native counterpart of the reference's debug-time `op_mem_checker`
+    (an interval-tree ownership check per node, compile_auto.py:269-351), done once at compile time
+    because here the hazards are decided by graph structure, not by run-time addresses:
+
+      1. symmetric ranges that peers write without a handshake (gathered parameter buffers, receive
+         slots of push GEMMs, static buffers of push collectives) are pairwise disjoint and each is
+         written by exactly one node per step;
+      2. every byte of every gathered parameter is prefetched exactly once, by nodes that precede its
+         first use; no prefetch item points outside a gathered buffer;
+      3. a group barrier separates the last node that reads peers' parameter shards from the first
+         in-place update of such a parameter; every `rs_finish(_epoch=1)` has a barrier between its
+         last push and itself;
+      4. the step ends with a barrier.
+
+    Returns {"ok", "problems": [...], "ranges", "items", "barriers"}; never raises."""
+    problems = []
+    nodes = list(gm.graph.nodes)
+    order = {nd: i for i, nd in enumerate(nodes)}
+
+    def nbytes(nd):
+        v = nd.meta.get("val") if isinstance(nd, Node) else None
+        return v.numel() * v.element_size() if isinstance(v, torch.Tensor) else None
+
+    has = lambda k: getattr(ops, k, None)
+    ranges = []      # (lo, hi, what)
+    gathered = {}    # ph -> (full_off, shard_bytes, first_use_pos)
+    items = []       # (pos, src, dst, take, dstride, sstride, node name)
+    pushes, finishes, barriers = [], [], []
+    for nd in nodes:
+        if nd.op != "call_function":
+            continue
+        t = nd.target
+        pf = nd.kwargs.get("_pf") or nd.meta.get("edb_pf")
+        if pf:
+            items += [(order[nd],) + tuple(it) + (nd.name,) for it in pf["items"]]
+        if has("ag_prefetch") and t is ops.ag_prefetch:
+            items += [(order[nd],) + tuple(it) + (nd.name,) for it in nd.kwargs.get("_items", [])]
+        elif has("gathered") and t is ops.gathered:
+            ph = nd.args[0]
+            nb = nbytes(ph)
+            if nb is None:
+                problems.append(f"{nd.name}: shard size unknown")
+                continue
+            shard_off, full_off = nd.kwargs["_buf"]
+            prev = gathered.get(ph)
+            if prev is None:
+                gathered[ph] = (full_off, nb, order[nd])
+                ranges.append((full_off, full_off + n * nb, f"gathered({ph.name})"))
+                if not (full_off <= shard_off and shard_off + nb <= full_off + n * nb):
+                    ranges.append((shard_off, shard_off + nb, f"shard({ph.name})"))
+            elif prev[0] != full_off:
+                problems.append(f"{nd.name}: parameter {ph.name} has two gathered buffers")
+        elif has("mm_push") and t is ops.mm_push:
+            a, b = nd.args[0].meta.get("val"), nd.args[1].meta.get("val")
+            pushes.append(nd)
+            if a is not None and b is not None:
+                lo = nd.kwargs["_buf"][0]
+                ranges.append((lo, lo + a.shape[0] * b.shape[1] * 2, f"recv({nd.name})"))
+        elif has("rs_finish") and t is ops.rs_finish and nd.kwargs.get("_epoch"):
+            finishes.append(nd)
+        elif has("epoch_barrier") and t is ops.epoch_barrier:
+            barriers.append(order[nd])
+        elif t in ops.COMM_FUNCS and nd.kwargs.get("_push"):
+            buf = nd.kwargs.get("_buf")
+            if not buf:
+                problems.append(f"{nd.name}: push collective without static buffers")
+                continue
+            ranges.append((buf[0], buf[0] + buf[1], f"{nd.name}[0]"))
+            xb = nbytes(nd.args[0])
+            for k, off in enumerate(buf[2:]):
+                ranges.append((off, off + (xb or 1), f"{nd.name}[{k + 1}]"))
+    # 1. disjoint ranges
+    ranges.sort()
+    for (a0, a1, wa), (b0, b1, wb) in zip(ranges, ranges[1:]):
+        if b0 < a1:
+            problems.append(f"symmetric ranges overlap: {wa} [{a0},{a1}) and {wb} [{b0},{b1})")
+    # 2. prefetch coverage
+    by_buf = sorted((full, nb, ph) for ph, (full, nb, _) in gathered.items())
+    cover = {ph: [] for ph in gathered}
+    for pos, src, dst, take, dstride, sstride, name in items:
+        owner = next((ph for full, nb, ph in by_buf if full <= dst and dst + take <= full + nb), None)
+        if owner is None:
+            problems.append(f"{name}: prefetch item dst={dst} (+{take}) is outside every gathered buffer")
+            continue
+        full, nb, first = gathered[owner]
+        if dstride != nb:
+            problems.append(f"{name}: item for {owner.name} has member stride {dstride} != shard {nb}")
+        if pos >= first:
+            problems.append(f"{name}: prefetch of {owner.name} is issued after its first use")
+        cover[owner].append((dst - full, dst - full + take))
+    for ph, segs in cover.items():
+        nb = gathered[ph][1]
+        segs.sort()
+        at = 0
+        for lo, hi in segs:
+            if lo != at:
+                problems.append(f"{ph.name}: prefetched ranges {'overlap' if lo < at else 'leave a gap'} "
+                                f"at byte {min(lo, at)}")
+                break
+            at = hi
+        else:
+            if at != nb:
+                problems.append(f"{ph.name}: only {at} of {nb} shard bytes are prefetched")
+    # 3. barriers around the optimizer
+    if gathered:
+        peer_read = set(gathered)
+
+        def writes_param(nd):
+            if nd.op != "call_function":
+                return False
+            name = str(getattr(nd.target, "_schema", None) and nd.target._schema.name or
+                       getattr(nd.target, "__name__", ""))
+            if nd.target == aten.copy_.default:
+                return nd.args[0] in peer_read
+            if name.startswith("aten::_foreach_") and name.endswith("_") or name == "sgd_momentum_":
+                first = nd.args[0] if nd.args else []
+                return isinstance(first, (list, tuple)) and any(x in peer_read for x in first)
+            return False
+
+        upd = [order[nd] for nd in nodes if writes_param(nd)]
+        last_read = max([pos for pos, *_ in items], default=-1)
+        if upd and not any(last_read < b < min(upd) for b in barriers):
+            problems.append("no epoch barrier between the last prefetch of peers' parameter shards "
+                            f"(node {last_read}) and the first in-place parameter update (node {min(upd)})")
+    for fin in finishes:
+        toks = [t_ for t_ in fin.args[0] if isinstance(t_, Node)]
+        srcs = []
+        for t_ in toks:
+            while t_.op == "call_function" and has("epoch_barrier") and t_.target is ops.epoch_barrier:
+                t_ = t_.args[0]
+            srcs.append(t_)
+        last_push = max((order[t_] for t_ in srcs), default=-1)
+        if not any(last_push < b < order[fin] for b in barriers):
+            problems.append(f"{fin.name}: no epoch barrier between its last push and the reduction")
+    unfinished = [p_.name for p_ in pushes if not any(
+        u.target is ops.rs_finish or (has("epoch_barrier") and u.target is ops.epoch_barrier)
+        for u in p_.users)]
+    if unfinished:
+        problems.append(f"push GEMMs without rs_finish: {unfinished[:4]}")
+    # 4. end of step
+    if ranges or items:
+        out = next((nd for nd in nodes if nd.op == "output"), None)
+        if out is None or not (out.prev.op == "call_function" and has("epoch_barrier")
+                               and out.prev.target is ops.epoch_barrier):
+            problems.append("the step does not end with an epoch barrier")
+    return {"ok": not problems, "problems": problems, "ranges": len(ranges), "items": len(items),
+            "barriers": len(barriers)}
+
+
 def reinplace_optimizer_updates(gm):
     """Undo the functionalisation of optimizer updates where it is safe.
 

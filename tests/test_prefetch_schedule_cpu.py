@@ -155,3 +155,90 @@ def test_static_buffers_mark_push_collectives_and_the_step_ends_with_a_barrier(m
     assert lowering.ensure_end_barrier(gm, ranks, gloo_ops) == 0
     out = next(nd for nd in gm.graph.nodes if nd.op == "output")
     assert out.prev.target is gloo_ops.epoch_barrier
+
+
+def _lowered_zero3_graph(n=4, me=1):
+    from easydist_b200 import lowering
+    from easydist_b200.api import _flat_inputs
+    from easydist_b200.compile import GraphIO, trace_train_step
+    from tests import gloo_ops
+    torch.manual_seed(0)
+    model = Deep(layers=2).bfloat16()
+    opt = make_opt("sgd", model.parameters())
+    x = torch.randn(64, 256).bfloat16()
+    params, buffers, named_states, gm, module, o = trace_train_step(train_step, (x, model, opt), {},
+                                                                   "fake")
+    io = GraphIO(gm, params, buffers, named_states)
+    ranks = list(range(n))
+    _, shard_info = lowering.transform_fsdp(gm, io, ranks, me, True, gloo_ops, bucket_numel=2048)
+    with torch.no_grad():
+        params = {k: v.detach() for k, v in params.items()}
+        for ph, name in zip(io.param_ph, io.param_names):
+            if ph.name in shard_info:
+                params[name] = torch.chunk(params[name].flatten(), n)[me].contiguous()
+        flat_states, spec = torch.utils._pytree.tree_flatten(named_states)
+        for i, ph in enumerate(io.state_ph):
+            if ph.name in shard_info and isinstance(flat_states[i], torch.Tensor):
+                flat_states[i] = torch.chunk(flat_states[i].detach().flatten(), n)[me].contiguous()
+        named_states = torch.utils._pytree.tree_unflatten(flat_states, spec)
+        lowering.propagate_local_meta(gm, [t.detach() if isinstance(t, torch.Tensor) else t for t in
+                                           _flat_inputs(params, buffers, named_states, (x, model, opt), {})])
+    rt = gloo_ops.FakeSymmRuntime()
+    lowering.fuse_collective_gemms(gm, io, rt, ranks, gloo_ops, my_index=me)
+    lowering.reinplace_optimizer_updates(gm)
+    lowering.assign_static_buffers(gm, rt, gloo_ops, push=True)
+    lowering.ensure_end_barrier(gm, ranks, gloo_ops)
+    lowering.dispatch_compute(gm)
+    return gm, ranks
+
+
+def test_static_epoch_protocol_check_passes_and_catches_planted_races(monkeypatch):
+    """lowering.verify_epoch_protocol (the compile-time counterpart of the reference's op_mem_checker,
+    compile_auto.py:269-351): the lowered zero3 graph satisfies the contract; a removed barrier, two
+    nodes sharing a receive buffer, a dropped prefetch range and a prefetch after the first use are
+    each reported."""
+    monkeypatch.setenv("EDB_EPOCH", "1")
+    from easydist_b200 import lowering
+    from tests import gloo_ops
+    gm, ranks = _lowered_zero3_graph()
+    rep = lowering.verify_epoch_protocol(gm, gloo_ops, len(ranks))
+    assert rep["ok"] and rep["barriers"] == 2 and rep["ranges"] > 4 and rep["items"] > 2, rep
+
+    def fresh():
+        return _lowered_zero3_graph()[0]
+
+    # (a) the barrier in front of the optimizer removed
+    g = fresh()
+    b = next(nd for nd in g.graph.nodes if nd.op == "call_function" and nd.target is gloo_ops.epoch_barrier)
+    b.replace_all_uses_with(b.args[0])
+    g.graph.erase_node(b)
+    probs = lowering.verify_epoch_protocol(g, gloo_ops, len(ranks))["problems"]
+    assert any("no epoch barrier" in p for p in probs), probs
+    # (b) two push GEMMs write the same receive slots
+    g = fresh()
+    ps = [nd for nd in g.graph.nodes if nd.op == "call_function" and nd.target is gloo_ops.mm_push]
+    ps[1].kwargs = dict(ps[1].kwargs, _buf=ps[0].kwargs["_buf"])
+    probs = lowering.verify_epoch_protocol(g, gloo_ops, len(ranks))["problems"]
+    assert any("overlap" in p for p in probs), probs
+    # (c) a prefetch that lost part of a shard
+    g = fresh()
+    pf = next(nd for nd in g.graph.nodes if nd.op == "call_function" and nd.target is gloo_ops.ag_prefetch)
+    its = list(pf.kwargs["_items"])
+    src, dst, take, ds, ss = its[0]
+    its[0] = (src, dst, take - 16, ds, ss)
+    pf.kwargs = dict(pf.kwargs, _items=its)
+    probs = lowering.verify_epoch_protocol(g, gloo_ops, len(ranks))["problems"]
+    assert any("shard bytes are prefetched" in p or "gap" in p for p in probs), probs
+    # (d) a prefetch issued after the parameter's first use
+    g = fresh()
+    pf = next(nd for nd in g.graph.nodes if nd.op == "call_function" and nd.target is gloo_ops.ag_prefetch)
+    last_g = [nd for nd in g.graph.nodes if nd.op == "call_function" and nd.target is gloo_ops.gathered][-1]
+    last_g.append(pf)
+    probs = lowering.verify_epoch_protocol(g, gloo_ops, len(ranks))["problems"]
+    assert any("after its first use" in p for p in probs), probs
+    # (e) the end-of-step barrier removed
+    g = fresh()
+    out = next(nd for nd in g.graph.nodes if nd.op == "output")
+    g.graph.erase_node(out.prev)
+    probs = lowering.verify_epoch_protocol(g, gloo_ops, len(ranks))["problems"]
+    assert any("does not end with an epoch barrier" in p for p in probs), probs
