@@ -58,7 +58,8 @@ def main():
     mesh_shape = tuple(int(v) for v in os.environ.get("EDB_TEST_MESH", str(world)).split("x"))
     record = os.environ.get("EDB_RECORD", "")
     planner = os.environ.get("EDB_PLANNER", "GREEDY")
-    torch.set_num_threads(1)
+    # recording large plans: rank 0 does the sharding discovery + ILP alone while the others wait
+    torch.set_num_threads(int(os.environ.get("EDB_THREADS_RANK0" if rank == 0 else "EDB_THREADS", "1")))
     dist.init_process_group("gloo")
     from oracle import refcompat
     refcompat.install()
@@ -89,7 +90,7 @@ def main():
         from benchmark.torch.model.gpt import GPT
         depth, dim, heads, gb, gs = (int(v) for v in os.environ.get("EDB_GPT", "2,64,4,4,32").split(","))
         model0 = GPT(depth=depth, dim=dim, num_heads=heads)
-        batches = [torch.randn(gb, gs, dim, generator=g) for _ in range(2)]
+        batches = [torch.randn(gb, gs, dim, generator=g) for _ in range(int(os.environ.get("EDB_STEPS", "2")))]
         model_tag = f"GPT(depth={depth}, dim={dim}, num_heads={heads})"
         batch_shape = [gb, gs, dim]
     else:

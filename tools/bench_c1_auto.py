@@ -28,6 +28,13 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--no-cuda-graph", action="store_true")
+    ap.add_argument("--bundle", default="",
+                    help="another recorded graph + plan (graph_io bundle, .json or .json.gz) instead of "
+                         "the config-1 golden bundles; give the model with --gpt")
+    ap.add_argument("--gpt", default="", help="depth,dim,heads,batch,seq of the bundle's model")
+    ap.add_argument("--dtype", default="fp32", choices=["fp32", "bf16"],
+                    help="bf16: parameters and inputs in bf16 (the plan is dtype independent; the "
+                         "Linear layers then run on the native tcgen05 GEMM)")
     run(ap.parse_args())
 
 
@@ -43,22 +50,33 @@ def run(args):
     set_device_mesh(np.arange(world).reshape(mesh_shape), [f"spmd{i}" for i in range(len(mesh_shape))],
                     rank=rank)
     golden = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
-    bundle = gzip.open(os.path.join(golden, f"auto_gpt_c1_mesh{tag}.json.gz"), "rt").read()
+    custom = getattr(args, "bundle", "")
+    depth, dim, heads, gbatch, seq = 4, 1024, 32, (8 if tag == "8" else 4), 128
+    if custom:
+        opener = gzip.open if custom.endswith(".gz") else open
+        bundle = opener(custom, "rt").read()
+        depth, dim, heads, gbatch, seq = (int(v) for v in args.gpt.split(","))
+    else:
+        bundle = gzip.open(os.path.join(golden, f"auto_gpt_c1_mesh{tag}.json.gz"), "rt").read()
+    tdt = torch.bfloat16 if getattr(args, "dtype", "fp32") == "bf16" else torch.float32
     # parity first (outside the timed region): outputs, every parameter and every momentum buffer
     # vs vanilla PyTorch on the same batches (the reference's comparator, rtol 1e-4 / atol 1e-5)
     from easydist_b200 import reshard
     from tests.test_auto_bundle_cpu import run_c1_bundle
-    ok, msg, _ = run_c1_bundle(rank, world, reshard, True, "cuda", steps=3, tag=tag)
+    if custom or tdt != torch.float32:
+        ok, msg = True, "parity leg only exists for the fp32 config-1 bundles"
+    else:
+        ok, msg, _ = run_c1_bundle(rank, world, reshard, True, "cuda", steps=3, tag=tag)
     flag = torch.tensor([0.0 if ok else 1.0], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MAX)
     parity_ok = bool(flag.item() == 0.0)
     if not ok:
         print(f"[rank {rank}] parity failed: {msg}", flush=True)
     torch.manual_seed(42)
-    model = EmbeddingGPT(4, 1024, 32).cuda()
+    model = EmbeddingGPT(depth, dim, heads).cuda().to(tdt)
     opt = torch.optim.SGD(model.parameters(), lr=1e-3, momentum=0.9, foreach=True)
-    batch = 8 if tag == "8" else 4
-    x = torch.randn(batch, 128, 1024, device="cuda")
+    batch = gbatch
+    x = torch.randn(batch, seq, dim, device="cuda").to(tdt)
     compiled = api.compile_from_bundle(bundle, (x, model, opt), {})
     step = lambda: compiled(x, model, opt)
     for _ in range(2):
@@ -86,9 +104,11 @@ def run(args):
         print(json.dumps({"metric": "train_step_throughput", "value": batch / ms * 1e3, "unit": "samples/s",
                           "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                           "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
-                          "vs_baseline": None, "data": "synthetic", "dtype": "f32",
-                          "config": {"workload": "config 1: GPT depth 4 dim 1024 heads 32, batch "
-                                                 f"{batch}x128, auto-SPMD plan of the reference solver",
+                          "vs_baseline": None, "data": "synthetic",
+                          "dtype": "bf16" if tdt == torch.bfloat16 else "f32",
+                          "config": {"workload": f"GPT depth {depth} dim {dim} heads {heads}, batch "
+                                                 f"{batch}x{seq}, auto-SPMD plan of the reference solver"
+                                                 + ("" if custom else " (config 1)"),
                                      "mesh": list(mesh_shape), "cuda_graph": not args.no_cuda_graph,
                                      "bucket_comm": os.environ.get("EDB_BUCKET_COMM", "0")},
                           "parity": {"ok": parity_ok, "what": "3 steps vs vanilla fp32 PyTorch: outputs, every "
