@@ -279,3 +279,57 @@ def test_config1_plans_for_larger_meshes_lower_to_the_recorded_structure(tag, me
     # every parameter ended up with its local shard shape under the plan
     full = dict(model.named_parameters())
     assert any(p.shape != full[n].shape for n, p in compiled.named_parameters().items())
+
+
+@pytest.mark.parametrize("tag,world,rank,batch,want", [
+    ("2", 2, 1, 4, {"all_gather_start": 1285, "scatter_wrapper": 589, "reduce_scatter_start": 84,
+                    "all_reduce_start": 49, "all_to_all_start": 48}),
+])
+def test_gpt2_small_size_plan_lowers_to_the_recorded_structure_and_passes_the_static_check(
+        tag, world, rank, batch, want, monkeypatch):
+    """A GPT-2-small-sized model (the reference's benchmark GPT: depth 12, dim 768, 12 heads, batch
+    4 x 256; SURVEY.md 8(d) 'GPT-2 small variant') solved by the unmodified reference at world 2 and
+    recorded with tests/ref/auto_worker.py (there: outputs and parameters == vanilla, and this
+    lowering == the reference's lowering of the very same plan: 1285 all-gathers, 589 scatters, 84
+    reduce-scatters, 49 all-reduces, 48 all-to-alls).  Here, without the reference and without
+    executing anything: (1) the bundle lowers to that structure; (2) with the product passes
+    (optimizer on shards, parameter gathers as prefetches, push collectives, epoch barriers) two
+    thirds of the all-gathers are gone and the static epoch-protocol check passes."""
+    import gzip
+    import numpy as np
+    from easydist_b200 import api, lowering
+    from easydist_b200.device_mesh import set_device_mesh
+    from easydist_b200.workloads import EmbeddingGPT
+    from tests import gloo_ops
+    set_device_mesh(np.arange(world).reshape((world,)), ["spmd0"], rank=rank)
+    bundle = gzip.open(os.path.join(GOLDEN, f"auto_gpt2small_s256_mesh{tag}.json.gz"), "rt").read()
+
+    def build():
+        torch.manual_seed(0)
+        model = EmbeddingGPT(12, 768, 12)
+        opt = torch.optim.SGD(model.parameters(), lr=0.1, momentum=0.9, foreach=True)
+        return api.compile_from_bundle(bundle, (torch.randn(batch, 256, 768), model, opt), {},
+                                       ops=gloo_ops, native=False)
+
+    monkeypatch.setenv("EDB_LOCALIZE_OPT", "0")
+    hist = build().info["comm_nodes"]
+    for k, v in want.items():
+        assert hist.get(k, 0) == v, (k, hist)
+    monkeypatch.setenv("EDB_LOCALIZE_OPT", "1")
+    compiled = build()
+    gm = compiled.graph
+    params = compiled.get_state()[0]
+    phs = [n for n in gm.graph.nodes if n.op == "placeholder"]
+    auto_io = api._ParamIO(phs[:len(params)], list(params.keys()))
+    rt = gloo_ops.FakeSymmRuntime()
+    ranks = list(range(world))
+    rehomed, n_pf = lowering.prefetch_param_gathers(gm, auto_io, rt, ranks, gloo_ops, my_index=rank)
+    assert n_pf == len(rehomed) > 100
+    lowering.insert_epoch_barriers(gm, ranks, gloo_ops)
+    lowering.assign_static_buffers(gm, rt, gloo_ops, push=True)
+    lowering.ensure_end_barrier(gm, ranks, gloo_ops)
+    lowering.dispatch_compute(gm)
+    after = lowering.count_nodes(gm, gloo_ops)
+    assert after.get("all_gather_start", 0) < want["all_gather_start"] // 3, after
+    rep = lowering.verify_epoch_protocol(gm, gloo_ops, world)
+    assert rep["ok"], rep["problems"]
