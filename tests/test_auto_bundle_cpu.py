@@ -284,14 +284,17 @@ def test_config1_plans_for_larger_meshes_lower_to_the_recorded_structure(tag, me
 @pytest.mark.parametrize("tag,world,rank,batch,want", [
     ("2", 2, 1, 4, {"all_gather_start": 1285, "scatter_wrapper": 589, "reduce_scatter_start": 84,
                     "all_reduce_start": 49, "all_to_all_start": 48}),
+    ("8", 8, 5, 8, {"all_gather_start": 1309, "scatter_wrapper": 589, "reduce_scatter_start": 60,
+                    "all_reduce_start": 49, "all_to_all_start": 72}),
 ])
 def test_gpt2_small_size_plan_lowers_to_the_recorded_structure_and_passes_the_static_check(
         tag, world, rank, batch, want, monkeypatch):
     """A GPT-2-small-sized model (the reference's benchmark GPT: depth 12, dim 768, 12 heads, batch
-    4 x 256; SURVEY.md 8(d) 'GPT-2 small variant') solved by the unmodified reference at world 2 and
-    recorded with tests/ref/auto_worker.py (there: outputs and parameters == vanilla, and this
-    lowering == the reference's lowering of the very same plan: 1285 all-gathers, 589 scatters, 84
-    reduce-scatters, 49 all-reduces, 48 all-to-alls).  Here, without the reference and without
+    4 x 256 at world 2, 8 x 256 at world 8; SURVEY.md 8(d) 'GPT-2 small variant') solved by the
+    unmodified reference on meshes (2,) and (8,) and recorded with tests/ref/auto_worker.py (there:
+    outputs and parameters == vanilla, and this lowering == the reference's lowering of the very same
+    plan, e.g. mesh (2,): 1285 all-gathers, 589 scatters, 84 reduce-scatters, 49 all-reduces, 48
+    all-to-alls).  Here, without the reference and without
     executing anything: (1) the bundle lowers to that structure; (2) with the product passes
     (optimizer on shards, parameter gathers as prefetches, push collectives, epoch barriers) two
     thirds of the all-gathers are gone and the static epoch-protocol check passes."""
