@@ -340,12 +340,26 @@ def parity_leg(torch, dist, args, cfg, GPT2, step_fn, model, opt, state0, par_ho
         try:
             from tests import mgpu_worker as W
             group = list(range(world))
-            n_resh = W.run_cases(rank, world, group, tag="bench")
-            n_resh += W.run_p2p(rank, world, group)
-            n_resh += W.run_epoch(rank, world, group)
-            n_resh += W.run_prefetch(rank, world, group)
-            n_resh += W.run_push_cases(rank, world, group, passes=2, big=False)
+            stages = [("cases", lambda: W.run_cases(rank, world, group, tag="bench")),
+                      ("p2p", lambda: W.run_p2p(rank, world, group)),
+                      ("epoch", lambda: W.run_epoch(rank, world, group)),
+                      ("prefetch", lambda: W.run_prefetch(rank, world, group)),
+                      ("push", lambda: W.run_push_cases(rank, world, group, passes=2, big=False))]
+            # wall-clock bound on this pre-timing leg (host-side oracle work grows with N): a stage
+            # starts only while every rank is inside the budget (MAX over ranks: one decision for all)
+            budget_s = float(os.environ.get("EDB_BENCH_BATTERY_S", "90"))
+            t_b, n_resh, skipped = time.time(), 0, []
+            for name, stage in stages:
+                el = torch.tensor([time.time() - t_b], device="cuda")
+                dist.all_reduce(el, op=dist.ReduceOp.MAX)
+                if el.item() > budget_s:
+                    skipped.append(name)
+                    continue
+                n_resh += stage()
             res["reshard_checks_bit_exact"] = n_resh
+            res["reshard_battery_s"] = time.time() - t_b
+            if skipped:
+                res["reshard_battery_skipped"] = skipped
             res["checks"] += n_resh
         except AssertionError as e:
             ok = False
