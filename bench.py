@@ -554,12 +554,12 @@ def run_edb(args):
                     args, args.cpu_sample_seqs).items() if k != "loss"}
             except Exception as e:  # the baseline must never sink the measurement
                 line["cpu_baseline"] = {"error": repr(e)}
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line, default=str), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     if parity is not None and not parity["ok"]:
-        raise SystemExit("parity leg failed: " + json.dumps(parity))
+        raise SystemExit("parity leg failed: " + json.dumps(parity, default=str))
 
 
 def run_torch_nccl(args):
