@@ -10,10 +10,10 @@ import sys
 import pytest
 import torch
 import torch.distributed as dist
-import torch.multiprocessing as mp
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+from tests._procs import run_world  # noqa: E402
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 
@@ -79,20 +79,13 @@ def _worker(rank, world, mesh_shape, port, q, bucket="0"):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("mesh_shape,port", [((2,), 29861), ((2, 2), 29862)])
-def test_recorded_reference_plan_lowers_and_matches_vanilla(mesh_shape, port):
+@pytest.mark.parametrize("mesh_shape", [(2,), (2, 2)])
+def test_recorded_reference_plan_lowers_and_matches_vanilla(mesh_shape):
     world = 1
     for v in mesh_shape:
         world *= v
-    ctx = mp.get_context("spawn")
-    q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, world, mesh_shape, port, q)) for r in range(world)]
-    for p in procs:
-        p.start()
-    for p in procs:
-        p.join(240)
-    assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
-    ok, msg, hist = q.get(timeout=5)
+    ok, msg, hist = run_world(_worker, world, lambda r, port, q: (r, world, mesh_shape, port, q),
+                              timeout=240)
     assert ok, msg
     # the communication structure the reference's own lowering produced for these plans
     want = {(2,): {"all_gather_start": 26, "all_reduce_start": 3, "scatter_wrapper": 13,
@@ -103,23 +96,16 @@ def test_recorded_reference_plan_lowers_and_matches_vanilla(mesh_shape, port):
         assert hist.get(k, 0) == v, (k, hist)
 
 
-@pytest.mark.parametrize("mesh_shape,port", [((2,), 29863), ((2, 2), 29864)])
-def test_bucketed_small_collectives_match_vanilla(mesh_shape, port):
+@pytest.mark.parametrize("mesh_shape", [(2,), (2, 2)])
+def test_bucketed_small_collectives_match_vanilla(mesh_shape):
     """EDB_BUCKET_COMM=1 (lowering.bucket_small_comm, the analogue of the reference's comm_group
     pass): the same recorded plans with their small all-reduces / dim-0 all-gathers bucketed still
     reproduce vanilla PyTorch, with fewer collectives."""
     world = 1
     for v in mesh_shape:
         world *= v
-    ctx = mp.get_context("spawn")
-    q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, world, mesh_shape, port, q, "1")) for r in range(world)]
-    for p in procs:
-        p.start()
-    for p in procs:
-        p.join(240)
-    assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
-    ok, msg, hist = q.get(timeout=5)
+    ok, msg, hist = run_world(_worker, world,
+                              lambda r, port, q: (r, world, mesh_shape, port, q, "1"), timeout=240)
     assert ok, msg
     plain = {(2,): (26, 3), (2, 2): (37, 5)}[mesh_shape]
     assert hist.get("all_gather_start", 0) < plain[0], hist
@@ -221,15 +207,7 @@ def _c1_worker(rank, world, port, q, localize="0"):
 
 
 def test_config1_gpt_plan_from_the_reference_solver_matches_vanilla():
-    ctx = mp.get_context("spawn")
-    q = ctx.Queue()
-    procs = [ctx.Process(target=_c1_worker, args=(r, 2, 29866, q)) for r in range(2)]
-    for p in procs:
-        p.start()
-    for p in procs:
-        p.join(600)
-    assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
-    ok, msg, hist = q.get(timeout=5)
+    ok, msg, hist = run_world(_c1_worker, 2, lambda r, port, q: (r, 2, port, q), timeout=600)
     assert ok, msg
     # what the reference's own lowering produces for this very plan (tests/ref/auto_worker.py,
     # EDB_SAMEPLAN=1: same_plan_equal=True)
@@ -244,15 +222,7 @@ def test_config1_optimizer_runs_on_shards_when_localized():
     (the reference gathers every parameter / gradient / state in front of each of them and scatters
     the results back).  Results still equal vanilla — outputs, every parameter,
     every momentum buffer — with 2/3 of the all-gathers and all optimizer scatters gone."""
-    ctx = mp.get_context("spawn")
-    q = ctx.Queue()
-    procs = [ctx.Process(target=_c1_worker, args=(r, 2, 29867, q, "1")) for r in range(2)]
-    for p in procs:
-        p.start()
-    for p in procs:
-        p.join(600)
-    assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
-    ok, msg, hist = q.get(timeout=5)
+    ok, msg, hist = run_world(_c1_worker, 2, lambda r, port, q: (r, 2, port, q, "1"), timeout=600)
     assert ok, msg
     assert hist.get("all_gather_start", 0) <= 429 - 280, hist
     assert hist.get("scatter_wrapper", 0) <= 197 - 170, hist

@@ -10,9 +10,10 @@ import os
 import pytest
 import torch
 import torch.distributed as dist
-import torch.multiprocessing as mp
 import torch.nn as nn
 import torch.nn.functional as F
+
+from tests._procs import run_world
 
 
 class Block(nn.Module):
@@ -106,17 +107,9 @@ def _worker(rank, world, port, mode, q, arch="tiny"):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("mode,port", [("ddp", 29901), ("zero2", 29902), ("zero3", 29903)])
-def test_conv_batchnorm_network_matches_per_rank_eager(mode, port):
-    ctx = mp.get_context("spawn")
-    q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, mode, q)) for r in range(2)]
-    for p in procs:
-        p.start()
-    for p in procs:
-        p.join(240)
-    assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
-    ok, msg, hist = q.get(timeout=5)
+@pytest.mark.parametrize("mode", ["ddp", "zero2", "zero3"])
+def test_conv_batchnorm_network_matches_per_rank_eager(mode):
+    ok, msg, hist = run_world(_worker, 2, lambda r, port, q: (r, 2, port, mode, q), timeout=240)
     assert ok, msg
     if mode == "ddp":
         # one all-reduce per parameter tensor: stem, bn (2), 2 x (conv + bn (2)), fc (2)
@@ -132,14 +125,7 @@ def test_torchvision_resnet50_ddp_matches_per_rank_eager():
     gradients (rtol 1e-4, atol 1e-5).  On GPUs its convolutions and BatchNorms stay ATen/cuDNN kernels
     (no native convolution path: DESIGN.md section 7); what runs natively there is the collectives."""
     pytest.importorskip("torchvision")
-    ctx = mp.get_context("spawn")
-    q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, 2, 29904, "ddp", q, "resnet50")) for r in range(2)]
-    for p in procs:
-        p.start()
-    for p in procs:
-        p.join(500)
-    assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
-    ok, msg, hist = q.get(timeout=5)
+    ok, msg, hist = run_world(_worker, 2, lambda r, port, q: (r, 2, port, "ddp", q, "resnet50"),
+                              timeout=500)
     assert ok, msg
     assert hist.get("all_reduce_start", 0) == 161, hist

@@ -8,10 +8,10 @@ import sys
 import pytest
 import torch
 import torch.distributed as dist
-import torch.multiprocessing as mp
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+from tests._procs import run_world  # noqa: E402
 
 
 class Foo(torch.nn.Module):
@@ -127,17 +127,8 @@ def test_fusion_rewrite_on_cpu(defer):
     a 2-layer MLP: both weights' all-gathers fuse into their forward GEMMs and both weight
     gradients' reduce-scatters fuse into the wgrad GEMMs (defer=1: push-only GEMMs + one rs_finish
     in front of the optimizer); training still matches vanilla."""
-    ctx = mp.get_context("spawn")
-    q = ctx.Queue()
-    procs = [ctx.Process(target=_fusion_worker,
-                         args=(r, 2, 29871 + {"0": 0, "1": 1, "epoch": 2}[defer], q, defer))
-             for r in range(2)]
-    for p in procs:
-        p.start()
-    for p in procs:
-        p.join(180)
-    assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
-    ok, msg, info = q.get(timeout=5)
+    ok, msg, info = run_world(_fusion_worker, 2, lambda r, port, q: (r, 2, port, q, defer),
+                              timeout=180)
     assert ok, msg
     want_fused = {"ag_mm": 0, "ag_pf": 2, "mm_rs": 2} if defer == "epoch" else \
         {"ag_mm": 2, "ag_pf": 0, "mm_rs": 2}
@@ -273,16 +264,7 @@ def _batch_worker(rank, world, port, q):
 
 @pytest.fixture(scope="module")
 def dp_results():
-    ctx = mp.get_context("spawn")
-    q = ctx.Queue()
-    procs = [ctx.Process(target=_batch_worker, args=(r, 2, 29650, q)) for r in range(2)]
-    for p in procs:
-        p.start()
-    results = q.get(timeout=600)
-    for p in procs:
-        p.join(60)
-    assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
-    return results
+    return run_world(_batch_worker, 2, lambda r, port, q: (r, 2, port, q), timeout=600)
 
 
 @pytest.mark.parametrize("mode,opt_kind,bucket", [("ddp", "sgd", 0), ("ddp", "sgd_plain", 0),

@@ -7,7 +7,8 @@ import os
 import pytest
 import torch
 import torch.distributed as dist
-import torch.multiprocessing as mp
+
+from tests._procs import run_world
 
 
 def _worker(rank, world, port, mode, q):
@@ -57,15 +58,7 @@ def _worker(rank, world, port, mode, q):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("mode,port", [("ddp", 29911), ("zero3", 29912)])
-def test_tiny_llama_dp_matches_vanilla(mode, port):
-    ctx = mp.get_context("spawn")
-    q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, mode, q)) for r in range(2)]
-    for p in procs:
-        p.start()
-    for p in procs:
-        p.join(300)
-    assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
-    ok, msg = q.get(timeout=5)
+@pytest.mark.parametrize("mode", ["ddp", "zero3"])
+def test_tiny_llama_dp_matches_vanilla(mode):
+    ok, msg = run_world(_worker, 2, lambda r, port, q: (r, 2, port, mode, q), timeout=300)
     assert ok, msg

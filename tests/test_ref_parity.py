@@ -3,39 +3,37 @@ reference traces, annotates and solves; its lowering (A) and the drop-in
 easydist_b200.lowering.sharding_transform (B) are run on the same plan and inputs over gloo and
 compared with each other and with vanilla PyTorch — tests/ref/auto_worker.py."""
 import os
-import subprocess
 import sys
 
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from tests._procs import run_torchrun  # noqa: E402
 pytestmark = pytest.mark.refonly
 
 
-@pytest.mark.parametrize("mesh,nproc,port,planner,model", [
-    ("2", 2, 29791, "GREEDY", "foo"), ("2x2", 4, 29792, "GREEDY", "foo"),
-    ("2x2", 4, 29793, "REPLICATE", "foo"), ("2x2", 4, 29794, "P2P", "foo"),
-    ("2", 2, 29795, "GREEDY", "gpt"),   # the reference's GPT test model: views, expand, bmm
+@pytest.mark.parametrize("mesh,nproc,planner,model", [
+    ("2", 2, "GREEDY", "foo"), ("2x2", 4, "GREEDY", "foo"),
+    ("2x2", 4, "REPLICATE", "foo"), ("2x2", 4, "P2P", "foo"),
+    ("2", 2, "GREEDY", "gpt"),   # the reference's GPT test model: views, expand, bmm
 ])
-def test_dropin_lowering_equals_reference_lowering(mesh, nproc, port, planner, model):
+def test_dropin_lowering_equals_reference_lowering(mesh, nproc, planner, model):
     if not os.path.isdir("/root/reference/easydist"):
         pytest.skip("reference not present (GPU box)")
     env = dict(os.environ, EDB_TEST_MESH=mesh, OMP_NUM_THREADS="1", EDB_PLANNER=planner,
                EDB_MODEL=model, EDB_SAMEPLAN="1")
-    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
-           f"--nproc-per-node={nproc}", "--master-addr", "127.0.0.1", "--master-port", str(port),
-           os.path.join(ROOT, "tests", "ref", "auto_worker.py")]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=280, cwd=ROOT, env=env)
-    line = next((l for l in r.stdout.splitlines() if l.startswith("AUTO_PARITY")), "")
-    assert r.returncode == 0 and "ok=True" in line, r.stdout[-2000:] + r.stderr[-3000:]
+    rc, out, err = run_torchrun(os.path.join(ROOT, "tests", "ref", "auto_worker.py"), nproc, env,
+                                timeout=280, cwd=ROOT, python=sys.executable)
+    line = next((l for l in out.splitlines() if l.startswith("AUTO_PARITY")), "")
+    assert rc == 0 and "ok=True" in line, out[-2000:] + err[-3000:]
     # same communication structure as the reference's lowering OF THE VERY SAME PLAN (run A solves
     # again and the ILP may return another equal-cost plan, so its histogram is informative only)
     assert "same_plan_equal=True" in line, line
 
 
-@pytest.mark.parametrize("mode,port", [("b200_ddp", 29796), ("b200_zero3", 29797), ("auto", 29798),
-                                       ("b200_auto", 29799), ("auto+localize", 29800)])
-def test_plugin_hook_through_the_reference_decorator(mode, port):
+@pytest.mark.parametrize("mode", ["b200_ddp", "b200_zero3", "auto", "b200_auto", "auto+localize"])
+def test_plugin_hook_through_the_reference_decorator(mode):
     """Hook A of INTEGRATION.md: `easydist_b200.api.register()` adds the modes to the reference's
     registry (`register_parallel_method`, api.py:39-50); the REFERENCE's own `easydist_compile`
     decorator and CompiledFuncWrapper then drive this backend's compiled object (`.graph`,
@@ -52,12 +50,10 @@ def test_plugin_hook_through_the_reference_decorator(mode, port):
     if mode == "b200_auto":
         import tempfile
         env["EDB_PLAN_CACHE_DIR"] = tempfile.mkdtemp(prefix="edb_plan_cache_")
-    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
-           "--master-addr", "127.0.0.1", "--master-port", str(port),
-           os.path.join(ROOT, "tests", "ref", "plugin_worker.py")]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=280, cwd=ROOT, env=env)
-    line = next((l for l in r.stdout.splitlines() if l.startswith("PLUGIN_PARITY")), "")
-    assert r.returncode == 0 and "ok=True" in line, r.stdout[-2000:] + r.stderr[-3000:]
+    rc, out, err = run_torchrun(os.path.join(ROOT, "tests", "ref", "plugin_worker.py"), 2, env,
+                                timeout=280, cwd=ROOT, python=sys.executable)
+    line = next((l for l in out.splitlines() if l.startswith("PLUGIN_PARITY")), "")
+    assert rc == 0 and "ok=True" in line, out[-2000:] + err[-3000:]
     if mode.startswith("b200_"):
         # the object the reference's wrapper drives is THIS backend's executor
         assert "compiled=easydist_b200.compile.EDCompiledFunc" in line, line
