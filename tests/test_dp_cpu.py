@@ -71,7 +71,7 @@ class Wide(torch.nn.Module):
         return self.fc2(torch.nn.functional.gelu(self.fc1(self.norm(x))))
 
 
-def _fusion_worker(rank, world, port, q, defer="0"):
+def _fusion_worker(rank, world, port, q, defer="0", d=256):
     os.environ["OMP_NUM_THREADS"] = "1"
     os.environ["EDB_EPOCH"] = "1" if defer == "epoch" else "0"
     defer = "0" if defer == "epoch" else defer
@@ -85,13 +85,13 @@ def _fusion_worker(rank, world, port, q, defer="0"):
     from tests import gloo_ops
     set_device_mesh(list(range(world)), ["dp"], rank=rank)
     torch.manual_seed(0)
-    model = Wide().bfloat16()
-    ref_model = Wide().bfloat16()
+    model = Wide(d).bfloat16()
+    ref_model = Wide(d).bfloat16()
     ref_model.load_state_dict(model.state_dict())
     opt = make_opt("sgd", model.parameters())
     ref_opt = make_opt("sgd", ref_model.parameters())
     g = torch.Generator().manual_seed(5)
-    batches = [torch.randn(world * 8, 256, generator=g).bfloat16() for _ in range(3)]
+    batches = [torch.randn(world * 8, d, generator=g).bfloat16() for _ in range(3)]
     compiled = api._compile_dp(train_step, "zero3", "fake", (batches[0][rank * 8:(rank + 1) * 8],
                                                             model, opt), {}, ops=gloo_ops,
                                native=False, bucket_numel=2048, fuse=True,
@@ -121,14 +121,15 @@ def _fusion_worker(rank, world, port, q, defer="0"):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("defer", ["0", "1", "epoch"])
-def test_fusion_rewrite_on_cpu(defer):
+@pytest.mark.parametrize("defer,world,d", [("0", 2, 256), ("1", 2, 256), ("epoch", 2, 256),
+                                           ("epoch", 4, 512)])
+def test_fusion_rewrite_on_cpu(defer, world, d):
     """The AG+GEMM / GEMM+RS peephole (lowering.fuse_collective_gemms) rewrites the zero3 graph of
     a 2-layer MLP: both weights' all-gathers fuse into their forward GEMMs and both weight
     gradients' reduce-scatters fuse into the wgrad GEMMs (defer=1: push-only GEMMs + one rs_finish
     in front of the optimizer); training still matches vanilla."""
-    ok, msg, info = run_world(_fusion_worker, 2, lambda r, port, q: (r, 2, port, q, defer),
-                              timeout=180)
+    ok, msg, info = run_world(_fusion_worker, world,
+                              lambda r, port, q: (r, world, port, q, defer, d), timeout=180)
     assert ok, msg
     want_fused = {"ag_mm": 0, "ag_pf": 2, "mm_rs": 2} if defer == "epoch" else \
         {"ag_mm": 2, "ag_pf": 0, "mm_rs": 2}
