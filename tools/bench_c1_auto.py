@@ -63,8 +63,11 @@ def run(args):
     # vs vanilla PyTorch on the same batches (the reference's comparator, rtol 1e-4 / atol 1e-5)
     from easydist_b200 import reshard
     from tests.test_auto_bundle_cpu import run_c1_bundle
-    if custom or tdt != torch.float32:
-        ok, msg = True, "parity leg only exists for the fp32 config-1 bundles"
+    if tdt != torch.float32:
+        ok, msg = True, "parity leg runs in fp32 only (bf16: tools/validate_bundle.py --dtype bf16)"
+    elif custom:
+        ok, msg, _ = run_c1_bundle(rank, world, reshard, True, "cuda", steps=3, tag=tag,
+                                   bundle_file=custom, gpt=(depth, dim, heads), batch=gbatch, seq=seq)
     else:
         ok, msg, _ = run_c1_bundle(rank, world, reshard, True, "cuda", steps=3, tag=tag)
     flag = torch.tensor([0.0 if ok else 1.0], device="cuda")
