@@ -112,6 +112,65 @@ def run_cases(rank, world, group, tag=""):
     return n_ok
 
 
+def run_randn_cases(rank, world, group, ops=None, device="cuda"):
+    """SURVEY.md section 8(d) config 5's second input class: `randn` with seed 1234 + rank (the
+    integer-valued batteries above make reductions exact; here they round).  Data movement stays
+    bit-exact; fp32 reductions within 1e-5 of the oracle relative to the largest element (both sum
+    in fp32, the kernel in rank order); bf16 reductions within one bf16 ulp of the fp32 sum at the
+    largest element (fp32 accumulation, one rounding).  `ops` defaults to the libedb callables; the
+    CPU suite passes the gloo stand-ins to check this checker."""
+    ops = ops or reshard
+    n_ok = 0
+
+    def inputs(shape, dtype):
+        out = []
+        for r in range(world):
+            g = torch.Generator().manual_seed(1234 + r)
+            x = torch.randn(shape, generator=g)
+            if dtype == "bfloat16":
+                x = x.bfloat16().float()   # the values the kernel sees
+            out.append(x.numpy())
+        return out
+
+    def dev(x, dtype):
+        return torch.from_numpy(np.ascontiguousarray(x)).to(device=device, dtype=TORCH_DT[dtype])
+
+    def close(got, want, dtype, what):
+        g = got.float().cpu().numpy().astype(np.float64)
+        w = np.asarray(want, dtype=np.float64)
+        assert g.shape == w.shape, f"{what}: shape {g.shape} vs {w.shape}"
+        top = float(np.abs(w).max()) if w.size else 0.0
+        tol = 1e-5 * top if dtype == "float32" else 2.0 ** (np.floor(np.log2(max(top, 1e-30))) - 7)
+        err = float(np.abs(g - w).max()) if w.size else 0.0
+        if err > tol:
+            raise AssertionError(f"{what}: max |d| {err:.3e} > {tol:.3e}")
+
+    for dtype in ("float32", "bfloat16"):
+        for shape, dim in [((64, 1024), 0), ((64, 1024), 1), ((2, 16, 128, 32), 2)]:
+            xs = inputs(shape, dtype)
+            got = ops.all_gather_start(dev(xs[rank], dtype), dim, group)
+            check_equal(got, O.all_gather(xs, dim)[rank], f"randn ag {shape} {dim} {dtype}")
+            n_ok += 1
+        for shape, g_, s_ in [((2, 128, 16 * world), 0, 2), ((64 * world, 64), 1, 0)]:
+            xs = inputs(shape, dtype)
+            got = ops.all_to_all_start(dev(xs[rank], dtype), g_, s_, world, rank, group)
+            check_equal(got, O.all_to_all(xs, g_, s_)[rank], f"randn a2a {shape} {dtype}")
+            n_ok += 1
+        for shape, dim in [((64 * world, 256), 0), ((16, 8 * world, 32), 1), ((1, 1024 * world), 1)]:
+            xs = inputs(shape, dtype)
+            got = ops.reduce_scatter_start(dev(xs[rank], dtype), "sum", dim, group)
+            close(got, O.reduce_scatter([x.astype(np.float32) for x in xs], "sum", dim)[rank], dtype,
+                  f"randn rs {shape} {dim} {dtype}")
+            n_ok += 1
+        for shape in [(1024,), (300, 1000), (1 << 20,)]:
+            xs = inputs(shape, dtype)
+            got = ops.all_reduce_start(dev(xs[rank], dtype), "sum", group)
+            close(got, O.all_reduce([x.astype(np.float32) for x in xs], "sum")[rank], dtype,
+                  f"randn ar {shape} {dtype}")
+            n_ok += 1
+    return n_ok
+
+
 def run_push_cases(rank, world, group, passes=4, big=True):
     """The push-protocol collectives (edb_*_push: static per-node buffers, one flag per peer, an
     epoch barrier between reuses of a buffer) bit for bit against the oracle: every op, the LL
@@ -1035,6 +1094,7 @@ def main():
         return
     n = run_cases(rank, world, group)
     n += run_cases(rank, world, group, tag="b")  # second pass: epochs keep counting
+    n += run_randn_cases(rank, world, group)
     n += run_p2p(rank, world, group)
     n += run_graph(rank, world, group)
     n += run_graph(rank, world, group, rows=4)
