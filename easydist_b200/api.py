@@ -134,12 +134,15 @@ def _finish(gm, params, buffers, named_states, args, kwargs, ops, native, io=Non
             params[pname] = home
         lowering.propagate_local_meta(gm, _flat_inputs(params, buffers, named_states, args,
                                                        kwargs))
-    elif native and fuse and auto_io is not None and ranks is not None and len(ranks) > 1 and \
-            os.environ.get("EDB_EPOCH", "1") == "1" and os.environ.get("EDB_AG_PREFETCH", "1") == "1":
-        # auto-SPMD plan on a 1-D mesh: dim-0 gathers of parameter shards become prefetches that
-        # ride on the step's GEMMs, one gather per parameter per step (epoch protocol)
-        from .runtime import get_runtime
-        rt = get_runtime()
+    elif (native or fuse_rt is not None) and fuse and auto_io is not None and ranks is not None \
+            and len(ranks) > 1 and os.environ.get("EDB_EPOCH", "1") == "1" \
+            and os.environ.get("EDB_AG_PREFETCH", "1") == "1":
+        # auto-SPMD plan on a 1-D mesh: gathers of parameter shards become prefetches that ride on
+        # the step's GEMMs, one gather per parameter per step (epoch protocol)
+        if fuse_rt is None:
+            from .runtime import get_runtime
+            fuse_rt = get_runtime()
+        rt = fuse_rt
         rehomed, n_pf = lowering.prefetch_param_gathers(gm, auto_io, rt, ranks, ops, my_index=my_index)
         if rehomed:
             lowering.insert_epoch_barriers(gm, ranks, ops)
@@ -247,7 +250,7 @@ def _compile_dp(func, parallel_mode, tracing_mode, args, kwargs, *, ops=_default
 
 
 def _lower_auto(gm, plan, state_io_map, params, buffers, named_states, args, kwargs, *, ops, native,
-                planner, mesh):
+                planner, mesh, fuse_rt=None):
     """Shared tail of the auto path: lower with the plan, shard state and inputs locally, finish."""
     n_p, n_b = len(params), len(buffers)
     flat_states, spec = pytree.tree_flatten(named_states)
@@ -290,7 +293,7 @@ def _lower_auto(gm, plan, state_io_map, params, buffers, named_states, args, kwa
         auto_io = _ParamIO(param_ph, list(params.keys()))
         ranks1d, my_index = mesh.ranks_along(0), mesh.get_coordinate()[0]
     info = _finish(gm, params, buffers, named_states, largs, lkwargs, ops, native, auto_io=auto_io,
-                   ranks=ranks1d, my_index=my_index)
+                   ranks=ranks1d, my_index=my_index, fuse_rt=fuse_rt)
     info.update(mode="auto", mesh=mesh.shape)
     if native:
         from .runtime import get_runtime, is_initialized
@@ -322,7 +325,7 @@ def _compile_auto(func, tracing_mode, args, kwargs, *, plan=None, ops=_default_o
 
 
 def compile_from_bundle(bundle_text, args, kwargs, *, ops=_default_ops, native=True,
-                        planner="GREEDY"):
+                        planner="GREEDY", fuse_rt=None):
     """Lower and run a graph + plan recorded by graph_io.dump_bundle (e.g. solved by the
     reference on another machine).  `args` must contain the nn.Module and Optimizer the graph was
     traced with (their parameters/optimizer state provide the initial values)."""
@@ -344,7 +347,7 @@ def compile_from_bundle(bundle_text, args, kwargs, *, ops=_default_ops, native=T
 
     io_map = {_Named(a): _Named(b) for a, b in state_io}
     return _lower_auto(gm, plan, io_map, params, buffers, named_states, args, kwargs, ops=ops,
-                       native=native, planner=planner, mesh=mesh)
+                       native=native, planner=planner, mesh=mesh, fuse_rt=fuse_rt)
 
 
 LAST_AUTO_SOURCE = [None]  # "solved" | "cache": where the last b200_auto compilation got its plan

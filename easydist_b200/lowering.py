@@ -1264,28 +1264,38 @@ def prefetch_param_gathers(gm, io, rt, ranks, ops=_default_ops, my_index=None):
     n = len(ranks)
     order = {nd: i for i, nd in enumerate(graph.nodes)}
     uses = {}
+    dim1_ok = os.environ.get("EDB_AG_PREFETCH_DIM1", "1") == "1"
     for ag_s in [x for x in graph.nodes if x.op == "call_function" and x.target is ops.all_gather_start]:
-        ph, transposed = ag_s.args[0], False
-        if isinstance(ph, Node) and ph.op == "call_function" and ph.target == aten.t.default and \
-                isinstance(ph.args[0], Node) and ph.args[0].op == "placeholder":
-            # all_gather(t(W), 1) == t(all_gather(W, 0)): auto-SPMD plans gather the transposed
-            # weight of a Linear right in front of its GEMM
-            ph, transposed = ph.args[0], True
+        # all_gather(t(W), 1) == t(all_gather(W, 0)): auto-SPMD plans gather the transposed weight
+        # of a Linear right in front of its GEMM (and t(t(W)) in front of the data-gradient GEMM)
+        ph, n_t = ag_s.args[0], 0
+        while isinstance(ph, Node) and ph.op == "call_function" and ph.target == aten.t.default and \
+                isinstance(ph.args[0], Node):
+            ph, n_t = ph.args[0], n_t + 1
+        transposed = bool(n_t % 2)
         if not (isinstance(ph, Node) and ph.op == "placeholder" and ph in io.param_ph):
             continue
         val = ph.meta.get("val")
         if not isinstance(val, torch.Tensor) or (val.numel() * val.element_size()) % 16 or val.numel() == 0:
             continue
-        want_dim = 1 if transposed else 0
-        if transposed and val.dim() != 2:
+        if n_t and val.dim() != 2:
             continue
-        if ag_s.args[1] not in (want_dim, want_dim - val.dim()) or list(ag_s.args[2]) != list(ranks) \
+        d = ag_s.args[1]
+        if not isinstance(d, int):
+            continue
+        d = d + val.dim() if d < 0 else d
+        wdim = 1 - d if transposed else d      # the gather dim in W's own coordinates
+        if wdim == 1 and not (val.dim() == 2 and dim1_ok):
+            continue   # weights the plan shards along dim 1: see the rewrite below
+        if wdim not in (0, 1) or list(ag_s.args[2]) != list(ranks) \
                 or ag_s.kwargs or len(ag_s.users) != 1 or not val.is_contiguous():
             continue
         ag_e = next(iter(ag_s.users))
         if ag_e.target is not ops.all_gather_end:
             continue
-        uses.setdefault(ph, []).append((ag_s, ag_e, transposed))
+        uses.setdefault(ph, []).append((ag_s, ag_e, transposed, wdim))
+    # one sharding dim per parameter (anything else is not a plain shard gather: leave it alone)
+    uses = {ph: lst for ph, lst in uses.items() if len({u[3] for u in lst}) == 1}
     if not uses:
         return {}, 0
     rehomed, bufs = {}, {}
@@ -1302,12 +1312,20 @@ def prefetch_param_gathers(gm, io, rt, ranks, ops=_default_ops, my_index=None):
     for ph, lst in uses.items():
         shard, full, nbytes = bufs[ph]
         pv = ph.meta["val"]
-        for ag_s, ag_e, transposed in lst:
+        for ag_s, ag_e, transposed, wdim in lst:
             with graph.inserting_before(ag_s):
                 g = graph.call_function(ops.gathered, args=(ph, list(ranks)),
                                         kwargs={"_buf": (shard.offset, full.offset)})
                 res = g
-                if pv.dim() > 1:  # flat concat of dim-0 shards == the dim-0 all-gather, reshaped
+                if wdim == 1:
+                    # shards [R, C/n] of a weight sharded along dim 1: the buffer holds them one
+                    # after the other ([n, R, C/n]); the dim-1 concatenation is one local strided
+                    # copy instead of a collective in front of the use
+                    r_, c_ = pv.shape
+                    res = graph.call_function(aten.view.default, args=(g, [n, r_, c_]))
+                    res = graph.call_function(aten.permute.default, args=(res, [1, 0, 2]))
+                    res = graph.call_function(aten.reshape.default, args=(res, [r_, n * c_]))
+                elif pv.dim() > 1:  # flat concat of dim-0 shards == the dim-0 all-gather, reshaped
                     res = graph.call_function(aten.view.default,
                                               args=(g, [n * pv.shape[0]] + list(pv.shape[1:])))
                 if transposed:
@@ -1317,7 +1335,7 @@ def prefetch_param_gathers(gm, io, rt, ranks, ops=_default_ops, my_index=None):
             graph.erase_node(ag_e)
             graph.erase_node(ag_s)
             gathered_nodes.setdefault(ph, []).append(g)
-    for nd in list(graph.nodes):  # t(W) nodes whose only reader was the all-gather
+    for nd in reversed(list(graph.nodes)):  # t(W) / t(t(W)) nodes whose only reader was the all-gather
         if nd.op == "call_function" and nd.target == aten.t.default and not nd.users:
             graph.erase_node(nd)
     # ---- schedule ----------------------------------------------------------------------------

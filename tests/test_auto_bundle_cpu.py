@@ -160,7 +160,11 @@ def run_c1_bundle(rank, world, ops, native, device, steps=2, tag=None, bundle_fi
         batch = 8 if tag == "8" else 4            # the (8,) plan was solved for a batch of 8
     batches = [torch.randn(batch, seq, gpt[1], generator=g).to(device=device, dtype=dtype)
                for _ in range(steps)]
-    compiled = api.compile_from_bundle(bundle, (batches[0], model, opt), {}, ops=ops, native=native)
+    # EDB_TEST_AUTO_PF=1 (CPU): the parameter-prefetch rewrite of the product path too, with the
+    # stand-in runtime of tests/gloo_ops.py (offsets only; `gathered` is a real gloo all-gather)
+    fake_rt = ops.FakeSymmRuntime() if (not native and os.environ.get("EDB_TEST_AUTO_PF") == "1") else None
+    compiled = api.compile_from_bundle(bundle, (batches[0], model, opt), {}, ops=ops, native=native,
+                                       fuse_rt=fake_rt)
     ok, msg = True, ""
     for b in batches:
         out = compiled(b, model, opt)
@@ -211,9 +215,10 @@ def run_c1_bundle(rank, world, ops, native, device, steps=2, tag=None, bundle_fi
     return ok, msg, compiled.info["comm_nodes"]
 
 
-def _c1_worker(rank, world, port, q, localize="0"):
+def _c1_worker(rank, world, port, q, localize="0", auto_pf="0"):
     os.environ["OMP_NUM_THREADS"] = "2"
     os.environ["EDB_LOCALIZE_OPT"] = localize
+    os.environ["EDB_TEST_AUTO_PF"] = auto_pf
     torch.set_num_threads(2)
     dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank,
                             world_size=world)
@@ -247,6 +252,19 @@ def test_config1_optimizer_runs_on_shards_when_localized():
     assert ok, msg
     assert hist.get("all_gather_start", 0) <= 429 - 280, hist
     assert hist.get("scatter_wrapper", 0) <= 197 - 170, hist
+
+
+def test_config1_parameter_gathers_become_prefetches():
+    """The product structure executed on CPU: optimizer on shards AND the parameter-prefetch rewrite
+    (lowering.prefetch_param_gathers with the stand-in runtime; `gathered` = a real gloo all-gather of
+    the flat shard).  Weights the plan shards along dim 0 are read as views of their gathered buffer;
+    weights it shards along dim 1 (gathers of t(W_shard) in front of the GEMMs) through one local
+    permuted copy of the buffer — 68 of the 125 all-gathers become buffer reads, results still equal
+    vanilla: outputs, every parameter, every momentum buffer."""
+    ok, msg, hist = run_world(_c1_worker, 2, lambda r, port, q: (r, 2, port, q, "1", "1"), timeout=600)
+    assert ok, msg
+    assert hist.get("gathered") == 68 and hist.get("all_gather_start") == 57, hist
+    assert hist.get("ag_prefetch") == 1 and hist.get("epoch_barrier") == 2, hist
 
 
 @pytest.mark.parametrize("tag,mesh_shape,rank,want", [
