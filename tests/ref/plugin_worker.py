@@ -60,9 +60,16 @@ def main():
         gloo_ops.init_groups(np.arange(world))
 
     torch.manual_seed(42)
-    model0 = Foo()
     g = torch.Generator().manual_seed(7)
-    batches = [torch.randn(world * 4, 32, generator=g) for _ in range(3)]
+    if os.environ.get("EDB_PLUGIN_MODEL", "foo") == "gpt":
+        # the reference's own test model (TEST_GPT, tests/test_torch/test_utils.py:55-68): attention
+        # with views / expand / bmm, GeLU MLPs, LayerNorms
+        from benchmark.torch.model.gpt import GPT
+        model0 = GPT(depth=2, dim=64, num_heads=4)
+        batches = [torch.randn(world * 2, 32, 64, generator=g) for _ in range(3)]
+    else:
+        model0 = Foo()
+        batches = [torch.randn(world * 4, 32, generator=g) for _ in range(3)]
     model = copy.deepcopy(model0)
     opt = torch.optim.SGD(model.parameters(), lr=0.1, momentum=0.9, foreach=True)
     step = easydist_compile(train_step, mode, "fake", cuda_graph=False)   # the REFERENCE's decorator

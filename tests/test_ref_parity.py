@@ -32,7 +32,8 @@ def test_dropin_lowering_equals_reference_lowering(mesh, nproc, planner, model):
     assert "same_plan_equal=True" in line, line
 
 
-@pytest.mark.parametrize("mode", ["b200_ddp", "b200_zero3", "auto", "b200_auto", "auto+localize"])
+@pytest.mark.parametrize("mode", ["b200_ddp", "b200_zero3", "auto", "b200_auto", "auto+localize",
+                                  "b200_auto+gpt"])
 def test_plugin_hook_through_the_reference_decorator(mode):
     """Hook A of INTEGRATION.md: `easydist_b200.api.register()` adds the modes to the reference's
     registry (`register_parallel_method`, api.py:39-50); the REFERENCE's own `easydist_compile`
@@ -47,7 +48,13 @@ def test_plugin_hook_through_the_reference_decorator(mode):
     if mode == "auto+localize":
         # Hook B with the optimizer localized: the REFERENCE's executor runs the rewritten graph
         env.update(EDB_PLUGIN_MODE="auto", EDB_LOCALIZE_OPT="1")
-    if mode == "b200_auto":
+    cached = mode == "b200_auto"
+    if mode == "b200_auto+gpt":
+        # Hook C on the reference's GPT test model, with the product structure of the auto path
+        # (optimizer on shards) executed by this backend's EDCompiledFunc
+        mode = "b200_auto"
+        env.update(EDB_PLUGIN_MODE="b200_auto", EDB_PLUGIN_MODEL="gpt", EDB_LOCALIZE_OPT="1")
+    elif mode == "b200_auto":
         import tempfile
         env["EDB_PLAN_CACHE_DIR"] = tempfile.mkdtemp(prefix="edb_plan_cache_")
     rc, out, err = run_torchrun(os.path.join(ROOT, "tests", "ref", "plugin_worker.py"), 2, env,
@@ -57,6 +64,6 @@ def test_plugin_hook_through_the_reference_decorator(mode):
     if mode.startswith("b200_"):
         # the object the reference's wrapper drives is THIS backend's executor
         assert "compiled=easydist_b200.compile.EDCompiledFunc" in line, line
-    if mode == "b200_auto":
+    if cached:
         # ... and a second compilation took graph + plan from the plan cache
         assert "plan_source=['solved', 'cache']" in line, line
