@@ -551,7 +551,7 @@ def register(reference_api=None, reference_compile_auto=None, **compile_kwargs):
         from . import graph_io
         from .device_mesh import set_device_mesh
         mesh = set_device_mesh(ref_mesh("spmd"), rank=torch.distributed.get_rank())
-        kw = {k: v for k, v in compile_kwargs.items() if k in ("ops", "native", "planner")}
+        kw = {k: v for k, v in compile_kwargs.items() if k in ("ops", "native", "planner", "fuse_rt")}
         # plan cache (the reference caches the solver's output per input signature,
         # compile_auto.py:97-106,181-184): here the whole captured bundle — traced graph + plan — is
         # cached, so a hit skips tracing, annotation, the ILP and the RPC plan broadcast.  Rank 0

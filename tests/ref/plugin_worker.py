@@ -52,7 +52,11 @@ def main():
 
     from easydist_b200 import api
     from tests import gloo_ops
-    api.register(ops=gloo_ops, native=False)
+    extra = {}
+    if os.environ.get("EDB_TEST_AUTO_PF") == "1":
+        # Hook C with the parameter-prefetch rewrite of the product path too (stand-in runtime)
+        extra["fuse_rt"] = gloo_ops.FakeSymmRuntime()
+    api.register(ops=gloo_ops, native=False, **extra)
     if mode in ("auto", "b200_auto"):
         # Hook B: register() also rebinds compile_auto.sharding_transform; the reference's auto
         # path (annotation, solver, executor) then runs on this backend's lowering
@@ -133,7 +137,8 @@ def main():
             msgs.append(f"plan cache not used: reference compiles={calls['n']} sources={source}")
     if rank == 0:
         print(f"PLUGIN_PARITY ok={ok} mode={mode} wrapper={type(step).__module__}.{type(step).__name__} "
-              f"compiled={type(cf).__module__}.{type(cf).__name__} plan_source={source} {msgs}",
+              f"compiled={type(cf).__module__}.{type(cf).__name__} plan_source={source} "
+              f"fused={getattr(cf, 'info', {}).get('fused')} {msgs}",
               flush=True)
     dist.barrier()
     dist.destroy_process_group()

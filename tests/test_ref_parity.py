@@ -51,9 +51,11 @@ def test_plugin_hook_through_the_reference_decorator(mode):
     cached = mode == "b200_auto"
     if mode == "b200_auto+gpt":
         # Hook C on the reference's GPT test model, with the product structure of the auto path
-        # (optimizer on shards) executed by this backend's EDCompiledFunc
+        # (optimizer on shards, parameter gathers rewritten to prefetched-buffer reads) executed by
+        # this backend's EDCompiledFunc
         mode = "b200_auto"
-        env.update(EDB_PLUGIN_MODE="b200_auto", EDB_PLUGIN_MODEL="gpt", EDB_LOCALIZE_OPT="1")
+        env.update(EDB_PLUGIN_MODE="b200_auto", EDB_PLUGIN_MODEL="gpt", EDB_LOCALIZE_OPT="1",
+                   EDB_TEST_AUTO_PF="1")
     elif mode == "b200_auto":
         import tempfile
         env["EDB_PLAN_CACHE_DIR"] = tempfile.mkdtemp(prefix="edb_plan_cache_")
@@ -64,6 +66,8 @@ def test_plugin_hook_through_the_reference_decorator(mode):
     if mode.startswith("b200_"):
         # the object the reference's wrapper drives is THIS backend's executor
         assert "compiled=easydist_b200.compile.EDCompiledFunc" in line, line
+    if env.get("EDB_TEST_AUTO_PF") == "1":
+        assert "'ag_pf': 0" not in line and "'ag_pf'" in line, line   # the prefetch rewrite applied
     if cached:
         # ... and a second compilation took graph + plan from the plan cache
         assert "plan_source=['solved', 'cache']" in line, line
