@@ -92,7 +92,12 @@ def _finish(gm, params, buffers, named_states, args, kwargs, ops, native, io=Non
         # tests run without it; the product path has it on)
         info["localized_foreach"] = lowering.localize_foreach(gm, ops, my_rank=get_device_mesh().rank)
         lowering.propagate_local_meta(gm, flat)
-    if os.environ.get("EDB_BUCKET_COMM", "0") == "1":
+    # auto-SPMD plan on a 1-D mesh: gathers of parameter shards become prefetches (below)
+    auto_pf = (native or fuse_rt is not None) and fuse and auto_io is not None and ranks is not None \
+        and len(ranks) > 1 and os.environ.get("EDB_EPOCH", "1") == "1" \
+        and os.environ.get("EDB_AG_PREFETCH", "1") == "1"
+    bucket = os.environ.get("EDB_BUCKET_COMM", "0") == "1"
+    if bucket and not auto_pf:
         # opt-in: changes the communication structure the reference's lowering would produce
         info["bucketed"] = lowering.bucket_small_comm(gm, ops)
         lowering.propagate_local_meta(gm, flat)
@@ -134,11 +139,9 @@ def _finish(gm, params, buffers, named_states, args, kwargs, ops, native, io=Non
             params[pname] = home
         lowering.propagate_local_meta(gm, _flat_inputs(params, buffers, named_states, args,
                                                        kwargs))
-    elif (native or fuse_rt is not None) and fuse and auto_io is not None and ranks is not None \
-            and len(ranks) > 1 and os.environ.get("EDB_EPOCH", "1") == "1" \
-            and os.environ.get("EDB_AG_PREFETCH", "1") == "1":
-        # auto-SPMD plan on a 1-D mesh: gathers of parameter shards become prefetches that ride on
-        # the step's GEMMs, one gather per parameter per step (epoch protocol)
+    elif auto_pf:
+        # gathers of parameter shards become prefetches that ride on the step's GEMMs, one gather
+        # per parameter per step (epoch protocol)
         if fuse_rt is None:
             from .runtime import get_runtime
             fuse_rt = get_runtime()
@@ -154,6 +157,11 @@ def _finish(gm, params, buffers, named_states, args, kwargs, ops, native, io=Non
                 params[name_of[ph_name]] = home
             lowering.propagate_local_meta(gm, _flat_inputs(params, buffers, named_states, args, kwargs))
         info["fused"] = {"ag_mm": 0, "ag_pf": n_pf, "mm_rs": 0}
+        if bucket:
+            # ... and only what is still a collective after that is bucketed (a prefetched parameter
+            # needs no collective at all: bucketing its gather first would keep one)
+            info["bucketed"] = lowering.bucket_small_comm(gm, ops)
+            lowering.propagate_local_meta(gm, _flat_inputs(params, buffers, named_states, args, kwargs))
     info["comm_nodes"] = lowering.count_nodes(gm, ops)
     info["reinplaced_updates"] = lowering.reinplace_optimizer_updates(gm)
     if native:

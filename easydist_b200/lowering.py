@@ -499,7 +499,8 @@ def transform_fsdp(gm, io, ranks, my_index, shard_param, ops=_default_ops, bucke
 
 
 def bucket_small_comm(gm, ops=_default_ops, max_bytes=1 << 20, max_bucket_bytes=32 << 20):
-    """Bucket small all-reduces and dim-0 all-gathers of the lowered graph (any parallel mode).
+    """Bucket small all-reduces, dim-0 all-gathers and reduce-scatters (any scatter dim) of the
+    lowered graph (any parallel mode).
 
     Auto-SPMD plans reshard many tiny tensors one collective each (16 all-reduces
     of 4 KB and 108 all-gathers of 2 KB per step in the reference's GPT example); the reference
@@ -516,7 +517,8 @@ def bucket_small_comm(gm, ops=_default_ops, max_bytes=1 << 20, max_bucket_bytes=
     order = {nd: i for i, nd in enumerate(graph.nodes)}
     cands = {}
     for st in graph.nodes:
-        if st.op != "call_function" or st.target not in (ops.all_reduce_start, ops.all_gather_start):
+        if st.op != "call_function" or st.target not in (ops.all_reduce_start, ops.all_gather_start,
+                                                         ops.reduce_scatter_start):
             continue
         x = st.args[0]
         if not isinstance(x, Node) or len(st.users) != 1 or st.kwargs:
@@ -531,6 +533,14 @@ def bucket_small_comm(gm, ops=_default_ops, max_bytes=1 << 20, max_bucket_bytes=
             if end.target is not ops.all_reduce_end:
                 continue
             key = ("all_reduce", st.args[1], tuple(st.args[2]), val.dtype)
+        elif st.target is ops.reduce_scatter_start:
+            d = st.args[2]
+            if end.target is not ops.reduce_scatter_end or not isinstance(d, int) or val.dim() == 0:
+                continue
+            d = d + val.dim() if d < 0 else d
+            if not 0 <= d < val.dim() or val.shape[d] % len(st.args[3]):
+                continue
+            key = ("reduce_scatter", st.args[1], tuple(st.args[3]), val.dtype)
         else:
             if end.target is not ops.all_gather_end or st.args[1] != 0 or val.dim() == 0:
                 continue
@@ -540,7 +550,7 @@ def bucket_small_comm(gm, ops=_default_ops, max_bytes=1 << 20, max_bucket_bytes=
     def first_use(items):
         return min((u for _, end, _, _ in items for u in end.users), key=lambda u: order[u])
 
-    done = {"all_reduce": 0, "all_gather": 0}
+    done = {"all_reduce": 0, "all_gather": 0, "reduce_scatter": 0}
     for key, items in cands.items():
         items.sort(key=lambda it: order[it[2]])
         runs, cur, cur_bytes = [], [], 0
@@ -556,6 +566,40 @@ def bucket_small_comm(gm, ops=_default_ops, max_bytes=1 << 20, max_bucket_bytes=
         n = len(group)
         for run in runs:
             if len(run) < 2:
+                continue
+            if kind == "reduce_scatter":
+                # x_i with its scatter dim in front, as [n, k_i]: row p is what member p keeps.
+                # cat over i -> [n, K] -> ONE reduce-scatter along dim 0 -> [1, K] -> column block i
+                # back into the shape (and dim order) of the single result
+                with graph.inserting_before(first_use(run)):
+                    mats, metas = [], []
+                    for st, _, x, v in run:
+                        d = st.args[2] + v.dim() if st.args[2] < 0 else st.args[2]
+                        perm = [d] + [i for i in range(v.dim()) if i != d]
+                        y = x if d == 0 else graph.call_function(aten.permute.default, args=(x, perm))
+                        mats.append(graph.call_function(aten.reshape.default, args=(y, [n, v.numel() // n])))
+                        metas.append((d, perm))
+                    cat = graph.call_function(aten.cat.default, args=(mats, 1))
+                    s_ = graph.call_function(ops.reduce_scatter_start, args=(cat, red, 0, list(group)))
+                    e_ = graph.call_function(ops.reduce_scatter_end, args=(s_, red, 0, list(group)))
+                    off = 0
+                    for (st, end, x, v), (d, perm) in zip(run, metas):
+                        k = v.numel() // n
+                        sl = graph.call_function(aten.slice.Tensor, args=(e_, 1, off, off + k))
+                        front = [v.shape[d] // n] + [v.shape[i] for i in perm[1:]]
+                        piece = graph.call_function(aten.reshape.default, args=(sl, front))
+                        if d != 0:
+                            inv = [perm.index(i) for i in range(v.dim())]
+                            piece = graph.call_function(aten.permute.default, args=(piece, inv))
+                            piece = graph.call_function(aten.clone.default, args=(piece,),
+                                                        kwargs={"memory_format": torch.contiguous_format})
+                        piece.meta = dict(end.meta)
+                        end.replace_all_uses_with(piece)
+                        off += k
+                for st, end, _, _ in run:
+                    graph.erase_node(end)
+                    graph.erase_node(st)
+                done[kind] += 1
                 continue
             with graph.inserting_before(first_use(run)):
                 flats = [graph.call_function(aten.flatten.using_ints, args=(x,)) for _, _, x, _ in run]
@@ -586,7 +630,7 @@ def bucket_small_comm(gm, ops=_default_ops, max_bytes=1 << 20, max_bucket_bytes=
                 graph.erase_node(end)
                 graph.erase_node(st)
             done[kind] += 1
-    if done["all_reduce"] or done["all_gather"]:
+    if any(done.values()):
         graph.lint()
         gm.recompile()
     return done
