@@ -57,11 +57,11 @@ def run_world(target, world, make_args, timeout=600):
                 p.join(5)
 
 
-def run_torchrun(script, nproc, env, timeout, cwd, python):
+def run_torchrun(script, nproc, env, timeout, cwd, python, args=()):
     """`python -m torch.distributed.run` on a free port in its own process group; on timeout the
     whole group (agent + workers) is killed, nothing is left behind.  -> (returncode, stdout, stderr)"""
     cmd = [python, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}",
-           "--master-addr", "127.0.0.1", "--master-port", str(free_port()), script]
+           "--master-addr", "127.0.0.1", "--master-port", str(free_port()), script, *args]
     proc = subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, cwd=cwd,
                             env=env, start_new_session=True)
     try:
